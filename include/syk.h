@@ -1,0 +1,169 @@
+/*
+ * syk.h -- C ABI of libsyk.so: B200 (sm_100a) kernels for SyConn's chunked label-volume extraction path.
+ *
+ * Every entry point replaces one function of the reference's two Cython extension modules (the reference's
+ * plugin boundary for this path) or one step of its Python merge logic.  Citations are file:line under the
+ * reference repository (StructuralNeurobiologyLab/SyConn).
+ *
+ * Conventions
+ *   - All functions return 0 on success, a negative SYK_E* code otherwise; syk_last_error() gives the
+ *     thread-local message.  Nothing falls back to the CPU: without a usable CUDA device every compute entry
+ *     point fails with SYK_ENODEV.
+ *   - Plain pointers and sizes only.  "dev" pointers are device memory (e.g. torch.Tensor.data_ptr()),
+ *     "host" pointers are host memory.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - Label volumes are addressed as base[x*strides[0] + y*strides[1] + z*strides[2]], strides in ELEMENTS,
+ *     elem_bytes is 4 (uint32) or 8 (uint64): any NumPy view of a dense block (e.g. ZYX memory seen as XYZ,
+ *     syconn/proc/sd_proc.py:629,641) is passed as is.  Results are always in the LOGICAL (x,y,z) order of
+ *     the view, exactly like the reference's typed memoryviews.
+ *   - Device-pointer functions are asynchronous on `stream`; *_host functions are synchronous (one call =
+ *     one chunk, like the reference's `def` functions that hold the GIL for the whole call).
+ */
+#ifndef SYK_H
+#define SYK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SYK_VERSION 100
+
+#define SYK_OK 0
+#define SYK_EINVAL (-1)    /* bad argument (even stencil, shape mismatch, bad dtype size ...) */
+#define SYK_ECUDA (-2)     /* CUDA runtime error, see syk_last_error() */
+#define SYK_ENODEV (-3)    /* no CUDA device: there is no CPU fallback */
+#define SYK_EOVERFLOW (-4) /* a hash table ran out of slots: retry with a larger capacity */
+#define SYK_ENOMEM (-5)
+
+/* Per-object record (64 bytes).  Array-level form of the reference's three dicts
+ * rep_coords / bounding_box / sizes (syconn/extraction/find_object_properties_C.pyx:24-49) and the unit
+ * that is exchanged between GPUs and merged (syconn/proc/sd_proc.py:1248-1273). */
+typedef struct syk_record {
+    uint64_t id;        /* object id (never 0) */
+    uint64_t count;     /* voxel count ("size"; the reference's C int, here 64 bit) */
+    uint64_t rep_key;   /* (chunk_seq << 40) | (2^40-1 - linear index (x*Sy+y)*Sz+z inside that chunk's call);
+                           max over rep_key == "first voxel in scan order of the LAST chunk holding the id"
+                           (find_object_properties_C.pyx:48 within a chunk, sd_proc.py:1261 across chunks) */
+    int32_t bb_min[3];  /* global coordinates (origin added), inclusive */
+    int32_t bb_max[3];  /* exclusive (max+1), as find_object_properties_C.pyx:39-41 */
+    int32_t rep[3];     /* decoded global rep_coord; filled by syk_table_export / syk_records_decode_rep */
+    uint32_t chunk_seq; /* == rep_key >> 40 */
+} syk_record_t;
+
+/* Overlap record (32 bytes): one entry of the reference's nested mapping dict
+ * {sub_id: {cell_id: count}} (find_object_properties_C.pyx:163-174). */
+typedef struct syk_pair {
+    uint64_t sub_id;
+    uint64_t cell_id;
+    uint64_t count;
+    uint64_t _pad;
+} syk_pair_t;
+
+/* geometry of one chunk call, needed to decode rep_key -> rep[3] */
+typedef struct syk_chunk_geom {
+    int64_t origin[3];
+    int64_t shape[3];
+} syk_chunk_geom_t;
+
+typedef struct syk_table syk_table_t; /* device open-addressing table id -> record */
+typedef struct syk_pairs syk_pairs_t; /* device open-addressing table (sub,cell) -> count */
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int syk_version(void);
+const char *syk_last_error(void);
+int syk_device_count(void);
+int syk_set_device(int device);
+
+/* ---- tables -------------------------------------------------------------------------------------------- */
+/* capacity is rounded up to a power of two (>= 1024); keep the load factor <= 0.5 */
+int syk_table_create(syk_table_t **out, uint64_t capacity);
+int syk_table_destroy(syk_table_t *t);
+int syk_table_clear(syk_table_t *t, void *stream);
+uint64_t syk_table_capacity(const syk_table_t *t);
+/* number of occupied slots / overflow flag; synchronises `stream` */
+int syk_table_count(syk_table_t *t, void *stream, uint64_t *n_out_host, int *overflow_out_host);
+/* compact the table into records_dev[0..n) (order unspecified, like the reference's unordered_map iteration);
+ * geoms_host[n_geoms] is indexed by chunk_seq to decode rep.  Synchronises `stream`. */
+int syk_table_export(syk_table_t *t, const syk_chunk_geom_t *geoms_host, uint32_t n_geoms, syk_record_t *records_dev,
+                     uint64_t max_records, uint64_t *n_out_host, void *stream);
+/* fold records into a table: count summed, bbox min/max, rep = max rep_key
+ * (merge_prop_dicts + final reduction, syconn/proc/sd_proc.py:1248-1273, :939-945, :1172-1177) */
+int syk_table_merge_records(syk_table_t *t, const syk_record_t *records_dev, uint64_t n, void *stream);
+/* owner(id) = hash(id) mod n_owners; reorders records into contiguous per-owner buckets (for the all-to-all).
+ * counts_dev[n_owners] receives the bucket sizes.  out_dev must hold n records. */
+int syk_records_bucket(const syk_record_t *records_dev, uint64_t n, uint32_t n_owners, syk_record_t *out_dev,
+                       uint64_t *counts_dev, void *stream);
+int syk_records_decode_rep(syk_record_t *records_dev, uint64_t n, const syk_chunk_geom_t *geoms_host, uint32_t n_geoms,
+                           void *stream);
+
+int syk_pairs_create(syk_pairs_t **out, uint64_t capacity);
+int syk_pairs_destroy(syk_pairs_t *t);
+int syk_pairs_clear(syk_pairs_t *t, void *stream);
+int syk_pairs_export(syk_pairs_t *t, syk_pair_t *pairs_dev, uint64_t max_pairs, uint64_t *n_out_host, void *stream);
+/* merge_map_dicts (syconn/proc/sd_proc.py:1300-1322): counts summed per (sub_id, cell_id) */
+int syk_pairs_merge(syk_pairs_t *t, const syk_pair_t *pairs_dev, uint64_t n, void *stream);
+/* owner = hash(sub_id) mod n_owners (the reference reduces per organelle object, sd_proc.py:830-853) */
+int syk_pairs_bucket(const syk_pair_t *pairs_dev, uint64_t n, uint32_t n_owners, syk_pair_t *out_dev, uint64_t *counts_dev,
+                     void *stream);
+
+/* ---- hot path, device buffers -------------------------------------------------------------------------- */
+/* find_object_properties(chunk)  -- syconn/extraction/find_object_properties_C.pyx:24-49
+ * accumulates into `t`: voxel count, bounding box, first voxel in (x,y,z) scan order per non-zero id.
+ * origin is added to all coordinates (merge_prop_dicts' offset, sd_proc.py:1259-1266). */
+int syk_find_object_properties(syk_table_t *t, const void *labels_dev, int elem_bytes, const int64_t shape[3],
+                               const int64_t strides[3], const int64_t origin[3], uint32_t chunk_seq, void *stream);
+
+/* map_subcell_extract_props(ch, subcell_chs) -- find_object_properties_C.pyx:112-192
+ * (cell_t == NULL and sub_t == NULL  =>  map_subcell_C, :72-109: mapping only)
+ * subcell_dev[c] are n_sub device pointers sharing shape/strides `sub_strides`. */
+int syk_map_subcell_extract_props(syk_table_t *cell_t, syk_table_t *const *sub_t, syk_pairs_t *const *pair_t,
+                                  const void *cell_dev, const int64_t cell_strides[3], const void *const *subcell_dev,
+                                  const int64_t sub_strides[3], int n_sub, int elem_bytes, const int64_t shape[3],
+                                  const int64_t origin[3], uint32_t chunk_seq, void *stream);
+
+/* detect_seg_boundaries(arr) -- syconn/extraction/find_object_properties.py:424-455; out: uint8 C-contiguous */
+int syk_detect_seg_boundaries(const void *arr_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                              uint8_t *out_dev, void *stream);
+
+/* process_block_nonzero(edges, arr, stencil) -- syconn/extraction/block_processing_C.pyx:53-75 (+ kernel :21-49)
+ * edges: uint8 or uint32 (edge_bytes 1|4).  arr: uint32, or uint64 truncated to uint32 (the caller-side
+ * .astype(np.uint32), cs_extraction_steps.py:385-387).  out: uint64 [shape - stencil + 1], strides in elements. */
+int syk_process_block_nonzero(const void *edges_dev, int edge_bytes, const int64_t edge_strides[3], const void *arr_dev,
+                              int elem_bytes, const int64_t arr_strides[3], const int64_t shape[3],
+                              const int32_t stencil[3], uint64_t *out_dev, const int64_t out_strides[3], void *stream);
+
+/* detect_cs(arr) -- syconn/extraction/find_object_properties.py:458-472: fused boundary mask + stencil */
+int syk_detect_cs(const void *arr_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                  const int32_t stencil[3], uint64_t *out_dev, const int64_t out_strides[3], void *stream);
+
+/* ---- synthetic label volumes (bench/test inputs; bit-identical to syconn_b200/synth.py) ------------------ */
+/* kind 0: cell supervoxels (ids < 2^32, ~3% background); kind 1..: organelle channel (sparse 64-bit ids) */
+int syk_synth_labels(void *out_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                     const int64_t origin[3], const int32_t pitch[3], int32_t warp_amp, uint64_t seed, int kind,
+                     int density16, void *stream);
+
+/* ---- hot path, HOST buffers (what a binding of the reference's Cython functions calls) ------------------ */
+/* Results are malloc'ed by the library; release with syk_free().  `labels` must be a dense block viewed
+ * with `strides` (a permutation of a C-contiguous layout); nbytes = elem_bytes * prod(shape). */
+int syk_find_object_properties_host(const void *labels_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                                    uint64_t capacity_hint, syk_record_t **records_out, uint64_t *n_out);
+int syk_map_subcell_extract_props_host(const void *cell_host, const int64_t cell_strides[3], const void *subcell_host,
+                                       const int64_t sub_strides[4], int n_sub, int elem_bytes, const int64_t shape[3],
+                                       int props_too, uint64_t capacity_hint, syk_record_t **cell_records_out,
+                                       uint64_t *n_cell_out, syk_record_t **sub_records_out /*[n_sub]*/,
+                                       uint64_t *n_sub_out /*[n_sub]*/, syk_pair_t **pairs_out /*[n_sub]*/,
+                                       uint64_t *n_pairs_out /*[n_sub]*/);
+int syk_detect_cs_host(const void *arr_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                       const int32_t stencil[3], uint64_t *out_host /* C-contiguous [shape-stencil+1] */);
+int syk_process_block_nonzero_host(const void *edges_host, int edge_bytes, const int64_t edge_strides[3],
+                                   const void *arr_host, int elem_bytes, const int64_t arr_strides[3],
+                                   const int64_t shape[3], const int32_t stencil[3], uint64_t *out_host);
+int syk_detect_seg_boundaries_host(const void *arr_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                                   uint8_t *out_host);
+void syk_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYK_H */

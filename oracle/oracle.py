@@ -1,0 +1,247 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+ctypes front-end of ``oracle/syk_oracle.c`` (plain-C CPU restatement of the reference's
+hot path).  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` leg may import this module; ``syconn_b200`` never does.
+
+Parity status: PINNED.  The restatement is checked against (a) the reference's own
+known-answer tests (``/root/reference/tests/test_segmentation_analysis.py:19-52,100-135,162-169``,
+re-stated in ``tests/test_oracle_pins.py``) and (b) golden vectors produced by the reference's
+compiled Cython/numba code (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``).
+
+The functions mirror the reference API (same return structures):
+  * find_object_properties      -- syconn/extraction/find_object_properties_C.pyx:24-49
+  * map_subcell_extract_props   -- syconn/extraction/find_object_properties_C.pyx:112-192
+  * map_subcell_C               -- syconn/extraction/find_object_properties_C.pyx:72-109
+  * detect_seg_boundaries       -- syconn/extraction/find_object_properties.py:424-455
+  * process_block_nonzero       -- syconn/extraction/block_processing_C.pyx:53-75 (+ kernel :21-49)
+  * detect_cs                   -- syconn/extraction/find_object_properties.py:458-472
+  * merge_prop_dicts / merge_map_dicts -- syconn/proc/sd_proc.py:1248-1273, :1300-1322
+"""
+import ctypes as C
+import os
+import subprocess
+from collections import defaultdict
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+_SRC = os.path.join(_HERE, "syk_oracle.c")
+_lib = None
+
+CS_FILTERSIZE = (13, 13, 7)  # syconn/handler/config.yml:148
+
+
+def build(force=False):
+    """Compile the C restatement (gcc only; a few seconds)."""
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-fvisibility=hidden",
+                               "-o", _SO, _SRC])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        p, i64p = C.c_void_p, C.POINTER(C.c_int64)
+        L.orc_detect_seg_boundaries.argtypes = [p, C.c_int, i64p, i64p, p]
+        L.orc_process_block_nonzero.argtypes = [p, C.c_int, i64p, p, C.c_int, i64p, i64p,
+                                                C.POINTER(C.c_int32), p]
+        L.orc_find_object_properties.argtypes = [p, C.c_int, i64p, i64p]
+        L.orc_find_object_properties.restype = p
+        L.orc_map_subcell_extract_props.argtypes = [p, i64p, p, i64p, C.c_int, C.c_int, i64p, C.c_int]
+        L.orc_map_subcell_extract_props.restype = p
+        L.orc_result_free.argtypes = [p]
+        L.orc_result_nobj.argtypes = [p, C.c_int]
+        L.orc_result_nobj.restype = C.c_uint64
+        L.orc_result_objs.argtypes = [p, C.c_int, p, p, p, p]
+        L.orc_result_npairs.argtypes = [p, C.c_int]
+        L.orc_result_npairs.restype = C.c_uint64
+        L.orc_result_pairs.argtypes = [p, C.c_int, p, p, p]
+        _lib = L
+    return _lib
+
+
+def _i64(vals):
+    return (C.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def _estrides(a):
+    assert all(s % a.itemsize == 0 for s in a.strides)
+    return [s // a.itemsize for s in a.strides]
+
+
+def _check_label_dtype(a, name="chunk"):
+    if a.dtype not in (np.uint32, np.uint64):
+        raise ValueError(f"Buffer dtype mismatch, expected 'uint64_t' or 'uint32_t' but got {a.dtype} ({name})")
+
+
+# ------------------------------------------------------------------------------------------ arrays
+def _objs(L, h, tab):
+    n = int(L.orc_result_nobj(h, tab))
+    ids = np.empty(n, np.uint64)
+    sizes = np.empty(n, np.int64)
+    bbox = np.empty((n, 2, 3), np.int32)
+    rep = np.empty((n, 3), np.int32)
+    if n:
+        L.orc_result_objs(h, tab, ids.ctypes.data, sizes.ctypes.data, bbox.ctypes.data, rep.ctypes.data)
+    return ids, sizes, bbox, rep
+
+
+def _pairs(L, h, ch):
+    n = int(L.orc_result_npairs(h, ch))
+    sub = np.empty(n, np.uint64)
+    cell = np.empty(n, np.uint64)
+    cnt = np.empty(n, np.int64)
+    if n:
+        L.orc_result_pairs(h, ch, sub.ctypes.data, cell.ctypes.data, cnt.ctypes.data)
+    return sub, cell, cnt
+
+
+def find_object_properties_arrays(chunk):
+    """-> (ids u64[N], sizes i64[N], bbox i32[N,2,3], rep i32[N,3]) in first-occurrence order."""
+    chunk = np.asarray(chunk)
+    _check_label_dtype(chunk)
+    assert chunk.ndim == 3
+    L = lib()
+    h = L.orc_find_object_properties(chunk.ctypes.data, chunk.itemsize, _i64(chunk.shape), _i64(_estrides(chunk)))
+    try:
+        return _objs(L, h, 0)
+    finally:
+        L.orc_result_free(h)
+
+
+def map_subcell_extract_props_arrays(ch, subcell_chs, props_too=True):
+    """-> (cell_objs, [objs_c], [pairs_c]) with objs = (ids,sizes,bbox,rep), pairs = (sub,cell,cnt)."""
+    ch = np.asarray(ch)
+    subcell_chs = np.asarray(subcell_chs)
+    _check_label_dtype(ch, "ch")
+    if subcell_chs.dtype != ch.dtype:
+        raise ValueError("Buffer dtype mismatch (ch and subcell_chs must share the dtype)")
+    assert ch.ndim == 3 and subcell_chs.ndim == 4
+    sh = ch.shape
+    for ii in range(subcell_chs.shape[0]):
+        s = subcell_chs[ii].shape
+        assert s == sh, ("Segmentation of cells and subcellular structures must have same shape. "
+                         "{} {} {} {} {} {}".format(s[0], s[1], s[2], sh[0], sh[1], sh[2]))
+    L = lib()
+    nsub = subcell_chs.shape[0]
+    h = L.orc_map_subcell_extract_props(ch.ctypes.data, _i64(_estrides(ch)), subcell_chs.ctypes.data,
+                                        _i64(_estrides(subcell_chs)), ch.itemsize, nsub, _i64(sh),
+                                        1 if props_too else 0)
+    try:
+        cell = _objs(L, h, 0)
+        subs = [_objs(L, h, 1 + i) for i in range(nsub)]
+        pairs = [_pairs(L, h, i) for i in range(nsub)]
+    finally:
+        L.orc_result_free(h)
+    return cell, subs, pairs
+
+
+# ------------------------------------------------------------------------------------------ dict API
+def _objs_to_dicts(objs):
+    ids, sizes, bbox, rep = objs
+    ids_l = ids.tolist()
+    rc = dict(zip(ids_l, rep.tolist()))
+    bb = dict(zip(ids_l, bbox.tolist()))
+    sz = dict(zip(ids_l, sizes.tolist()))
+    return rc, bb, sz
+
+
+def _pairs_to_dict(pairs):
+    sub, cell, cnt = pairs
+    out = {}
+    for s, c, n in zip(sub.tolist(), cell.tolist(), cnt.tolist()):
+        out.setdefault(s, {})[c] = n
+    return out
+
+
+def find_object_properties(chunk):
+    return _objs_to_dicts(find_object_properties_arrays(chunk))
+
+
+def map_subcell_extract_props(ch, subcell_chs):
+    cell, subs, pairs = map_subcell_extract_props_arrays(ch, subcell_chs, True)
+    rc, bb, sz = _objs_to_dicts(cell)
+    sd = [_objs_to_dicts(s) for s in subs]
+    return [rc, bb, sz], [[d[0] for d in sd], [d[1] for d in sd], [d[2] for d in sd]], \
+        [_pairs_to_dict(p) for p in pairs]
+
+
+def map_subcell_C(ch, subcell_chs):
+    _, _, pairs = map_subcell_extract_props_arrays(ch, subcell_chs, False)
+    return [_pairs_to_dict(p) for p in pairs]
+
+
+def detect_seg_boundaries(arr):
+    arr = np.asarray(arr)
+    a = arr
+    if a.dtype not in (np.uint32, np.uint64):
+        # the numba reference accepts any integer/float array; compare as 64-bit patterns
+        a = np.ascontiguousarray(arr).astype(np.int64).view(np.uint64) if arr.dtype.kind in "iu" \
+            else np.ascontiguousarray(arr, dtype=np.float64).view(np.uint64)
+    out = np.empty(a.shape, np.uint8)
+    rc = lib().orc_detect_seg_boundaries(a.ctypes.data, a.itemsize, _i64(a.shape), _i64(_estrides(a)),
+                                         out.ctypes.data)
+    assert rc == 0
+    return out.view(np.bool_)
+
+
+def process_block_nonzero(edges, arr, stencil1=(7, 7, 3)):
+    edges = np.asarray(edges)
+    arr = np.asarray(arr)
+    if edges.dtype != np.uint32 or arr.dtype != np.uint32:
+        raise ValueError("Buffer dtype mismatch, expected 'uint32_t'")
+    st = [int(s) for s in stencil1]
+    assert (st[0] % 2 + st[1] % 2 + st[2] % 2) == 3
+    oshape = tuple(max(0, arr.shape[i] - st[i] + 1) for i in range(3))
+    out = np.zeros(oshape, np.uint64)
+    rc = lib().orc_process_block_nonzero(edges.ctypes.data, 4, _i64(_estrides(edges)), arr.ctypes.data, 4,
+                                         _i64(_estrides(arr)), _i64(arr.shape), (C.c_int32 * 3)(*st),
+                                         out.ctypes.data)
+    assert rc == 0, rc
+    return out
+
+
+def detect_cs(arr, stencil=CS_FILTERSIZE):
+    edges = detect_seg_boundaries(arr).astype(np.uint32, copy=False)
+    arr = np.asarray(arr).astype(np.uint32, copy=False)
+    return process_block_nonzero(edges, arr, stencil)
+
+
+# ------------------------------------------------------------------------------------------ merges (a6)
+def merge_prop_dicts(prop_dicts, offset=None):
+    """syconn/proc/sd_proc.py:1248-1273: rc overwritten by later chunks, bboxes appended, sizes summed."""
+    tot_rc, tot_bb, tot_size = prop_dicts[0]
+    for el in prop_dicts[1:]:
+        if len(el[0]) == 0:
+            continue
+        if offset is not None:
+            for k in el[0]:
+                el[0][k] = [el[0][k][ii] + offset[ii] for ii in range(3)]
+        tot_rc.update(el[0])
+        for k, v in el[1].items():
+            bb = v if offset is None else [[v[0][ii] + offset[ii] for ii in range(3)],
+                                           [v[1][ii] + offset[ii] for ii in range(3)]]
+            tot_bb[k].append(bb)
+        for k, v in el[2].items():
+            tot_size[k] = tot_size.get(k, 0) + v
+
+
+def merge_map_dicts(map_dicts):
+    """syconn/proc/sd_proc.py:1300-1322."""
+    tot_map = map_dicts[0]
+    for el in map_dicts[1:]:
+        for sc_id, sc_dc in el.items():
+            if sc_id in tot_map:
+                for cellsv_id, n in sc_dc.items():
+                    tot_map[sc_id][cellsv_id] = tot_map[sc_id].get(cellsv_id, 0) + n
+            else:
+                tot_map[sc_id] = sc_dc
+
+
+def new_prop_acc():
+    return [{}, defaultdict(list), {}]

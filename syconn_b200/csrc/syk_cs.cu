@@ -1,0 +1,390 @@
+// syk_cs.cu -- contact-site detection (sm_100a).
+//
+//   syk_detect_seg_boundaries  <- syconn/extraction/find_object_properties.py:424-455
+//   syk_process_block_nonzero  <- syconn/extraction/block_processing_C.pyx:53-75 (+ kernel :21-49)
+//   syk_detect_cs              <- syconn/extraction/find_object_properties.py:458-472 (fused, no edge volume in HBM)
+//
+// Generic path (this file): haloed 3-D tile of uint32 ids staged in shared memory; boundary voxels of the tile are
+// compacted into a list; one warp per boundary voxel sweeps the stencil window 32 neighbours at a time,
+// de-duplicates them with __match_any_sync and keeps a warp-distributed histogram (lane i owns the i-th distinct
+// id).  Windows with more than 32 distinct ids fall back to a block-cooperative shared-memory hash table.
+// The arg-max follows the reference exactly: ids 0 and centre excluded, ties -> smallest id.
+#include "syk_common.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int CS_THREADS = 128;
+constexpr int CS_WARPS = CS_THREADS / 32;
+constexpr int OU = 4, OV = 8, OW = 32;  // output tile (internal axes u, v, w); w = lane axis
+constexpr int OT = OU * OV * OW;
+
+struct CsGeom {
+    long long n[3];    // input extents along internal axes
+    long long ist[3];  // input strides (elements)
+    long long est[3];  // edge-volume strides (elements), only with explicit edges
+    long long ost[3];  // output strides (elements)
+    long long on[3];   // output extents = n - sten + 1
+    int sten[3];       // stencil along internal axes
+    int off[3];        // sten / 2
+    int hlo[3];        // smem halo below the output tile: max(off, 1)
+    int hd[3];         // smem tile dims
+    int total;         // sten[0]*sten[1]*sten[2]
+    int hslots;        // fallback hash slots (power of two >= 2*total)
+    long long tiles[3];
+    long long ntiles;
+    int elem_bytes;
+    int edge_bytes;
+};
+
+__device__ __forceinline__ unsigned ld_id(const void *base, int elem_bytes, long long idx) {
+    return elem_bytes == 8 ? (unsigned)__ldg((const unsigned long long *)base + idx) : __ldg((const unsigned *)base + idx);
+}
+
+__device__ __forceinline__ unsigned long long pack_result(unsigned center, unsigned key, unsigned best) {
+    if (best == 0u) return 0ull;
+    return center > key ? (((unsigned long long)key << 32) + center) : (((unsigned long long)center << 32) + key);
+}
+
+__global__ void __launch_bounds__(CS_THREADS) k_detect_cs(const void *__restrict__ arr, const void *__restrict__ edges,
+                                                          unsigned long long *__restrict__ out, CsGeom G) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned *tile = reinterpret_cast<unsigned *>(smem_raw);                       // hd[0]*hd[1]*hd[2]
+    const int tile_n = G.hd[0] * G.hd[1] * G.hd[2];
+    unsigned short *offs = reinterpret_cast<unsigned short *>(tile + tile_n);       // total (padded to x2)
+    unsigned short *elist = offs + ((G.total + 1) & ~1);                            // OT
+    unsigned short *olist = elist + OT;                                             // OT (overflow voxels)
+    unsigned *hkeys = reinterpret_cast<unsigned *>(olist + OT);                     // hslots
+    unsigned *hcnt = hkeys + G.hslots;                                              // hslots
+    __shared__ int n_edge, n_over;
+    __shared__ unsigned long long best_sh;
+
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    // window offsets inside the smem tile, relative to the window origin
+    for (int i = tid; i < G.total; i += CS_THREADS) {
+        const int k = i % G.sten[2];
+        const int r = i / G.sten[2];
+        const int j = r % G.sten[1];
+        const int ii = r / G.sten[1];
+        offs[i] = (unsigned short)((ii * G.hd[1] + j) * G.hd[2] + k);
+    }
+    for (int i = tid; i < G.hslots; i += CS_THREADS) {
+        hkeys[i] = 0u;
+        hcnt[i] = 0u;
+    }
+
+    for (long long t = blockIdx.x; t < G.ntiles; t += gridDim.x) {
+        const long long tw = t % G.tiles[2];
+        const long long r0 = t / G.tiles[2];
+        const long long tv = r0 % G.tiles[1];
+        const long long tu = r0 / G.tiles[1];
+        const long long o0[3] = {tu * OU, tv * OV, tw * OW};  // output-tile origin (output coords)
+        // input coords of smem tile origin: output coord + off - hlo
+        const long long i0[3] = {o0[0] + G.off[0] - G.hlo[0], o0[1] + G.off[1] - G.hlo[1], o0[2] + G.off[2] - G.hlo[2]};
+        __syncthreads();
+        if (tid == 0) {
+            n_edge = 0;
+            n_over = 0;
+        }
+        // ---- stage the haloed tile (zero fill outside the volume; never read by valid windows) ----
+        for (int i = tid; i < tile_n; i += CS_THREADS) {
+            const int k = i % G.hd[2];
+            const int r = i / G.hd[2];
+            const int j = r % G.hd[1];
+            const int ii = r / G.hd[1];
+            const long long a = i0[0] + ii, b = i0[1] + j, c = i0[2] + k;
+            unsigned v = 0u;
+            if (a >= 0 && a < G.n[0] && b >= 0 && b < G.n[1] && c >= 0 && c < G.n[2])
+                v = ld_id(arr, G.elem_bytes, a * G.ist[0] + b * G.ist[1] + c * G.ist[2]);
+            tile[i] = v;
+        }
+        __syncthreads();
+        // ---- boundary mask (detect_seg_boundaries) + zero fill of non-boundary outputs ----
+        for (int i = tid; i < OT; i += CS_THREADS) {
+            const int lw = i % OW;
+            const int r = i / OW;
+            const int lv = r % OV;
+            const int lu = r / OV;
+            const long long ou = o0[0] + lu, ov = o0[1] + lv, ow = o0[2] + lw;
+            if (ou >= G.on[0] || ov >= G.on[1] || ow >= G.on[2]) continue;
+            const int ci = ((lu + G.hlo[0]) * G.hd[1] + (lv + G.hlo[1])) * G.hd[2] + (lw + G.hlo[2]);
+            const unsigned c = tile[ci];
+            bool edge;
+            if (edges != nullptr) {
+                const long long ei = (ou + G.off[0]) * G.est[0] + (ov + G.off[1]) * G.est[1] + (ow + G.off[2]) * G.est[2];
+                edge = G.edge_bytes == 1 ? (__ldg((const unsigned char *)edges + ei) != 0)
+                                         : (__ldg((const unsigned *)edges + ei) != 0u);
+            } else {
+                edge = false;
+                if (c != 0u) {
+                    const long long cu = ou + G.off[0], cv = ov + G.off[1], cw = ow + G.off[2];  // input coords of the centre
+                    const int su = G.hd[1] * G.hd[2], sv = G.hd[2];
+                    if (cu > 0 && tile[ci - su] != c) edge = true;
+                    if (cu + 1 < G.n[0] && tile[ci + su] != c) edge = true;
+                    if (cv > 0 && tile[ci - sv] != c) edge = true;
+                    if (cv + 1 < G.n[1] && tile[ci + sv] != c) edge = true;
+                    if (cw > 0 && tile[ci - 1] != c) edge = true;
+                    if (cw + 1 < G.n[2] && tile[ci + 1] != c) edge = true;
+                }
+            }
+            if (edge) {
+                elist[atomicAdd(&n_edge, 1)] = (unsigned short)i;
+            } else {
+                out[ou * G.ost[0] + ov * G.ost[1] + ow * G.ost[2]] = 0ull;
+            }
+        }
+        __syncthreads();
+        // ---- one warp per boundary voxel ----
+        const int ne = n_edge;
+        for (int e = wib; e < ne; e += CS_WARPS) {
+            const int i = elist[e];
+            const int lw = i % OW;
+            const int r = i / OW;
+            const int lv = r % OV;
+            const int lu = r / OV;
+            // window origin inside the smem tile
+            const int wbase = ((lu + G.hlo[0] - G.off[0]) * G.hd[1] + (lv + G.hlo[1] - G.off[1])) * G.hd[2] + (lw + G.hlo[2] - G.off[2]);
+            const unsigned center = tile[((lu + G.hlo[0]) * G.hd[1] + (lv + G.hlo[1])) * G.hd[2] + (lw + G.hlo[2])];
+            unsigned my_key = 0u, my_cnt = 0u;
+            int nheld = 0;
+            bool overflow = false;
+            for (int base = 0; base < G.total && !overflow; base += 32) {
+                const int idx = base + lane;
+                unsigned id = 0u;
+                if (idx < G.total) id = tile[wbase + offs[idx]];
+                if (id == center) id = 0u;
+                if (!__any_sync(FULL, id != 0u)) continue;
+                const unsigned peers = __match_any_sync(FULL, id);
+                const bool leader = (id != 0u) && (lane == __ffs(peers) - 1);
+                const unsigned n = (unsigned)__popc(peers);
+                unsigned todo = __ballot_sync(FULL, leader);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1u;
+                    const unsigned kv = __shfl_sync(FULL, id, src);
+                    const unsigned kn = __shfl_sync(FULL, n, src);
+                    const unsigned hit = __ballot_sync(FULL, lane < nheld && my_key == kv);
+                    if (hit) {
+                        if (lane == __ffs(hit) - 1) my_cnt += kn;
+                    } else if (nheld < 32) {
+                        if (lane == nheld) {
+                            my_key = kv;
+                            my_cnt = kn;
+                        }
+                        ++nheld;
+                    } else {
+                        overflow = true;
+                        break;
+                    }
+                }
+            }
+            if (overflow) {
+                if (lane == 0) olist[atomicAdd(&n_over, 1)] = (unsigned short)i;
+                continue;
+            }
+            // arg-max: larger count wins, ties -> smaller id
+            unsigned long long best = (lane < nheld) ? (((unsigned long long)my_cnt << 32) | (unsigned long long)(~my_key)) : 0ull;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(FULL, best, o);
+                best = other > best ? other : best;
+            }
+            if (lane == 0) {
+                const unsigned bc = (unsigned)(best >> 32);
+                const unsigned bk = ~(unsigned)(best & 0xffffffffull);
+                out[(o0[0] + lu) * G.ost[0] + (o0[1] + lv) * G.ost[1] + (o0[2] + lw) * G.ost[2]] = pack_result(center, bk, bc);
+            }
+        }
+        __syncthreads();
+        // ---- windows with > 32 distinct ids: block-cooperative shared-memory hash ----
+        const int no = n_over;
+        for (int e = 0; e < no; ++e) {
+            const int i = olist[e];
+            const int lw = i % OW;
+            const int r = i / OW;
+            const int lv = r % OV;
+            const int lu = r / OV;
+            const int wbase = ((lu + G.hlo[0] - G.off[0]) * G.hd[1] + (lv + G.hlo[1] - G.off[1])) * G.hd[2] + (lw + G.hlo[2] - G.off[2]);
+            const unsigned center = tile[((lu + G.hlo[0]) * G.hd[1] + (lv + G.hlo[1])) * G.hd[2] + (lw + G.hlo[2])];
+            if (tid == 0) best_sh = 0ull;
+            __syncthreads();
+            const unsigned hm = (unsigned)G.hslots - 1u;
+            for (int idx = tid; idx < G.total; idx += CS_THREADS) {
+                const unsigned id = tile[wbase + offs[idx]];
+                if (id == 0u || id == center) continue;
+                unsigned h = syk_mix32(id) & hm;
+                for (;;) {
+                    const unsigned prev = atomicCAS(&hkeys[h], 0u, id);
+                    if (prev == 0u || prev == id) {
+                        atomicAdd(&hcnt[h], 1u);
+                        break;
+                    }
+                    h = (h + 1u) & hm;
+                }
+            }
+            __syncthreads();
+            unsigned long long best = 0ull;
+            for (int h = tid; h < G.hslots; h += CS_THREADS) {
+                const unsigned k = hkeys[h];
+                if (k != 0u) {
+                    const unsigned long long cand = ((unsigned long long)hcnt[h] << 32) | (unsigned long long)(~k);
+                    best = cand > best ? cand : best;
+                    hkeys[h] = 0u;
+                    hcnt[h] = 0u;
+                }
+            }
+            if (best) atomicMax(&best_sh, best);
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned long long b = best_sh;
+                const unsigned bc = (unsigned)(b >> 32);
+                const unsigned bk = ~(unsigned)(b & 0xffffffffull);
+                out[(o0[0] + lu) * G.ost[0] + (o0[1] + lv) * G.ost[1] + (o0[2] + lw) * G.ost[2]] = pack_result(center, bk, bc);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void k_seg_boundaries(const void *__restrict__ arr, int elem_bytes, long long nx, long long ny, long long nz,
+                                 long long sx, long long sy, long long sz, unsigned char *__restrict__ out) {
+    const long long total = nx * ny * nz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long z = i % nz;
+        const long long r = i / nz;
+        const long long y = r % ny;
+        const long long x = r / ny;
+        const long long a = x * sx + y * sy + z * sz;
+        unsigned char b = 0;
+        if (elem_bytes == 8) {
+            const unsigned long long *p = (const unsigned long long *)arr;
+            const unsigned long long c = __ldg(p + a);
+            if (c != 0ull) {
+                if (x > 0 && __ldg(p + a - sx) != c) b = 1;
+                if (x + 1 < nx && __ldg(p + a + sx) != c) b = 1;
+                if (y > 0 && __ldg(p + a - sy) != c) b = 1;
+                if (y + 1 < ny && __ldg(p + a + sy) != c) b = 1;
+                if (z > 0 && __ldg(p + a - sz) != c) b = 1;
+                if (z + 1 < nz && __ldg(p + a + sz) != c) b = 1;
+            }
+        } else {
+            const unsigned *p = (const unsigned *)arr;
+            const unsigned c = __ldg(p + a);
+            if (c != 0u) {
+                if (x > 0 && __ldg(p + a - sx) != c) b = 1;
+                if (x + 1 < nx && __ldg(p + a + sx) != c) b = 1;
+                if (y > 0 && __ldg(p + a - sy) != c) b = 1;
+                if (y + 1 < ny && __ldg(p + a + sy) != c) b = 1;
+                if (z > 0 && __ldg(p + a - sz) != c) b = 1;
+                if (z + 1 < nz && __ldg(p + a + sz) != c) b = 1;
+            }
+        }
+        out[i] = b;
+    }
+}
+
+// internal axes: w = axis with the smallest |input stride| (lanes / coalescing), u = largest
+static void cs_plan(const int64_t shape[3], const int64_t strides[3], const int32_t stencil[3], const int64_t *edge_strides,
+                    const int64_t out_strides[3], int elem_bytes, int edge_bytes, CsGeom &G) {
+    int ax[3] = {0, 1, 2};
+    auto key = [&](int a) { return strides[a] < 0 ? -strides[a] : strides[a]; };
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j)
+            if (key(ax[j]) > key(ax[i])) {
+                int t = ax[i];
+                ax[i] = ax[j];
+                ax[j] = t;
+            }
+    G.total = 1;
+    for (int a = 0; a < 3; ++a) {
+        const int l = ax[a];
+        G.n[a] = shape[l];
+        G.ist[a] = strides[l];
+        G.est[a] = edge_strides ? edge_strides[l] : 0;
+        G.ost[a] = out_strides[l];
+        G.sten[a] = stencil[l];
+        G.off[a] = stencil[l] / 2;
+        G.on[a] = shape[l] - stencil[l] + 1;
+        G.hlo[a] = G.off[a] > 1 ? G.off[a] : 1;
+        G.total *= stencil[l];
+    }
+    const int od[3] = {OU, OV, OW};
+    for (int a = 0; a < 3; ++a) {
+        G.hd[a] = od[a] + 2 * G.hlo[a];
+        G.tiles[a] = (G.on[a] + od[a] - 1) / od[a];
+    }
+    G.ntiles = G.tiles[0] * G.tiles[1] * G.tiles[2];
+    int hs = 64;
+    while (hs < 2 * G.total) hs <<= 1;
+    G.hslots = hs;
+    G.elem_bytes = elem_bytes;
+    G.edge_bytes = edge_bytes;
+}
+
+static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_strides, const void *arr, int elem_bytes,
+                     const int64_t strides[3], const int64_t shape[3], const int32_t stencil[3], uint64_t *out,
+                     const int64_t out_strides[3], cudaStream_t s) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    SYK_CHECK_ARG(shape && strides && stencil && out_strides, "NULL geometry argument");
+    for (int a = 0; a < 3; ++a) {
+        SYK_CHECK_ARG(stencil[a] >= 1 && (stencil[a] % 2) == 1, "stencil must be odd along every axis (block_processing_C.pyx:57)");
+        SYK_CHECK_ARG(shape[a] >= 0, "negative shape");
+    }
+    SYK_CHECK_ARG((long long)stencil[0] * stencil[1] * stencil[2] <= 16384, "stencil window larger than 16384 voxels");
+    for (int a = 0; a < 3; ++a)
+        if (shape[a] - stencil[a] + 1 <= 0) return SYK_OK;  // empty output
+    SYK_CHECK_ARG(arr != nullptr && out != nullptr, "arr/out is NULL");
+    CsGeom G;
+    cs_plan(shape, strides, stencil, edge_strides, out_strides, elem_bytes, edge_bytes, G);
+    const size_t tile_n = (size_t)G.hd[0] * G.hd[1] * G.hd[2];
+    SYK_CHECK_ARG(tile_n < 65536, "stencil too large for the shared-memory tile");
+    const size_t smem = tile_n * 4 + (size_t)((G.total + 1) & ~1) * 2 + (size_t)OT * 2 * 2 + (size_t)G.hslots * 8;
+    SYK_CHECK_ARG(smem <= 220 * 1024, "stencil too large for shared memory");
+    SYK_CUDA(cudaFuncSetAttribute(k_detect_cs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int bps = (int)((220 * 1024) / (smem + 1024));
+    if (bps < 1) bps = 1;
+    if (bps > 8) bps = 8;
+    long long grid = (long long)sms * bps;
+    if (grid > G.ntiles) grid = G.ntiles;
+    k_detect_cs<<<(unsigned)grid, CS_THREADS, smem, s>>>(arr, edges, (unsigned long long *)out, G);
+    SYK_CUDA(cudaGetLastError());
+    return SYK_OK;
+}
+
+}  // namespace
+
+SYK_API int syk_detect_seg_boundaries(const void *arr_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                                      uint8_t *out_dev, void *stream) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    SYK_CHECK_ARG(shape && strides, "NULL geometry argument");
+    const long long total = shape[0] * shape[1] * shape[2];
+    if (total == 0) return SYK_OK;
+    SYK_CHECK_ARG(arr_dev && out_dev, "NULL buffer");
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_seg_boundaries<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(arr_dev, elem_bytes, shape[0], shape[1], shape[2],
+                                                                        strides[0], strides[1], strides[2], out_dev);
+    SYK_CUDA(cudaGetLastError());
+    return SYK_OK;
+}
+
+SYK_API int syk_process_block_nonzero(const void *edges_dev, int edge_bytes, const int64_t edge_strides[3], const void *arr_dev,
+                                      int elem_bytes, const int64_t arr_strides[3], const int64_t shape[3],
+                                      const int32_t stencil[3], uint64_t *out_dev, const int64_t out_strides[3], void *stream) {
+    SYK_CHECK_ARG(edges_dev != nullptr && edge_strides != nullptr, "edges is NULL");
+    SYK_CHECK_ARG(edge_bytes == 1 || edge_bytes == 4, "edge_bytes must be 1 or 4");
+    return cs_launch(edges_dev, edge_bytes, edge_strides, arr_dev, elem_bytes, arr_strides, shape, stencil, out_dev, out_strides,
+                     (cudaStream_t)stream);
+}
+
+SYK_API int syk_detect_cs(const void *arr_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                          const int32_t stencil[3], uint64_t *out_dev, const int64_t out_strides[3], void *stream) {
+    return cs_launch(nullptr, 0, nullptr, arr_dev, elem_bytes, strides, shape, stencil, out_dev, out_strides, (cudaStream_t)stream);
+}

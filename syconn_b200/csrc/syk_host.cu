@@ -1,0 +1,340 @@
+// syk_host.cu -- synthetic label generator and the HOST-buffer entry points (one synchronous call per chunk, the shape
+// of the reference's Cython `def` functions; host<->device copies happen inside the call).
+#include <stdlib.h>
+
+#include "syk_common.cuh"
+
+namespace {
+
+// ---- synthetic labels: integer-only, coordinate hashed => identical bits on CPU (syconn_b200/synth.py) and GPU ----
+__host__ __device__ __forceinline__ long long tri(long long t, long long P) {
+    long long m = t % (2 * P);
+    m -= P;
+    return m < 0 ? -m : m;
+}
+
+__host__ __device__ __forceinline__ unsigned long long synth_label(long long x, long long y, long long z, int px, int py,
+                                                                   int pz, int amp, unsigned long long seed, int kind,
+                                                                   int density16, int elem_bytes) {
+    const long long B = 1ll << 20;
+    const long long X = x + B, Y = y + B, Z = z + B;
+    const long long xw = X + (((tri(Y, 41) + tri(Z, 29)) * amp) >> 4);
+    const long long yw = Y + (((tri(Z, 37) + tri(X, 43)) * amp) >> 4);
+    const long long zw = Z + (((tri(X, 31) + tri(Y, 47)) * amp) >> 5);
+    const unsigned long long cx = (unsigned long long)(xw / px), cy = (unsigned long long)(yw / py),
+                             cz = (unsigned long long)(zw / pz);
+    const unsigned long long h =
+        syk_mix64((cx * 0x9E3779B97F4A7C15ULL) ^ (cy * 0xC2B2AE3D27D4EB4FULL) ^ (cz * 0x165667B19E3779F9ULL) ^
+                  (seed * 0xD6E8FEB86659FD93ULL + (unsigned long long)kind * 0xA0761D6478BD642FULL));
+    if (kind == 0) {
+        if ((h & 31ull) == 0ull) return 0ull;
+        unsigned long long id = h >> 32;
+        return id ? id : 1ull;
+    }
+    if (((h >> 8) & 15ull) >= (unsigned long long)density16) return 0ull;
+    return elem_bytes == 8 ? (h | 1ull) : ((h >> 32) | 1ull);
+}
+
+__global__ void k_synth(void *out, int elem_bytes, long long nx, long long ny, long long nz, long long sx, long long sy,
+                        long long sz, long long ox, long long oy, long long oz, int px, int py, int pz, int amp,
+                        unsigned long long seed, int kind, int density16, int fast_axis) {
+    const long long total = nx * ny * nz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long x, y, z;
+        if (fast_axis == 2) {  // z fastest in memory
+            z = i % nz;
+            const long long r = i / nz;
+            y = r % ny;
+            x = r / ny;
+        } else {  // x fastest in memory
+            x = i % nx;
+            const long long r = i / nx;
+            y = r % ny;
+            z = r / ny;
+        }
+        const unsigned long long v = synth_label(x + ox, y + oy, z + oz, px, py, pz, amp, seed, kind, density16, elem_bytes);
+        const long long a = x * sx + y * sy + z * sz;
+        if (elem_bytes == 8) ((unsigned long long *)out)[a] = v;
+        else ((unsigned *)out)[a] = (unsigned)v;
+    }
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+// a dense block viewed through `strides`: nbytes = elem_bytes * prod(shape); base offset must be 0
+static int check_dense(const int64_t *shape, const int64_t *strides, int nd) {
+    // sort by stride, check that strides are the running products
+    int idx[4] = {0, 1, 2, 3};
+    for (int i = 0; i < nd; ++i)
+        for (int j = i + 1; j < nd; ++j)
+            if (strides[idx[j]] < strides[idx[i]]) {
+                int t = idx[i];
+                idx[i] = idx[j];
+                idx[j] = t;
+            }
+    int64_t expect = 1;
+    for (int i = 0; i < nd; ++i) {
+        const int a = idx[i];
+        if (shape[a] == 1) continue;
+        if (strides[a] != expect) {
+            syk_set_error("host array must be a dense block (permuted C layout); make it contiguous first");
+            return SYK_EINVAL;
+        }
+        expect *= shape[a];
+    }
+    return SYK_OK;
+}
+
+static uint64_t pick_capacity(uint64_t hint, uint64_t nvox) {
+    uint64_t c = hint ? hint * 2 : (nvox / 64 < (1u << 16) ? (1u << 16) : nvox / 64);
+    if (c > nvox * 2 + 1024) c = nvox * 2 + 1024;
+    return c;
+}
+
+static int export_to_host(syk_table_t *t, const syk_chunk_geom_t *geom, syk_record_t **out, uint64_t *n_out) {
+    uint64_t n = 0;
+    int ovf = 0;
+    int rc = syk_table_count(t, nullptr, &n, &ovf);
+    if (rc) return rc;
+    if (ovf) {
+        syk_set_error("id table overflow");
+        return SYK_EOVERFLOW;
+    }
+    *n_out = n;
+    *out = nullptr;
+    if (n == 0) return SYK_OK;
+    DevBuf recs;
+    SYK_CUDA(cudaMalloc(&recs.p, n * sizeof(syk_record_t)));
+    rc = syk_table_export(t, geom, 1, (syk_record_t *)recs.p, n, &n, nullptr);
+    if (rc) return rc;
+    *out = (syk_record_t *)malloc(n * sizeof(syk_record_t));
+    if (!*out) return SYK_ENOMEM;
+    SYK_CUDA(cudaMemcpy(*out, recs.p, n * sizeof(syk_record_t), cudaMemcpyDeviceToHost));
+    return SYK_OK;
+}
+
+}  // namespace
+
+SYK_API int syk_synth_labels(void *out_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                             const int64_t origin[3], const int32_t pitch[3], int32_t warp_amp, uint64_t seed, int kind,
+                             int density16, void *stream) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    SYK_CHECK_ARG(pitch[0] > 0 && pitch[1] > 0 && pitch[2] > 0, "pitch must be positive");
+    const long long total = shape[0] * shape[1] * shape[2];
+    if (total == 0) return SYK_OK;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    const int fast_axis = (strides[0] < strides[2]) ? 0 : 2;
+    k_synth<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(out_dev, elem_bytes, shape[0], shape[1], shape[2], strides[0],
+                                                               strides[1], strides[2], origin[0], origin[1], origin[2],
+                                                               pitch[0], pitch[1], pitch[2], warp_amp, seed, kind, density16,
+                                                               fast_axis);
+    SYK_CUDA(cudaGetLastError());
+    return SYK_OK;
+}
+
+SYK_API int syk_find_object_properties_host(const void *labels_host, int elem_bytes, const int64_t shape[3],
+                                            const int64_t strides[3], uint64_t capacity_hint, syk_record_t **records_out,
+                                            uint64_t *n_out) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(records_out && n_out, "output pointers are NULL");
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    *records_out = nullptr;
+    *n_out = 0;
+    const uint64_t nvox = (uint64_t)shape[0] * shape[1] * shape[2];
+    if (nvox == 0) return SYK_OK;
+    rc = check_dense(shape, strides, 3);
+    if (rc) return rc;
+    DevBuf lab;
+    SYK_CUDA(cudaMalloc(&lab.p, nvox * elem_bytes));
+    SYK_CUDA(cudaMemcpy(lab.p, labels_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
+    const int64_t origin[3] = {0, 0, 0};
+    syk_chunk_geom_t geom;
+    for (int a = 0; a < 3; ++a) {
+        geom.origin[a] = 0;
+        geom.shape[a] = shape[a];
+    }
+    uint64_t cap = pick_capacity(capacity_hint, nvox);
+    for (;;) {
+        syk_table_t *t = nullptr;
+        rc = syk_table_create(&t, cap);
+        if (rc) return rc;
+        rc = syk_find_object_properties(t, lab.p, elem_bytes, shape, strides, origin, 0, nullptr);
+        if (!rc) rc = export_to_host(t, &geom, records_out, n_out);
+        syk_table_destroy(t);
+        if (rc != SYK_EOVERFLOW || cap >= nvox * 2) return rc;
+        cap *= 4;
+    }
+}
+
+SYK_API int syk_map_subcell_extract_props_host(const void *cell_host, const int64_t cell_strides[3], const void *subcell_host,
+                                               const int64_t sub_strides[4], int n_sub, int elem_bytes, const int64_t shape[3],
+                                               int props_too, uint64_t capacity_hint, syk_record_t **cell_records_out,
+                                               uint64_t *n_cell_out, syk_record_t **sub_records_out, uint64_t *n_sub_out,
+                                               syk_pair_t **pairs_out, uint64_t *n_pairs_out) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    SYK_CHECK_ARG(n_sub >= 0 && n_sub <= 4, "n_sub must be in [0, 4] per call");
+    if (cell_records_out) *cell_records_out = nullptr;
+    if (n_cell_out) *n_cell_out = 0;
+    for (int c = 0; c < n_sub; ++c) {
+        if (sub_records_out) sub_records_out[c] = nullptr;
+        if (n_sub_out) n_sub_out[c] = 0;
+        pairs_out[c] = nullptr;
+        n_pairs_out[c] = 0;
+    }
+    const uint64_t nvox = (uint64_t)shape[0] * shape[1] * shape[2];
+    if (nvox == 0) return SYK_OK;
+    rc = check_dense(shape, cell_strides, 3);
+    if (rc) return rc;
+    if (n_sub) {
+        const int64_t sshape[4] = {n_sub, shape[0], shape[1], shape[2]};
+        rc = check_dense(sshape, sub_strides, 4);
+        if (rc) return rc;
+    }
+    DevBuf cell, sub;
+    SYK_CUDA(cudaMalloc(&cell.p, nvox * elem_bytes));
+    SYK_CUDA(cudaMemcpy(cell.p, cell_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
+    const void *subp[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (n_sub) {
+        SYK_CUDA(cudaMalloc(&sub.p, nvox * elem_bytes * n_sub));
+        SYK_CUDA(cudaMemcpy(sub.p, subcell_host, nvox * elem_bytes * n_sub, cudaMemcpyHostToDevice));
+        for (int c = 0; c < n_sub; ++c) subp[c] = (const char *)sub.p + (size_t)c * sub_strides[0] * elem_bytes;
+    }
+    const int64_t origin[3] = {0, 0, 0};
+    syk_chunk_geom_t geom;
+    for (int a = 0; a < 3; ++a) {
+        geom.origin[a] = 0;
+        geom.shape[a] = shape[a];
+    }
+    uint64_t cap = pick_capacity(capacity_hint, nvox);
+    for (;;) {
+        syk_table_t *ct = nullptr, *st[4] = {nullptr, nullptr, nullptr, nullptr};
+        syk_pairs_t *pt[4] = {nullptr, nullptr, nullptr, nullptr};
+        rc = SYK_OK;
+        if (props_too) rc = syk_table_create(&ct, cap);
+        for (int c = 0; c < n_sub && !rc; ++c) {
+            if (props_too) rc = syk_table_create(&st[c], cap);
+            if (!rc) rc = syk_pairs_create(&pt[c], cap);
+        }
+        if (!rc)
+            rc = syk_map_subcell_extract_props(props_too ? ct : nullptr, props_too ? st : nullptr, pt, cell.p, cell_strides, subp,
+                                               sub_strides + 1, n_sub, elem_bytes, shape, origin, 0, nullptr);
+        if (!rc && props_too) rc = export_to_host(ct, &geom, cell_records_out, n_cell_out);
+        for (int c = 0; c < n_sub && !rc; ++c) {
+            if (props_too) rc = export_to_host(st[c], &geom, &sub_records_out[c], &n_sub_out[c]);
+            if (rc) break;
+            uint64_t np = 0;
+            DevBuf pb;
+            const uint64_t maxp = pt[c]->capacity;
+            SYK_CUDA(cudaMalloc(&pb.p, maxp * sizeof(syk_pair_t)));
+            rc = syk_pairs_export(pt[c], (syk_pair_t *)pb.p, maxp, &np, nullptr);
+            if (rc) break;
+            n_pairs_out[c] = np;
+            if (np) {
+                pairs_out[c] = (syk_pair_t *)malloc(np * sizeof(syk_pair_t));
+                SYK_CUDA(cudaMemcpy(pairs_out[c], pb.p, np * sizeof(syk_pair_t), cudaMemcpyDeviceToHost));
+            }
+        }
+        syk_table_destroy(ct);
+        for (int c = 0; c < n_sub; ++c) {
+            syk_table_destroy(st[c]);
+            syk_pairs_destroy(pt[c]);
+        }
+        if (rc != SYK_EOVERFLOW || cap >= nvox * 2) {
+            if (rc) {  // release partial results
+                if (cell_records_out && *cell_records_out) { free(*cell_records_out); *cell_records_out = nullptr; }
+                for (int c = 0; c < n_sub; ++c) {
+                    if (sub_records_out && sub_records_out[c]) { free(sub_records_out[c]); sub_records_out[c] = nullptr; }
+                    if (pairs_out[c]) { free(pairs_out[c]); pairs_out[c] = nullptr; }
+                }
+            }
+            return rc;
+        }
+        if (cell_records_out && *cell_records_out) { free(*cell_records_out); *cell_records_out = nullptr; }
+        for (int c = 0; c < n_sub; ++c) {
+            if (sub_records_out && sub_records_out[c]) { free(sub_records_out[c]); sub_records_out[c] = nullptr; }
+            if (pairs_out[c]) { free(pairs_out[c]); pairs_out[c] = nullptr; }
+        }
+        cap *= 4;
+    }
+}
+
+static int cs_host_impl(const void *edges_host, int edge_bytes, const int64_t *edge_strides, const void *arr_host, int elem_bytes,
+                        const int64_t shape[3], const int64_t strides[3], const int32_t stencil[3], uint64_t *out_host) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    for (int a = 0; a < 3; ++a)
+        SYK_CHECK_ARG(stencil[a] >= 1 && (stencil[a] % 2) == 1, "stencil must be odd along every axis (block_processing_C.pyx:57)");
+    int64_t oshape[3];
+    uint64_t nout = 1;
+    for (int a = 0; a < 3; ++a) {
+        oshape[a] = shape[a] - stencil[a] + 1;
+        if (oshape[a] <= 0) return SYK_OK;
+        nout *= (uint64_t)oshape[a];
+    }
+    const uint64_t nvox = (uint64_t)shape[0] * shape[1] * shape[2];
+    rc = check_dense(shape, strides, 3);
+    if (rc) return rc;
+    DevBuf arr, edg, out;
+    SYK_CUDA(cudaMalloc(&arr.p, nvox * elem_bytes));
+    SYK_CUDA(cudaMemcpy(arr.p, arr_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
+    if (edges_host) {
+        rc = check_dense(shape, edge_strides, 3);
+        if (rc) return rc;
+        SYK_CUDA(cudaMalloc(&edg.p, nvox * edge_bytes));
+        SYK_CUDA(cudaMemcpy(edg.p, edges_host, nvox * edge_bytes, cudaMemcpyHostToDevice));
+    }
+    SYK_CUDA(cudaMalloc(&out.p, nout * 8));
+    const int64_t ost[3] = {oshape[1] * oshape[2], oshape[2], 1};
+    if (edges_host)
+        rc = syk_process_block_nonzero(edg.p, edge_bytes, edge_strides, arr.p, elem_bytes, strides, shape, stencil, (uint64_t *)out.p,
+                                       ost, nullptr);
+    else
+        rc = syk_detect_cs(arr.p, elem_bytes, shape, strides, stencil, (uint64_t *)out.p, ost, nullptr);
+    if (rc) return rc;
+    SYK_CUDA(cudaMemcpy(out_host, out.p, nout * 8, cudaMemcpyDeviceToHost));
+    return SYK_OK;
+}
+
+SYK_API int syk_detect_cs_host(const void *arr_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                               const int32_t stencil[3], uint64_t *out_host) {
+    return cs_host_impl(nullptr, 0, nullptr, arr_host, elem_bytes, shape, strides, stencil, out_host);
+}
+
+SYK_API int syk_process_block_nonzero_host(const void *edges_host, int edge_bytes, const int64_t edge_strides[3],
+                                           const void *arr_host, int elem_bytes, const int64_t arr_strides[3],
+                                           const int64_t shape[3], const int32_t stencil[3], uint64_t *out_host) {
+    SYK_CHECK_ARG(edges_host != nullptr && edge_strides != nullptr, "edges is NULL");
+    SYK_CHECK_ARG(edge_bytes == 1 || edge_bytes == 4, "edge_bytes must be 1 or 4");
+    return cs_host_impl(edges_host, edge_bytes, edge_strides, arr_host, elem_bytes, shape, arr_strides, stencil, out_host);
+}
+
+SYK_API int syk_detect_seg_boundaries_host(const void *arr_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                                           uint8_t *out_host) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    const uint64_t nvox = (uint64_t)shape[0] * shape[1] * shape[2];
+    if (nvox == 0) return SYK_OK;
+    rc = check_dense(shape, strides, 3);
+    if (rc) return rc;
+    DevBuf arr, out;
+    SYK_CUDA(cudaMalloc(&arr.p, nvox * elem_bytes));
+    SYK_CUDA(cudaMemcpy(arr.p, arr_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
+    SYK_CUDA(cudaMalloc(&out.p, nvox));
+    rc = syk_detect_seg_boundaries(arr.p, elem_bytes, shape, strides, (uint8_t *)out.p, nullptr);
+    if (rc) return rc;
+    SYK_CUDA(cudaMemcpy(out_host, out.p, nvox, cudaMemcpyDeviceToHost));
+    return SYK_OK;
+}

@@ -1,0 +1,425 @@
+// syk_table.cu -- device hash tables of per-id records / overlap pairs: create, clear, export, merge, bucket.
+// Replaces the reference's Python dict plumbing between chunks and workers:
+//   merge_prop_dicts  syconn/proc/sd_proc.py:1248-1273     -> syk_table_merge_records
+//   merge_map_dicts   syconn/proc/sd_proc.py:1300-1322     -> syk_pairs_merge
+//   id -> reducer hash  syconn/reps/rep_helper.py:143-163  -> syk_records_bucket / syk_pairs_bucket
+#include <stdarg.h>
+
+#include "syk_common.cuh"
+
+// ---- errors ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void syk_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int syk_require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        syk_set_error("no CUDA device available (%s); libsyk has no CPU fallback",
+                      e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return SYK_ENODEV;
+    }
+    return SYK_OK;
+}
+
+SYK_API int syk_version(void) { return SYK_VERSION; }
+SYK_API const char *syk_last_error(void) { return g_err; }
+SYK_API int syk_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+SYK_API int syk_set_device(int device) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CUDA(cudaSetDevice(device));
+    return SYK_OK;
+}
+SYK_API void syk_free(void *p) { free(p); }
+
+static uint64_t round_pow2(uint64_t c) {
+    uint64_t p = 1024;
+    while (p < c) p <<= 1;
+    return p;
+}
+
+// ---- id tables ------------------------------------------------------------------------------------------------
+SYK_API int syk_table_create(syk_table_t **out, uint64_t capacity) {
+    SYK_CHECK_ARG(out != nullptr, "out is NULL");
+    int rc = syk_require_device();
+    if (rc) return rc;
+    syk_table *t = (syk_table *)calloc(1, sizeof(syk_table));
+    if (!t) return SYK_ENOMEM;
+    t->capacity = round_pow2(capacity);
+    SYK_CUDA(cudaGetDevice(&t->device));
+    cudaError_t e = cudaMalloc(&t->slots, t->capacity * sizeof(SykSlot));
+    if (e != cudaSuccess) {
+        syk_set_error("cudaMalloc of %llu table slots failed: %s", (unsigned long long)t->capacity, cudaGetErrorString(e));
+        free(t);
+        return SYK_ENOMEM;
+    }
+    SYK_CUDA(cudaMalloc(&t->flags, 4 * sizeof(int)));
+    SYK_CUDA(cudaMalloc(&t->counter, 4 * sizeof(unsigned long long)));
+    SYK_CUDA(cudaMemset(t->slots, 0, t->capacity * sizeof(SykSlot)));
+    SYK_CUDA(cudaMemset(t->flags, 0, 4 * sizeof(int)));
+    SYK_CUDA(cudaMemset(t->counter, 0, 4 * sizeof(unsigned long long)));
+    *out = t;
+    return SYK_OK;
+}
+
+SYK_API int syk_table_destroy(syk_table_t *t) {
+    if (!t) return SYK_OK;
+    cudaFree(t->slots);
+    cudaFree(t->flags);
+    cudaFree(t->counter);
+    free(t);
+    return SYK_OK;
+}
+
+SYK_API uint64_t syk_table_capacity(const syk_table_t *t) { return t ? t->capacity : 0; }
+
+SYK_API int syk_table_clear(syk_table_t *t, void *stream) {
+    SYK_CHECK_ARG(t != nullptr, "table is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    SYK_CUDA(cudaMemsetAsync(t->slots, 0, t->capacity * sizeof(SykSlot), s));
+    SYK_CUDA(cudaMemsetAsync(t->flags, 0, 4 * sizeof(int), s));
+    return SYK_OK;
+}
+
+__global__ void k_table_count(const SykSlot *slots, uint64_t cap, unsigned long long *counter) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long n = 0;
+    for (; i < cap; i += (uint64_t)gridDim.x * blockDim.x) n += slots[i].key != 0ull;
+    for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, n);
+}
+
+SYK_API int syk_table_count(syk_table_t *t, void *stream, uint64_t *n_out, int *overflow_out) {
+    SYK_CHECK_ARG(t != nullptr, "table is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    SYK_CUDA(cudaMemsetAsync(t->counter, 0, sizeof(unsigned long long), s));
+    int blocks = (int)((t->capacity + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_table_count<<<blocks, 256, 0, s>>>(t->slots, t->capacity, t->counter);
+    unsigned long long n = 0;
+    int fl = 0;
+    SYK_CUDA(cudaMemcpyAsync(&n, t->counter, sizeof(n), cudaMemcpyDeviceToHost, s));
+    SYK_CUDA(cudaMemcpyAsync(&fl, t->flags, sizeof(fl), cudaMemcpyDeviceToHost, s));
+    SYK_CUDA(cudaStreamSynchronize(s));
+    if (n_out) *n_out = n;
+    if (overflow_out) *overflow_out = fl;
+    return SYK_OK;
+}
+
+__device__ __forceinline__ void decode_rep(syk_record_t &r, const syk_chunk_geom_t *geoms, uint32_t n_geoms) {
+    uint32_t seq = (uint32_t)(r.rep_key >> 40);
+    r.chunk_seq = seq;
+    if (geoms == nullptr || seq >= n_geoms) {
+        r.rep[0] = r.rep[1] = r.rep[2] = -1;
+        return;
+    }
+    const syk_chunk_geom_t g = geoms[seq];
+    unsigned long long lin = SYK_REP_MASK - (r.rep_key & SYK_REP_MASK);
+    unsigned long long z = lin % (unsigned long long)g.shape[2];
+    unsigned long long xy = lin / (unsigned long long)g.shape[2];
+    unsigned long long y = xy % (unsigned long long)g.shape[1];
+    unsigned long long x = xy / (unsigned long long)g.shape[1];
+    r.rep[0] = (int32_t)((long long)x + g.origin[0]);
+    r.rep[1] = (int32_t)((long long)y + g.origin[1]);
+    r.rep[2] = (int32_t)((long long)z + g.origin[2]);
+}
+
+__global__ void k_table_export(const SykSlot *slots, uint64_t cap, syk_record_t *out, unsigned long long max_out,
+                               unsigned long long *counter, const syk_chunk_geom_t *geoms, uint32_t n_geoms) {
+    uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    for (uint64_t base = i0 - lane; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = base + lane;
+        SykSlot s;
+        bool occ = false;
+        if (i < cap) {
+            s = slots[i];
+            occ = s.key != 0ull;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, occ);
+        if (!m) continue;
+        unsigned long long pos0 = 0;
+        if (lane == 0) pos0 = atomicAdd(counter, (unsigned long long)__popc(m));
+        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+        if (occ) {
+            unsigned long long pos = pos0 + __popc(m & ((1u << lane) - 1u));
+            if (pos < max_out) {
+                syk_record_t r;
+                r.id = s.key;
+                r.count = s.count;
+                r.rep_key = s.rep_enc - 1ull;
+                for (int a = 0; a < 3; ++a) {
+                    r.bb_min[a] = (int32_t)((0xFFFFFFFFu - s.min_enc[a]) - SYK_COORD_BIAS);
+                    r.bb_max[a] = (int32_t)(s.max_enc[a] - SYK_COORD_BIAS);
+                }
+                decode_rep(r, geoms, n_geoms);
+                out[pos] = r;
+            }
+        }
+    }
+}
+
+static int upload_geoms(const syk_chunk_geom_t *geoms_host, uint32_t n_geoms, cudaStream_t s, syk_chunk_geom_t **dev) {
+    *dev = nullptr;
+    if (!geoms_host || n_geoms == 0) return SYK_OK;
+    SYK_CUDA(cudaMallocAsync((void **)dev, sizeof(syk_chunk_geom_t) * n_geoms, s));
+    SYK_CUDA(cudaMemcpyAsync(*dev, geoms_host, sizeof(syk_chunk_geom_t) * n_geoms, cudaMemcpyHostToDevice, s));
+    return SYK_OK;
+}
+
+SYK_API int syk_table_export(syk_table_t *t, const syk_chunk_geom_t *geoms_host, uint32_t n_geoms, syk_record_t *records_dev,
+                             uint64_t max_records, uint64_t *n_out, void *stream) {
+    SYK_CHECK_ARG(t != nullptr, "table is NULL");
+    SYK_CHECK_ARG(records_dev != nullptr || max_records == 0, "records_dev is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    syk_chunk_geom_t *gd = nullptr;
+    int rc = upload_geoms(geoms_host, n_geoms, s, &gd);
+    if (rc) return rc;
+    SYK_CUDA(cudaMemsetAsync(t->counter, 0, sizeof(unsigned long long), s));
+    int blocks = (int)((t->capacity + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_table_export<<<blocks, 256, 0, s>>>(t->slots, t->capacity, records_dev, max_records, t->counter, gd, n_geoms);
+    SYK_CUDA(cudaGetLastError());
+    unsigned long long n = 0;
+    int fl = 0;
+    SYK_CUDA(cudaMemcpyAsync(&n, t->counter, sizeof(n), cudaMemcpyDeviceToHost, s));
+    SYK_CUDA(cudaMemcpyAsync(&fl, t->flags, sizeof(fl), cudaMemcpyDeviceToHost, s));
+    if (gd) SYK_CUDA(cudaFreeAsync(gd, s));
+    SYK_CUDA(cudaStreamSynchronize(s));
+    if (n_out) *n_out = n;
+    if (fl) {
+        syk_set_error("id table overflow (capacity %llu): retry with a larger capacity", (unsigned long long)t->capacity);
+        return SYK_EOVERFLOW;
+    }
+    if (n > max_records) {
+        syk_set_error("export buffer too small: %llu records, room for %llu", n, (unsigned long long)max_records);
+        return SYK_EOVERFLOW;
+    }
+    return SYK_OK;
+}
+
+__global__ void k_decode_rep(syk_record_t *recs, uint64_t n, const syk_chunk_geom_t *geoms, uint32_t n_geoms) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    syk_record_t r = recs[i];
+    decode_rep(r, geoms, n_geoms);
+    recs[i] = r;
+}
+
+SYK_API int syk_records_decode_rep(syk_record_t *records_dev, uint64_t n, const syk_chunk_geom_t *geoms_host, uint32_t n_geoms,
+                                   void *stream) {
+    if (n == 0) return SYK_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    syk_chunk_geom_t *gd = nullptr;
+    int rc = upload_geoms(geoms_host, n_geoms, s, &gd);
+    if (rc) return rc;
+    k_decode_rep<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(records_dev, n, gd, n_geoms);
+    SYK_CUDA(cudaGetLastError());
+    if (gd) SYK_CUDA(cudaFreeAsync(gd, s));
+    return SYK_OK;
+}
+
+__global__ void k_merge_records(TableView t, const syk_record_t *recs, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const syk_record_t r = recs[i];
+    if (r.id == 0ull) return;
+    syk_table_update(t, r.id, r.count, r.rep_key, r.bb_min[0], r.bb_min[1], r.bb_min[2], r.bb_max[0], r.bb_max[1],
+                     r.bb_max[2]);
+}
+
+SYK_API int syk_table_merge_records(syk_table_t *t, const syk_record_t *records_dev, uint64_t n, void *stream) {
+    SYK_CHECK_ARG(t != nullptr, "table is NULL");
+    if (n == 0) return SYK_OK;
+    k_merge_records<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(view_of(t), records_dev, n);
+    SYK_CUDA(cudaGetLastError());
+    return SYK_OK;
+}
+
+// ---- bucketing by owner (for the hash-owner all-to-all) ------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ uint64_t owner_key(const R &r);
+template <>
+__device__ __forceinline__ uint64_t owner_key<syk_record_t>(const syk_record_t &r) { return r.id; }
+template <>
+__device__ __forceinline__ uint64_t owner_key<syk_pair_t>(const syk_pair_t &r) { return r.sub_id; }
+
+__host__ __device__ __forceinline__ uint32_t syk_owner_of(uint64_t id, uint32_t n_owners) {
+    return (uint32_t)((syk_mix64(id ^ 0x5bd1e9955bd1e995ULL) >> 20) % n_owners);
+}
+
+template <typename R>
+__global__ void k_bucket_count(const R *recs, uint64_t n, uint32_t n_owners, unsigned long long *counts) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    atomicAdd(&counts[syk_owner_of(owner_key(recs[i]), n_owners)], 1ull);
+}
+// counts[0..n) -> cursors[0..n) = exclusive prefix
+__global__ void k_bucket_scan(const unsigned long long *counts, unsigned long long *cursors, uint32_t n_owners) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (uint32_t o = 0; o < n_owners; ++o) {
+            cursors[o] = acc;
+            acc += counts[o];
+        }
+    }
+}
+template <typename R>
+__global__ void k_bucket_scatter(const R *recs, uint64_t n, uint32_t n_owners, unsigned long long *cursors, R *out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const R r = recs[i];
+    unsigned long long pos = atomicAdd(&cursors[syk_owner_of(owner_key(r), n_owners)], 1ull);
+    out[pos] = r;
+}
+
+template <typename R>
+static int bucket_impl(const R *recs, uint64_t n, uint32_t n_owners, R *out, uint64_t *counts_dev, cudaStream_t s) {
+    SYK_CHECK_ARG(n_owners >= 1 && n_owners <= 4096, "n_owners out of range");
+    SYK_CHECK_ARG(counts_dev != nullptr, "counts_dev is NULL");
+    SYK_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(uint64_t) * n_owners, s));
+    if (n == 0) return SYK_OK;
+    unsigned long long *cursors = nullptr;
+    SYK_CUDA(cudaMallocAsync((void **)&cursors, sizeof(unsigned long long) * n_owners, s));
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    k_bucket_count<R><<<blocks, 256, 0, s>>>(recs, n, n_owners, (unsigned long long *)counts_dev);
+    k_bucket_scan<<<1, 32, 0, s>>>((unsigned long long *)counts_dev, cursors, n_owners);
+    k_bucket_scatter<R><<<blocks, 256, 0, s>>>(recs, n, n_owners, cursors, out);
+    SYK_CUDA(cudaGetLastError());
+    SYK_CUDA(cudaFreeAsync(cursors, s));
+    return SYK_OK;
+}
+
+SYK_API int syk_records_bucket(const syk_record_t *records_dev, uint64_t n, uint32_t n_owners, syk_record_t *out_dev,
+                               uint64_t *counts_dev, void *stream) {
+    return bucket_impl<syk_record_t>(records_dev, n, n_owners, out_dev, counts_dev, (cudaStream_t)stream);
+}
+SYK_API int syk_pairs_bucket(const syk_pair_t *pairs_dev, uint64_t n, uint32_t n_owners, syk_pair_t *out_dev,
+                             uint64_t *counts_dev, void *stream) {
+    return bucket_impl<syk_pair_t>(pairs_dev, n, n_owners, out_dev, counts_dev, (cudaStream_t)stream);
+}
+
+// ---- pair tables ------------------------------------------------------------------------------------------------
+SYK_API int syk_pairs_create(syk_pairs_t **out, uint64_t capacity) {
+    SYK_CHECK_ARG(out != nullptr, "out is NULL");
+    int rc = syk_require_device();
+    if (rc) return rc;
+    syk_pairs *t = (syk_pairs *)calloc(1, sizeof(syk_pairs));
+    if (!t) return SYK_ENOMEM;
+    t->capacity = round_pow2(capacity);
+    SYK_CUDA(cudaGetDevice(&t->device));
+    cudaError_t e = cudaMalloc(&t->slots, t->capacity * sizeof(SykPairSlot));
+    if (e != cudaSuccess) {
+        syk_set_error("cudaMalloc of %llu pair slots failed: %s", (unsigned long long)t->capacity, cudaGetErrorString(e));
+        free(t);
+        return SYK_ENOMEM;
+    }
+    SYK_CUDA(cudaMalloc(&t->flags, 4 * sizeof(int)));
+    SYK_CUDA(cudaMalloc(&t->counter, 4 * sizeof(unsigned long long)));
+    SYK_CUDA(cudaMemset(t->slots, 0, t->capacity * sizeof(SykPairSlot)));
+    SYK_CUDA(cudaMemset(t->flags, 0, 4 * sizeof(int)));
+    *out = t;
+    return SYK_OK;
+}
+SYK_API int syk_pairs_destroy(syk_pairs_t *t) {
+    if (!t) return SYK_OK;
+    cudaFree(t->slots);
+    cudaFree(t->flags);
+    cudaFree(t->counter);
+    free(t);
+    return SYK_OK;
+}
+SYK_API int syk_pairs_clear(syk_pairs_t *t, void *stream) {
+    SYK_CHECK_ARG(t != nullptr, "pair table is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    SYK_CUDA(cudaMemsetAsync(t->slots, 0, t->capacity * sizeof(SykPairSlot), s));
+    SYK_CUDA(cudaMemsetAsync(t->flags, 0, 4 * sizeof(int), s));
+    return SYK_OK;
+}
+
+__global__ void k_pairs_export(const SykPairSlot *slots, uint64_t cap, syk_pair_t *out, unsigned long long max_out,
+                               unsigned long long *counter) {
+    uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31;
+    for (uint64_t base = i0 - lane; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t i = base + lane;
+        SykPairSlot s;
+        bool occ = false;
+        if (i < cap) {
+            s = slots[i];
+            occ = s.sub != 0ull;
+        }
+        unsigned m = __ballot_sync(0xffffffffu, occ);
+        if (!m) continue;
+        unsigned long long pos0 = 0;
+        if (lane == 0) pos0 = atomicAdd(counter, (unsigned long long)__popc(m));
+        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+        if (occ) {
+            unsigned long long pos = pos0 + __popc(m & ((1u << lane) - 1u));
+            if (pos < max_out) {
+                syk_pair_t r;
+                r.sub_id = s.sub;
+                r.cell_id = s.cell;
+                r.count = s.count;
+                r._pad = 0;
+                out[pos] = r;
+            }
+        }
+    }
+}
+
+SYK_API int syk_pairs_export(syk_pairs_t *t, syk_pair_t *pairs_dev, uint64_t max_pairs, uint64_t *n_out, void *stream) {
+    SYK_CHECK_ARG(t != nullptr, "pair table is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    SYK_CUDA(cudaMemsetAsync(t->counter, 0, sizeof(unsigned long long), s));
+    int blocks = (int)((t->capacity + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_pairs_export<<<blocks, 256, 0, s>>>(t->slots, t->capacity, pairs_dev, max_pairs, t->counter);
+    SYK_CUDA(cudaGetLastError());
+    unsigned long long n = 0;
+    int fl = 0;
+    SYK_CUDA(cudaMemcpyAsync(&n, t->counter, sizeof(n), cudaMemcpyDeviceToHost, s));
+    SYK_CUDA(cudaMemcpyAsync(&fl, t->flags, sizeof(fl), cudaMemcpyDeviceToHost, s));
+    SYK_CUDA(cudaStreamSynchronize(s));
+    if (n_out) *n_out = n;
+    if (fl) {
+        syk_set_error("pair table overflow (capacity %llu): retry with a larger capacity", (unsigned long long)t->capacity);
+        return SYK_EOVERFLOW;
+    }
+    if (n > max_pairs) {
+        syk_set_error("pair export buffer too small: %llu pairs, room for %llu", n, (unsigned long long)max_pairs);
+        return SYK_EOVERFLOW;
+    }
+    return SYK_OK;
+}
+
+__global__ void k_pairs_merge(PairView t, const syk_pair_t *p, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const syk_pair_t r = p[i];
+    if (r.sub_id == 0ull || r.cell_id == 0ull) return;
+    syk_pairs_update(t, r.sub_id, r.cell_id, r.count);
+}
+
+SYK_API int syk_pairs_merge(syk_pairs_t *t, const syk_pair_t *pairs_dev, uint64_t n, void *stream) {
+    SYK_CHECK_ARG(t != nullptr, "pair table is NULL");
+    if (n == 0) return SYK_OK;
+    k_pairs_merge<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(view_of(t), pairs_dev, n);
+    SYK_CUDA(cudaGetLastError());
+    return SYK_OK;
+}
