@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- GVoxels/s of the chunked label-volume extraction hot path (contact sites + object properties +
+organelle->cell mapping) on N B200s, next to the reference's CPU path timed on the same box.
+
+  python bench.py --gpus 1 --steps 3 --warmup 3             (our arm; under torchrun for N > 1)
+  python bench.py --impl reference --gpus 1 --steps 1       (the reference's own Cython code on the host cores)
+
+A step = one pass of the three stages over this rank's chunks (default 8 chunks of 512^3 per GPU = the per-GPU
+share of BASELINE config 4, "full chunked 2048^3 dataset ... sharded across 8 B200"), followed by the hash-owner
+all-to-all of the per-id partial records and the owner-side reduce.  Weak scaling: per-GPU work is fixed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STENCIL = (13, 13, 7)          # syconn/handler/config.yml:148
+CELL_PITCH = (32, 32, 16)      # synthetic supervoxel pitch (voxels); ~22 % boundary voxels with warp 4
+ORG_PITCH = (12, 12, 6)        # organelle blob pitch; density 1/16 foreground per channel
+N_SUB = 3                      # mi, vc, sj
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunk", type=int, default=512, help="chunk edge length (voxels)")
+    ap.add_argument("--chunks-per-gpu", type=int, default=8)
+    ap.add_argument("--e2e-chunks", type=int, default=2, help="chunks per step of the host-buffer (e2e) measurement")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _cpu_block(args):
+    """One sample block through the reference's CPU path: detect_cs -> find_object_properties(contacts) ->
+    map_subcell_extract_props (the per-chunk work of cs_extraction_steps.py:385-439 and sd_proc.py:646)."""
+    seq, edge, use_ref = args
+    sys.path.insert(0, ROOT)
+    from oracle import oracle
+    from syconn_b200.synth import synth_labels
+    if use_ref:
+        from oracle import ref as impl
+    else:
+        impl = oracle
+    so = [s // 2 for s in STENCIL]
+    origin = (seq * edge, 0, 0)
+    halo = synth_labels([edge + 2 * s for s in so], [origin[i] - so[i] for i in range(3)], CELL_PITCH, 4, 0, 0,
+                        dtype=np.uint32, order="F")
+    cell = synth_labels((edge,) * 3, origin, CELL_PITCH, 4, 0, 0, order="F")
+    subs = np.stack([synth_labels((edge,) * 3, origin, ORG_PITCH, 4, 0, 1 + c, 1, order="F").transpose(2, 1, 0)
+                     for c in range(N_SUB)]).transpose(0, 3, 2, 1)
+    t0 = time.perf_counter()
+    edges = oracle.detect_seg_boundaries(halo).astype(np.uint32)   # numba in the reference; C restatement here
+    contacts = np.asarray(impl.process_block_nonzero(edges, halo, STENCIL))
+    impl.find_object_properties(contacts)
+    impl.map_subcell_extract_props(cell, subs)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(budget_s, edge=64):
+    """Reference CPU path on all host cores, driven like the reference's non-SLURM fan-out
+    (start_multiprocess_imap, syconn/mp/mp_utils.py:138-200): a process pool with one block per task."""
+    from concurrent.futures import ProcessPoolExecutor
+    from oracle import oracle, ref
+    oracle.build()
+    use_ref = ref.available()
+    cores = os.cpu_count() or 1
+    t1 = _cpu_block((0, edge, use_ref))                 # calibrate (also warms the page cache)
+    per_core = max(1, int(budget_s / max(t1, 1e-3)))
+    n_blocks = cores * min(per_core, 64)
+    t0 = time.perf_counter()
+    with ProcessPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(_cpu_block, [(i, edge, use_ref) for i in range(n_blocks)], chunksize=1))
+    wall = time.perf_counter() - t0
+    vox = n_blocks * edge ** 3
+    return dict(value=vox / wall / 1e9, unit="GVoxels/s", cores=cores, kind="reference" if use_ref else "port",
+                sample=f"{n_blocks} blocks of {edge}^3 voxels (+{STENCIL} halo) through detect_cs + "
+                       f"find_object_properties(contacts) + map_subcell_extract_props(C={N_SUB}); same synthetic "
+                       f"generator as the GPU arm; {wall:.1f} s wall on {cores} processes"), wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(max(1, args.warmup and 0)):
+        pass
+    per_step = max(2.0, min(args.cpu_seconds, 60.0 / max(1, args.steps)))
+    cb = None
+    for _ in range(max(1, args.steps)):
+        cb, wall = cpu_baseline(per_step)
+        vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = v
+    line = {"metric": "GVoxels/s contact-site+property extraction", "impl": "reference", "value": v, "unit": "GVoxels/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": (time.perf_counter() - t0) * 1e3 / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "timing": "wall clock of a bounded sample on host cores"},
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": "GVoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"chunked extraction, {args.chunks_per_gpu} chunks of {args.chunk}^3 per GPU "
+            f"(= 2048^3 over 8 GPUs at the defaults): detect_cs stencil {list(STENCIL)} on uint32 haloed chunks, "
+            f"find_object_properties on the contact volume, map_subcell_extract_props with {N_SUB} organelle channels "
+            f"on uint64 chunks, per-id merge")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (NVML in-process; nvidia-smi as fallback)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], False
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES ordering when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        if nv is not None:
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            names = []
+            for n, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                           ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                           ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                           ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):
+                if r & bit:
+                    names.append(n)
+            return float(sm), float(mx), names
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        c = [x.strip() for x in out.strip().split(",")]
+        names = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:6])
+                 if v.lower().startswith("active")]
+        return float(c[0]), float(c[1]), names
+
+    def _run(self):
+        while not self.stop:
+            try:
+                self.rows.append(self._sample())
+            except Exception:
+                pass
+            time.sleep(0.02 if self.nv is not None else 0.5)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        reasons = sorted(set(n for r in self.rows for n in r[2]))
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nv is not None else "nvidia-smi"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from syconn_b200 import device as dev
+    from syconn_b200.chunked import ChunkPlan, ExtractionPipeline, cs_halo_geometry
+    from syconn_b200._lib import GEOM_DTYPE
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    E, cpg = args.chunk, args.chunks_per_gpu
+    # global volume: world*cpg chunks laid out as an (nx, 2, 2)-ish grid; 8 GPUs x 8 chunks = 4x4x4 of 512^3 = 2048^3
+    total = world * cpg
+    g = [1, 1, 1]
+    a = 2
+    while g[0] * g[1] * g[2] < total:
+        g[a] *= 2
+        a = (a - 1) % 3
+    plan = ChunkPlan((g[0] * E, g[1] * E, g[2] * E), (E, E, E))
+    mine = plan.chunks_of_rank(rank, world)[:cpg]
+    geoms = {"cell": np.zeros(len(plan), GEOM_DTYPE), "cs": np.zeros(len(plan), GEOM_DTYPE)}
+    for s in range(len(plan)):
+        lo, ls, oo, os_ = cs_halo_geometry(plan.offsets[s], plan.sizes[s], STENCIL)
+        geoms["cell"][s] = (plan.offsets[s], plan.sizes[s])
+        geoms["cs"][s] = (oo, os_)
+
+    # ---- inputs resident in HBM before the timed region (production layout: x fastest in memory) ----
+    chunks = []
+    for s in mine:
+        off, size = plan.offsets[s], plan.sizes[s]
+        lo, ls, _, _ = cs_halo_geometry(off, size, STENCIL)
+        cell = dev.synth_labels(size, off, CELL_PITCH, 4, 0, 0, order="F")
+        subs = torch.empty((N_SUB,) + tuple(size[::-1]), dtype=torch.int64, device="cuda").permute(0, 3, 2, 1)
+        for c in range(N_SUB):
+            dev.synth_labels(size, off, ORG_PITCH, 4, 0, 1 + c, 1, out=subs[c])
+        halo = dev.synth_labels(ls, lo, CELL_PITCH, 4, 0, 0, dtype=torch.int32, order="F")
+        chunks.append((s, off, cell, subs, halo))
+    torch.cuda.synchronize()
+    in_bytes = sum(c[2].numel() * 8 + c[3].numel() * 8 + c[4].numel() * 4 for c in chunks)
+
+    pipe = ExtractionPipeline(N_SUB, STENCIL, chunk_table_capacity=1 << 18, log_capacity=max(1 << 20, cpg << 17),
+                              pair_log_capacity=max(1 << 20, cpg << 17), rank=rank, world=world)
+    cs_events = []
+
+    def step(timed):
+        pipe.reset()
+        pipe.cs_events = cs_events if timed else None   # dominant kernel: bracket every k_detect_cs launch
+        for (s, off, cell, subs, halo) in chunks:
+            pipe.process_chunk(s, off, cell, subs, halo)
+        owned, owned_pairs = pipe.finish()
+        return pipe.reduce_on_device(owned, owned_pairs, geoms)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        res = step(False)
+    barrier()
+    with ClockSampler(local) as clk:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            res = step(True)
+        t1.record()
+        barrier()
+        ms = t0.elapsed_time(t1)
+    launches = pipe.launches
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    vox_per_step = sum(int(np.prod(c[2].shape)) for c in chunks) * world
+    value = vox_per_step / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (detect_cs), live CUDA-event durations from the timed region ----
+    cs_ms = [a.elapsed_time(b) for a, b in cs_events]
+    halo0 = chunks[0][4]
+    out_vox = int(np.prod([halo0.shape[i] - STENCIL[i] + 1 for i in range(3)]))
+    alg_bytes = halo0.numel() * 4 + out_vox * 8            # 4 B read (uint32) + 8 B write per voxel
+    avg_ms = float(np.mean(cs_ms))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_detect_cs (fused detect_seg_boundaries + process_block_nonzero)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
+                "share_of_step": float(np.sum(cs_ms)) / ms}
+
+    line = {"metric": "GVoxels/s contact-site+property extraction", "value": value, "unit": "GVoxels/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "chunks_per_gpu": cpg, "chunk": E,
+                       "volume": list(plan.volume_shape), "cell_pitch": list(CELL_PITCH), "layout": "x fastest (ZYX memory)",
+                       "l2": f"inputs per step {in_bytes / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
+                       "objects": {k: int(v.shape[0]) for k, v in res[0].items()}},
+            "clocks": clk.summary(), "roofline": roofline, "gpu_launches": int(launches)}
+
+    if rank == 0 and world == 1 and not args.no_e2e:
+        line["e2e"] = e2e_host(args, chunks)
+    elif rank == 0:
+        line["e2e"] = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"], _ = cpu_baseline(args.cpu_seconds)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def e2e_host(args, chunks):
+    """Same stages through the reference-facing C-ABI *_host entry points with HOST buffers: every call uploads its
+    inputs and downloads its results inside the timed region."""
+    import torch
+    from syconn_b200.extraction import _host
+    from syconn_b200.extraction.find_object_properties import detect_cs
+    n = min(args.e2e_chunks, len(chunks))
+    host = []
+    for (s, off, cell, subs, halo) in chunks[:n]:
+        host.append((cell.cpu().numpy().view(np.uint64), subs.cpu().numpy().view(np.uint64), halo.cpu().numpy().view(np.uint32)))
+    h2d = d2h = 0
+
+    def one_pass():
+        nonlocal h2d, d2h
+        h2d = d2h = 0
+        for cell, subs, halo in host:
+            contacts = detect_cs(halo, STENCIL)
+            h2d += halo.nbytes
+            d2h += contacts.nbytes
+            r = _host.find_object_properties_records(contacts)
+            h2d += contacts.nbytes
+            d2h += r.nbytes
+            cr, sr, pr = _host.map_subcell_records(cell, subs)
+            h2d += cell.nbytes + subs.nbytes
+            d2h += cr.nbytes + sum(x.nbytes for x in sr) + sum(x.nbytes for x in pr)
+    one_pass()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = max(1, min(args.steps, 3))
+    for _ in range(reps):
+        one_pass()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    vox = sum(int(c[0].size) for c in host)
+    return {"value": vox / dt / 1e9, "unit": "GVoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "chunks_per_step": n, "api": "syk_detect_cs_host + syk_find_object_properties_host + "
+                                        "syk_map_subcell_extract_props_host (pageable host buffers)"}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

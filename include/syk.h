@@ -87,6 +87,11 @@ int syk_table_count(syk_table_t *t, void *stream, uint64_t *n_out_host, int *ove
  * geoms_host[n_geoms] is indexed by chunk_seq to decode rep.  Synchronises `stream`. */
 int syk_table_export(syk_table_t *t, const syk_chunk_geom_t *geoms_host, uint32_t n_geoms, syk_record_t *records_dev,
                      uint64_t max_records, uint64_t *n_out_host, void *stream);
+/* Asynchronous variant for chunk loops: appends the table's records to a device log at position *counter_dev
+ * (a device uint64 that accumulates across calls; records beyond max_records are dropped but still counted, so
+ * the host can detect a short log).  geom is the calling chunk's geometry (one entry, indexed by any chunk_seq). */
+int syk_table_append_records(syk_table_t *t, const syk_chunk_geom_t *geom_host, syk_record_t *log_dev, uint64_t max_records,
+                             uint64_t *counter_dev, void *stream);
 /* fold records into a table: count summed, bbox min/max, rep = max rep_key
  * (merge_prop_dicts + final reduction, syconn/proc/sd_proc.py:1248-1273, :939-945, :1172-1177) */
 int syk_table_merge_records(syk_table_t *t, const syk_record_t *records_dev, uint64_t n, void *stream);
@@ -101,6 +106,7 @@ int syk_pairs_create(syk_pairs_t **out, uint64_t capacity);
 int syk_pairs_destroy(syk_pairs_t *t);
 int syk_pairs_clear(syk_pairs_t *t, void *stream);
 int syk_pairs_export(syk_pairs_t *t, syk_pair_t *pairs_dev, uint64_t max_pairs, uint64_t *n_out_host, void *stream);
+int syk_pairs_append(syk_pairs_t *t, syk_pair_t *log_dev, uint64_t max_pairs, uint64_t *counter_dev, void *stream);
 /* merge_map_dicts (syconn/proc/sd_proc.py:1300-1322): counts summed per (sub_id, cell_id) */
 int syk_pairs_merge(syk_pairs_t *t, const syk_pair_t *pairs_dev, uint64_t n, void *stream);
 /* owner = hash(sub_id) mod n_owners (the reference reduces per organelle object, sd_proc.py:830-853) */

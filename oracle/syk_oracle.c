@@ -68,7 +68,7 @@ ORC_API int orc_detect_seg_boundaries(const void *arr, int elem_bytes, const int
  * = the caller-side .astype(np.uint32) of extraction/cs_extraction_steps.py:385-387).
  * out: C-contiguous uint64 [X-sx+1, Y-sy+1, Z-sz+1].
  * ------------------------------------------------------------------------------------------ */
-#define WTAB 4096 /* > 2 * max supported window (17*17*7=2023) */
+#define WTAB 16384 /* > 2 * max supported window (e.g. 21*21*9 = 3969) */
 typedef struct { uint32_t key; int32_t cnt; uint32_t stamp; } wslot_t;
 
 ORC_API int orc_process_block_nonzero(const void *edges, int edge_bytes, const int64_t est[3],
@@ -99,7 +99,7 @@ ORC_API int orc_process_block_nonzero(const void *edges, int edge_bytes, const i
                             const int64_t b = (x + i) * ast[0] + (y + j) * ast[1] + z * ast[2];
                             for (int k = 0; k < sz; ++k) {
                                 const uint32_t id = (uint32_t)ld_label(arr, elem_bytes, b + k * ast[2]);
-                                uint32_t h = (uint32_t)(id * 2654435761u) >> 20; /* 12 bits */
+                                uint32_t h = (uint32_t)(id * 2654435761u) >> 18; /* 14 bits */
                                 for (;;) {
                                     wslot_t *s = &tab[h];
                                     if (s->stamp != stamp) { s->stamp = stamp; s->key = id; s->cnt = 1; touched[nt++] = h; break; }

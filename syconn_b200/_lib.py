@@ -23,8 +23,8 @@ assert RECORD_DTYPE.itemsize == 64 and PAIR_DTYPE.itemsize == 32 and GEOM_DTYPE.
 EXPORTS = [
     "syk_version", "syk_last_error", "syk_device_count", "syk_set_device",
     "syk_table_create", "syk_table_destroy", "syk_table_clear", "syk_table_capacity", "syk_table_count",
-    "syk_table_export", "syk_table_merge_records", "syk_records_bucket", "syk_records_decode_rep",
-    "syk_pairs_create", "syk_pairs_destroy", "syk_pairs_clear", "syk_pairs_export", "syk_pairs_merge",
+    "syk_table_export", "syk_table_append_records", "syk_table_merge_records", "syk_records_bucket", "syk_records_decode_rep",
+    "syk_pairs_create", "syk_pairs_destroy", "syk_pairs_clear", "syk_pairs_export", "syk_pairs_append", "syk_pairs_merge",
     "syk_pairs_bucket",
     "syk_find_object_properties", "syk_map_subcell_extract_props", "syk_detect_seg_boundaries",
     "syk_process_block_nonzero", "syk_detect_cs", "syk_synth_labels",
@@ -64,6 +64,8 @@ def load():
     L.syk_table_capacity.restype = u64
     L.syk_table_count.argtypes = [vp, vp, u64p, C.POINTER(ci)]
     L.syk_table_export.argtypes = [vp, vp, u32, vp, u64, u64p, vp]
+    L.syk_table_append_records.argtypes = [vp, vp, vp, u64, vp, vp]
+    L.syk_pairs_append.argtypes = [vp, vp, u64, vp, vp]
     L.syk_table_merge_records.argtypes = [vp, vp, u64, vp]
     L.syk_records_bucket.argtypes = [vp, u64, u32, vp, vp, vp]
     L.syk_records_decode_rep.argtypes = [vp, u64, vp, u32, vp]

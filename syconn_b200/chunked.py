@@ -1,0 +1,253 @@
+"""Chunked dataset extraction on one or several GPUs (one process per GPU).
+
+Replaces, for the hot path only, the reference's map/reduce plumbing:
+
+  * chunk list split across workers           syconn/proc/sd_proc.py:360-366, extraction/cs_extraction_steps.py:199-203
+  * per-chunk kernels + per-worker dict merge  syconn/proc/sd_proc.py:579-684, cs_extraction_steps.py:376-486
+  * reducers partitioned by an id hash         syconn/reps/rep_helper.py:143-163, sd_proc.py:511-556
+
+Every rank runs its chunks through libsyk, keeps the per-(id, chunk) records in a device log, buckets them by
+``owner = hash(id) mod world`` (organelle id for overlap pairs) and exchanges the buckets with one all-to-all
+(NCCL over NVLink; gloo on CPU for tests).  The owner folds the received records with the reference's merge
+semantics (size summed, bbox min/max, per-chunk bbox list kept in chunk order, rep_coord of the last chunk).
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._lib import GEOM_DTYPE, PAIR_DTYPE, RECORD_DTYPE
+
+
+# ------------------------------------------------------------------------------------------------ chunk plan
+@dataclass
+class ChunkPlan:
+    """Chunk grid of a volume; chunk ``seq`` numbers follow the reference's chunk list order (x slowest)."""
+    volume_shape: Tuple[int, int, int]
+    chunk_size: Tuple[int, int, int] = (512, 512, 512)
+    offsets: List[Tuple[int, int, int]] = field(default_factory=list)
+    sizes: List[Tuple[int, int, int]] = field(default_factory=list)
+
+    def __post_init__(self):
+        if not self.offsets:
+            vs, cs = self.volume_shape, self.chunk_size
+            for x in range(0, vs[0], cs[0]):
+                for y in range(0, vs[1], cs[1]):
+                    for z in range(0, vs[2], cs[2]):
+                        self.offsets.append((x, y, z))
+                        self.sizes.append((min(cs[0], vs[0] - x), min(cs[1], vs[1] - y), min(cs[2], vs[2] - z)))
+
+    def __len__(self):
+        return len(self.offsets)
+
+    def chunks_of_rank(self, rank: int, world: int) -> List[int]:
+        """Contiguous block partition (``chunkify_successive``, sd_proc.py:366): neighbouring chunks stay on one GPU."""
+        n = len(self)
+        base, rem = divmod(n, world)
+        start = rank * base + min(rank, rem)
+        return list(range(start, start + base + (1 if rank < rem else 0)))
+
+
+def cs_halo_geometry(offset, size, stencil=(13, 13, 7)):
+    """Geometry of the contact-site call of one chunk (cs_extraction_steps.py:376-391): the loaded block is
+    ``size + 2*overlap + 2*stencil_offset`` at ``offset - overlap - stencil_offset``; detect_cs returns the
+    ``size + 2*overlap`` block at ``offset - overlap`` (overlap = max(stencil // 2))."""
+    so = [s // 2 for s in stencil]
+    overlap = max(so)
+    load_off = [offset[i] - overlap - so[i] for i in range(3)]
+    load_size = [size[i] + 2 * overlap + 2 * so[i] for i in range(3)]
+    out_off = [offset[i] - overlap for i in range(3)]
+    out_size = [size[i] + 2 * overlap for i in range(3)]
+    return load_off, load_size, out_off, out_size
+
+
+# ------------------------------------------------------------------------------------------------ exchange
+def exchange_buckets(bucketed: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
+    """Hash-owner all-to-all: ``bucketed`` [n, k] holds this rank's rows grouped per destination rank
+    (``counts[d]`` rows for rank d, in rank order).  Returns the rows this rank owns (from all ranks)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return bucketed
+    counts = [int(c) for c in counts]
+    assert len(counts) == world and sum(counts) == bucketed.shape[0]
+    send_counts = torch.tensor(counts, dtype=torch.int64, device=bucketed.device)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    recv = [int(c) for c in recv_counts.tolist()]
+    out = torch.empty((sum(recv), bucketed.shape[1]), dtype=bucketed.dtype, device=bucketed.device)
+    dist.all_to_all_single(out, bucketed.contiguous(), output_split_sizes=recv, input_split_sizes=counts, group=group)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ host-side reductions
+def reduce_records(log: np.ndarray):
+    """Fold a per-(id, chunk) record log with the reference's merge semantics (sd_proc.py:1248-1273 and the final
+    reduction :939-945): returns a dict of arrays ``id, size, bounding_box [N,2,3] int32, rep_coord [N,3] int32``
+    plus the per-object voxel index ``bbs`` (list of [n_chunks_i, 2, 3] arrays, chunk order)."""
+    if len(log) == 0:
+        return dict(id=np.empty(0, np.uint64), size=np.empty(0, np.int64), bounding_box=np.empty((0, 2, 3), np.int32),
+                    rep_coord=np.empty((0, 3), np.int32), bbs=[])
+    o = np.lexsort((log["chunk_seq"], log["id"]))
+    log = log[o]
+    ids, start = np.unique(log["id"], return_index=True)
+    end = np.append(start[1:], len(log))
+    size = np.add.reduceat(log["count"].astype(np.int64), start)
+    bmin = np.minimum.reduceat(log["bb_min"], start, axis=0)
+    bmax = np.maximum.reduceat(log["bb_max"], start, axis=0)
+    rep = log["rep"][end - 1]  # last chunk wins (dict.update, sd_proc.py:1261)
+    bb_all = np.stack([log["bb_min"], log["bb_max"]], axis=1)
+    bbs = [bb_all[s:e] for s, e in zip(start, end)]
+    return dict(id=ids, size=size, bounding_box=np.stack([bmin, bmax], axis=1).astype(np.int32),
+                rep_coord=rep.astype(np.int32), bbs=bbs)
+
+
+def reduce_pairs(log: np.ndarray):
+    """merge_map_dicts (sd_proc.py:1300-1322) on a pair log -> sorted (sub_id, cell_id, count) arrays."""
+    if len(log) == 0:
+        return dict(sub_id=np.empty(0, np.uint64), cell_id=np.empty(0, np.uint64), count=np.empty(0, np.int64))
+    o = np.lexsort((log["cell_id"], log["sub_id"]))
+    log = log[o]
+    key_change = np.ones(len(log), bool)
+    key_change[1:] = (log["sub_id"][1:] != log["sub_id"][:-1]) | (log["cell_id"][1:] != log["cell_id"][:-1])
+    start = np.flatnonzero(key_change)
+    return dict(sub_id=log["sub_id"][start], cell_id=log["cell_id"][start],
+                count=np.add.reduceat(log["count"].astype(np.int64), start))
+
+
+# ------------------------------------------------------------------------------------------------ device pipeline
+class ExtractionPipeline:
+    """Per-rank driver of the three hot-path stages over this rank's chunks (device-resident inputs)."""
+
+    def __init__(self, n_sub: int, stencil=(13, 13, 7), chunk_table_capacity=1 << 18, log_capacity=1 << 21,
+                 pair_log_capacity=1 << 21, rank=0, world=1, group=None):
+        from . import device as dev
+        self.dev = dev
+        self.n_sub, self.stencil, self.rank, self.world, self.group = n_sub, tuple(stencil), rank, world, group
+        self.t_cell = dev.IdTable(chunk_table_capacity)
+        self.t_cs = dev.IdTable(chunk_table_capacity)
+        self.t_sub = [dev.IdTable(chunk_table_capacity) for _ in range(n_sub)]
+        self.t_pair = [dev.PairTable(chunk_table_capacity) for _ in range(n_sub)]
+        self.kinds = ["cell", "cs"] + [f"sub{c}" for c in range(n_sub)]
+        self.log_capacity, self.pair_log_capacity = log_capacity, pair_log_capacity
+        self.logs = {k: torch.empty((log_capacity, 8), dtype=torch.int64, device="cuda") for k in self.kinds}
+        self.pair_logs = [torch.empty((pair_log_capacity, 4), dtype=torch.int64, device="cuda") for _ in range(n_sub)]
+        # one device counter per log (+ pair logs)
+        self.counters = torch.zeros(len(self.kinds) + n_sub, dtype=torch.int64, device="cuda")
+        self.cs_out = None
+        self.launches = 0
+        self._final = {}
+        self.cs_events = None  # set to a list to collect (start, end) CUDA events around every detect_cs launch
+
+    def reset(self):
+        self.counters.zero_()
+        self.launches = 0
+
+    def _append(self, table, kind_idx, log, origin, shape):
+        L = self.dev._lib.load()
+        g = np.zeros(1, GEOM_DTYPE)
+        g["origin"][0] = origin
+        g["shape"][0] = shape
+        self.dev.check(L.syk_table_append_records(table.h, g.ctypes.data, log.data_ptr(), log.shape[0],
+                                                  self.counters[kind_idx:].data_ptr(), self.dev._stream_ptr()))
+        self.launches += 1
+
+    def process_chunk(self, seq, offset, cell, subcell, cell_halo):
+        """One chunk: ``cell`` [X,Y,Z] and ``subcell`` [C,X,Y,Z] 64-bit labels at ``offset``; ``cell_halo`` the
+        uint32 block of cs_halo_geometry (or None to skip contact sites)."""
+        dev, L = self.dev, self.dev._lib.load()
+        # stage 1: contact sites + their properties (cs_extraction_steps.py:391,439)
+        if cell_halo is not None:
+            so = [s // 2 for s in self.stencil]
+            overlap = max(so)
+            out_off = [offset[i] - overlap for i in range(3)]
+            buf = self._cs_buffer(cell_halo)
+            if self.cs_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            self.cs_out = dev.detect_cs(cell_halo, self.stencil, out=buf)
+            if self.cs_events is not None:
+                e1.record()
+                self.cs_events.append((e0, e1))
+            self.t_cs.clear()
+            dev.find_object_properties(self.t_cs, self.cs_out, origin=out_off, chunk_seq=seq)
+            self._append(self.t_cs, 1, self.logs["cs"], out_off, self.cs_out.shape)
+            self.launches += 3
+        # stages 2+3: cell / organelle properties and overlap mapping (sd_proc.py:646-684)
+        self.t_cell.clear()
+        for t in self.t_sub + self.t_pair:
+            t.clear()
+        dev.map_subcell_extract_props(self.t_cell, self.t_sub, self.t_pair, cell, subcell, origin=offset, chunk_seq=seq)
+        self.launches += 2 + 2 * self.n_sub
+        self._append(self.t_cell, 0, self.logs["cell"], offset, cell.shape)
+        for c in range(self.n_sub):
+            self._append(self.t_sub[c], 2 + c, self.logs[f"sub{c}"], offset, cell.shape)
+            dev.check(L.syk_pairs_append(self.t_pair[c].h, self.pair_logs[c].data_ptr(), self.pair_logs[c].shape[0],
+                                         self.counters[len(self.kinds) + c:].data_ptr(), dev._stream_ptr()))
+            self.launches += 1
+
+    def _cs_buffer(self, cell_halo):
+        oshape = [cell_halo.shape[i] - self.stencil[i] + 1 for i in range(3)]
+        if self.cs_out is not None and list(self.cs_out.shape) == oshape and \
+                (self.cs_out.stride(0) == 1) == (cell_halo.stride(0) == 1):
+            return self.cs_out
+        return None
+
+    def finish(self):
+        """Bucket the logs by owner, exchange them (all-to-all) and fold them on the owner.
+        Returns {kind: int64 tensor [n, 8]} of this rank's owned per-(id, chunk) records and the owned pair logs."""
+        dev = self.dev
+        n = self.counters.tolist()  # the only host sync of the step
+        for i, k in enumerate(self.kinds):
+            if n[i] > self.log_capacity:
+                raise dev._lib.SykError(dev._lib.SYK_EOVERFLOW, f"record log '{k}' too small ({n[i]} > {self.log_capacity})")
+        for c in range(self.n_sub):
+            if n[len(self.kinds) + c] > self.pair_log_capacity:
+                raise dev._lib.SykError(dev._lib.SYK_EOVERFLOW, "pair log too small")
+        owned, owned_pairs = {}, []
+        for i, k in enumerate(self.kinds):
+            recs = self.logs[k][:n[i]]
+            if self.world > 1:
+                b, counts = dev.bucket_records(recs, self.world)
+                recs = exchange_buckets(b, counts.tolist(), self.group)
+                self.launches += 3
+            owned[k] = recs
+        for c in range(self.n_sub):
+            p = self.pair_logs[c][:n[len(self.kinds) + c]]
+            if self.world > 1:
+                b, counts = dev.bucket_pairs(p, self.world)
+                p = exchange_buckets(b, counts.tolist(), self.group)
+                self.launches += 3
+            owned_pairs.append(p)
+        return owned, owned_pairs
+
+    def reduce_on_device(self, owned, owned_pairs, geoms_by_kind=None, capacity=None):
+        """Owner-side fold of the owned records into final tables (syk_table_merge_records / syk_pairs_merge).
+        ``geoms_by_kind[kind]`` is the GEOM array of ALL chunks (indexed by chunk seq) used to decode rep_coord.
+        Returns ({kind: records tensor}, [pairs tensor]) with one row per object / per (sub, cell) pair."""
+        dev = self.dev
+        out, outp = {}, []
+        for k, recs in owned.items():
+            need = max(1 << 16, 4 * recs.shape[0]) if capacity is None else capacity
+            t = self._final.get(k)
+            if t is None or t.capacity < need:   # persistent owner tables: no cudaMalloc/cudaFree inside a step
+                t = self._final[k] = dev.IdTable(need)
+            else:
+                t.clear()
+            t.merge_records(recs)
+            g = np.zeros(0, GEOM_DTYPE) if geoms_by_kind is None else geoms_by_kind["cs" if k == "cs" else "cell"]
+            out[k] = t.export(g, max_records=max(recs.shape[0], 1))
+            self.launches += 3
+        for c, p in enumerate(owned_pairs):
+            need = max(1 << 16, 4 * p.shape[0]) if capacity is None else capacity
+            t = self._final.get(("pairs", c))
+            if t is None or t.capacity < need:
+                t = self._final[("pairs", c)] = dev.PairTable(need)
+            else:
+                t.clear()
+            t.merge(p)
+            outp.append(t.export(max_pairs=max(p.shape[0], 1)))
+            self.launches += 3
+        return out, outp

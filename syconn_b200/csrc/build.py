@@ -25,8 +25,10 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     objs = []
+    bdir = os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, src.replace(".cu", ".o"))
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
         cmd = [NVCC] + FLAGS + ["-c", os.path.join(HERE, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:

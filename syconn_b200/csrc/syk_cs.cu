@@ -9,7 +9,10 @@
 // de-duplicates them with __match_any_sync and keeps a warp-distributed histogram (lane i owns the i-th distinct
 // id).  Windows with more than 32 distinct ids fall back to a block-cooperative shared-memory hash table.
 // The arg-max follows the reference exactly: ids 0 and centre excluded, ties -> smallest id.
+#include <stdlib.h>
+
 #include "syk_common.cuh"
+#include "syk_cs_fast.cuh"
 
 namespace {
 
@@ -35,6 +38,11 @@ struct CsGeom {
     long long ntiles;
     int elem_bytes;
     int edge_bytes;
+    // list mode (fallback of the fast path): only the segments named in seg_list are processed
+    const unsigned *seg_list;
+    const unsigned *seg_count;
+    long long segs[3];  // segment grid of the fast path
+    int seg_tiles[3];   // tiles per segment along u, v, w
 };
 
 __device__ __forceinline__ unsigned ld_id(const void *base, int elem_bytes, long long idx) {
@@ -73,11 +81,29 @@ __global__ void __launch_bounds__(CS_THREADS) k_detect_cs(const void *__restrict
         hcnt[i] = 0u;
     }
 
-    for (long long t = blockIdx.x; t < G.ntiles; t += gridDim.x) {
-        const long long tw = t % G.tiles[2];
-        const long long r0 = t / G.tiles[2];
-        const long long tv = r0 % G.tiles[1];
-        const long long tu = r0 / G.tiles[1];
+    const int tps = G.seg_tiles[0] * G.seg_tiles[1] * G.seg_tiles[2];
+    const long long ntiles = G.seg_list ? (long long)(*G.seg_count) * tps : G.ntiles;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        long long tu, tv, tw;
+        if (G.seg_list) {  // tile t = sub-tile (t % tps) of listed segment t / tps
+            const long long seg = G.seg_list[t / tps];
+            int sub = (int)(t % tps);
+            const int sw_ = sub % G.seg_tiles[2];
+            sub /= G.seg_tiles[2];
+            const int sv_ = sub % G.seg_tiles[1];
+            const int su_ = sub / G.seg_tiles[1];
+            const long long gw = seg % G.segs[2];
+            const long long r1 = seg / G.segs[2];
+            tw = gw * G.seg_tiles[2] + sw_;
+            tv = (r1 % G.segs[1]) * G.seg_tiles[1] + sv_;
+            tu = (r1 / G.segs[1]) * G.seg_tiles[0] + su_;
+            if (tu * OU >= G.on[0] || tv * OV >= G.on[1] || tw * OW >= G.on[2]) continue;
+        } else {
+            tw = t % G.tiles[2];
+            const long long r0 = t / G.tiles[2];
+            tv = r0 % G.tiles[1];
+            tu = r0 / G.tiles[1];
+        }
         const long long o0[3] = {tu * OU, tv * OV, tw * OW};  // output-tile origin (output coords)
         // input coords of smem tile origin: output coord + off - hlo
         const long long i0[3] = {o0[0] + G.off[0] - G.hlo[0], o0[1] + G.off[1] - G.hlo[1], o0[2] + G.off[2] - G.hlo[2]};
@@ -319,6 +345,39 @@ static void cs_plan(const int64_t shape[3], const int64_t strides[3], const int3
     G.hslots = hs;
     G.elem_bytes = elem_bytes;
     G.edge_bytes = edge_bytes;
+    G.seg_list = nullptr;
+    G.seg_count = nullptr;
+    G.segs[0] = G.segs[1] = G.segs[2] = 1;
+    G.seg_tiles[0] = G.seg_tiles[1] = G.seg_tiles[2] = 1;
+}
+
+// The fast path needs: every stencil dim >= 3 (the boundary test of a centre plane uses its two neighbour planes),
+// 4-bit fields for the v-sum (sv <= 15), 8-bit fields for the plane ring sum (su*sv <= 255), 16-bit totals, and the
+// haloed plane / rings must fit the CTA's shared memory.
+static bool fast_plan(const CsGeom &C, csfast::FastGeom &F, csfast::FastSmem &L) {
+    using namespace csfast;
+    for (int a = 0; a < 3; ++a)
+        if (C.sten[a] < 3) return false;
+    if (C.sten[1] > 15 || C.sten[0] * C.sten[1] > 255 || C.total > 65535) return false;
+    for (int a = 0; a < 3; ++a) {
+        F.n[a] = C.n[a];
+        F.ist[a] = C.ist[a];
+        F.ost[a] = C.ost[a];
+        F.on[a] = C.on[a];
+        F.sten[a] = C.sten[a];
+        F.off[a] = C.off[a];
+    }
+    F.VP = TV + C.sten[1] - 1;
+    F.WP = TW + C.sten[2] - 1;
+    F.CF = C.off[0] + 1;
+    F.segs[0] = (C.on[0] + LU - 1) / LU;
+    F.segs[1] = (C.on[1] + TV - 1) / TV;
+    F.segs[2] = (C.on[2] + TW - 1) / TW;
+    F.nsegs = F.segs[0] * F.segs[1] * F.segs[2];
+    F.elem_bytes = C.elem_bytes;
+    if (F.VP * F.WP > MAXPER * NT || F.nsegs >= (1ll << 31)) return false;
+    L = fast_layout(F);
+    return L.total <= 200 * 1024;
 }
 
 static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_strides, const void *arr, int elem_bytes,
@@ -351,6 +410,28 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
     if (bps > 8) bps = 8;
     long long grid = (long long)sms * bps;
     if (grid > G.ntiles) grid = G.ntiles;
+    csfast::FastGeom F;
+    csfast::FastSmem L;
+    if (edges == nullptr && !getenv("SYK_CS_GENERIC") && fast_plan(G, F, L)) {
+        // fast path; segments with too many distinct ids are listed and redone by the generic kernel
+        unsigned *hard = nullptr;
+        SYK_CUDA(cudaMallocAsync((void **)&hard, sizeof(unsigned) * (size_t)(F.nsegs + 1), s));
+        SYK_CUDA(cudaMemsetAsync(hard, 0, sizeof(unsigned), s));
+        SYK_CUDA(cudaFuncSetAttribute(csfast::k_cs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        long long fgrid = F.nsegs < sms ? F.nsegs : sms;
+        csfast::k_cs_fast<<<(unsigned)fgrid, csfast::NT, L.total, s>>>(arr, (unsigned long long *)out, F, L, hard + 1, hard);
+        SYK_CUDA(cudaGetLastError());
+        G.seg_list = hard + 1;
+        G.seg_count = hard;
+        for (int a = 0; a < 3; ++a) G.segs[a] = F.segs[a];
+        G.seg_tiles[0] = csfast::LU / OU;
+        G.seg_tiles[1] = csfast::TV / OV;
+        G.seg_tiles[2] = csfast::TW / OW;
+        k_detect_cs<<<(unsigned)((long long)sms * bps), CS_THREADS, smem, s>>>(arr, nullptr, (unsigned long long *)out, G);
+        SYK_CUDA(cudaGetLastError());
+        SYK_CUDA(cudaFreeAsync(hard, s));
+        return SYK_OK;
+    }
     k_detect_cs<<<(unsigned)grid, CS_THREADS, smem, s>>>(arr, edges, (unsigned long long *)out, G);
     SYK_CUDA(cudaGetLastError());
     return SYK_OK;

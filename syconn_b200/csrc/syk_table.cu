@@ -121,10 +121,12 @@ SYK_API int syk_table_count(syk_table_t *t, void *stream, uint64_t *n_out, int *
     return SYK_OK;
 }
 
+// n_geoms == 0xFFFFFFFF: geoms[0] applies to every chunk_seq (single-chunk export)
 __device__ __forceinline__ void decode_rep(syk_record_t &r, const syk_chunk_geom_t *geoms, uint32_t n_geoms) {
     uint32_t seq = (uint32_t)(r.rep_key >> 40);
     r.chunk_seq = seq;
-    if (geoms == nullptr || seq >= n_geoms) {
+    if (n_geoms == 0xFFFFFFFFu && geoms != nullptr) seq = 0;
+    else if (geoms == nullptr || seq >= n_geoms) {
         r.rep[0] = r.rep[1] = r.rep[2] = -1;
         return;
     }
@@ -210,6 +212,22 @@ SYK_API int syk_table_export(syk_table_t *t, const syk_chunk_geom_t *geoms_host,
         syk_set_error("export buffer too small: %llu records, room for %llu", n, (unsigned long long)max_records);
         return SYK_EOVERFLOW;
     }
+    return SYK_OK;
+}
+
+SYK_API int syk_table_append_records(syk_table_t *t, const syk_chunk_geom_t *geom_host, syk_record_t *log_dev,
+                                     uint64_t max_records, uint64_t *counter_dev, void *stream) {
+    SYK_CHECK_ARG(t != nullptr && log_dev != nullptr && counter_dev != nullptr, "NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    syk_chunk_geom_t *gd = nullptr;
+    int rc = upload_geoms(geom_host, geom_host ? 1 : 0, s, &gd);
+    if (rc) return rc;
+    int blocks = (int)((t->capacity + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_table_export<<<blocks, 256, 0, s>>>(t->slots, t->capacity, log_dev, max_records, (unsigned long long *)counter_dev, gd,
+                                          gd ? 0xFFFFFFFFu : 0u);
+    SYK_CUDA(cudaGetLastError());
+    if (gd) SYK_CUDA(cudaFreeAsync(gd, s));
     return SYK_OK;
 }
 
@@ -405,6 +423,16 @@ SYK_API int syk_pairs_export(syk_pairs_t *t, syk_pair_t *pairs_dev, uint64_t max
         syk_set_error("pair export buffer too small: %llu pairs, room for %llu", n, (unsigned long long)max_pairs);
         return SYK_EOVERFLOW;
     }
+    return SYK_OK;
+}
+
+SYK_API int syk_pairs_append(syk_pairs_t *t, syk_pair_t *log_dev, uint64_t max_pairs, uint64_t *counter_dev, void *stream) {
+    SYK_CHECK_ARG(t != nullptr && log_dev != nullptr && counter_dev != nullptr, "NULL argument");
+    int blocks = (int)((t->capacity + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_pairs_export<<<blocks, 256, 0, (cudaStream_t)stream>>>(t->slots, t->capacity, log_dev, max_pairs,
+                                                             (unsigned long long *)counter_dev);
+    SYK_CUDA(cudaGetLastError());
     return SYK_OK;
 }
 

@@ -1,0 +1,197 @@
+"""Chunk plan, record/pair folding (reference merge semantics) and the hash-owner exchange.
+CPU: plan + folds against the oracle's merge_prop_dicts / merge_map_dicts; world_size-2 gloo all-to-all.
+GPU: the whole chunked pipeline on a small volume against the oracle run chunk by chunk."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import oracle
+from syconn_b200._lib import PAIR_DTYPE, RECORD_DTYPE
+from syconn_b200.chunked import ChunkPlan, cs_halo_geometry, exchange_buckets, reduce_pairs, reduce_records
+from syconn_b200.synth import synth_labels
+
+
+def test_chunk_plan_partition():
+    plan = ChunkPlan((100, 64, 70), (32, 32, 32))
+    assert len(plan) == 4 * 2 * 3
+    assert plan.offsets[0] == (0, 0, 0) and plan.offsets[1] == (0, 0, 32) and plan.sizes[-1] == (4, 32, 6)
+    for world in (1, 2, 3, 5, 8):
+        parts = [plan.chunks_of_rank(r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(len(plan)))
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+        assert all(p == list(range(p[0], p[0] + len(p))) for p in parts if p)
+    lo, ls, oo, os_ = cs_halo_geometry((512, 0, 1024), (512, 512, 512))
+    assert lo == [500, -12, 1015] and ls == [536, 536, 530] and oo == [506, -6, 1018] and os_ == [524, 524, 524]
+
+
+def _oracle_chunk_log(vol, plan, seqs):
+    """per-(id, chunk) records from the oracle, chunk by chunk, with global coordinates."""
+    rows = []
+    acc = oracle.new_prop_acc()
+    for s in seqs:
+        off, size = plan.offsets[s], plan.sizes[s]
+        sl = tuple(slice(off[i], off[i] + size[i]) for i in range(3))
+        ids, sizes, bbox, rep = oracle.find_object_properties_arrays(vol[sl])
+        r = np.zeros(len(ids), RECORD_DTYPE)
+        r["id"], r["count"], r["chunk_seq"] = ids, sizes, s
+        r["bb_min"], r["bb_max"], r["rep"] = bbox[:, 0] + off, bbox[:, 1] + off, rep + off
+        rows.append(r)
+        oracle.merge_prop_dicts([acc, list(oracle.find_object_properties(vol[sl]))], offset=np.array(off))
+    return np.concatenate(rows), acc
+
+
+def test_reduce_records_matches_reference_merge():
+    """reduce_records == merge_prop_dicts (sd_proc.py:1248-1273) + the writers' final reduction (:939-945)."""
+    vol = synth_labels((48, 40, 36), pitch=(14, 12, 9), seed=4)
+    plan = ChunkPlan(vol.shape, (16, 16, 16))
+    log, acc = _oracle_chunk_log(vol, plan, range(len(plan)))
+    rng = np.random.default_rng(0)
+    red = reduce_records(log[rng.permutation(len(log))])
+    rc, bb, sz = acc
+    assert red["id"].tolist() == sorted(sz)
+    for i, k in enumerate(red["id"].tolist()):
+        assert red["size"][i] == sz[k]
+        assert red["rep_coord"][i].tolist() == list(rc[k])          # last chunk's first voxel
+        bbs = np.array(bb[k])                                        # per-chunk boxes, chunk order
+        assert np.array_equal(red["bbs"][i], bbs)
+        assert np.array_equal(red["bounding_box"][i], [bbs[:, 0].min(axis=0), bbs[:, 1].max(axis=0)])
+
+
+def test_reduce_pairs_matches_reference_merge():
+    cell = synth_labels((40, 32, 24), pitch=(12, 10, 8), seed=5)
+    sub = synth_labels((40, 32, 24), pitch=(5, 5, 4), seed=5, kind=1, density16=5)
+    plan = ChunkPlan(cell.shape, (16, 16, 16))
+    tot, rows = {}, []
+    for s in range(len(plan)):
+        off, size = plan.offsets[s], plan.sizes[s]
+        sl = tuple(slice(off[i], off[i] + size[i]) for i in range(3))
+        md = oracle.map_subcell_C(cell[sl], sub[sl][None])[0]
+        oracle.merge_map_dicts([tot, {k: dict(v) for k, v in md.items()}])
+        for a, d in md.items():
+            for b, n in d.items():
+                rows.append((a, b, n, 0))
+    red = reduce_pairs(np.array(rows, dtype=PAIR_DTYPE))
+    want = sorted((a, b, n) for a, d in tot.items() for b, n in d.items())
+    assert list(zip(red["sub_id"].tolist(), red["cell_id"].tolist(), red["count"].tolist())) == want
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # rank r sends (r+1)*(d+2) rows to rank d; row = [src, dst, k, ...]
+        counts = [(rank + 1) * (d + 2) for d in range(world)]
+        rows = []
+        for d in range(world):
+            for k in range(counts[d]):
+                rows.append([rank, d, k, 7, 8, 9, 10, 11])
+        got = exchange_buckets(torch.tensor(rows, dtype=torch.int64), counts)
+        ok = all(int(r[1]) == rank for r in got)
+        exp = sum((s + 1) * (rank + 2) for s in range(world))
+        srcs = sorted(set(int(r[0]) for r in got))
+        # empty buckets must work too
+        e = exchange_buckets(torch.zeros((0, 4), dtype=torch.int64), [0] * world)
+        q.put((rank, ok and got.shape[0] == exp and srcs == list(range(world)) and e.shape[0] == 0))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_buckets_gloo_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in ps]
+    [p.join(timeout=60) for p in ps]
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+@pytest.mark.gpu
+def test_pipeline_small_volume_vs_oracle():
+    """All three stages over a 2x2x2 chunk grid on one GPU: device logs -> owner fold == oracle chunk by chunk."""
+    from syconn_b200 import device as dev
+    from syconn_b200._lib import GEOM_DTYPE
+    from syconn_b200.chunked import ExtractionPipeline
+    E, st, nsub = 48, (5, 5, 3), 2
+    plan = ChunkPlan((2 * E, 2 * E, 2 * E), (E, E, E))
+    pipe = ExtractionPipeline(nsub, st, chunk_table_capacity=1 << 12, log_capacity=1 << 14, pair_log_capacity=1 << 14)
+    geoms = {"cell": np.zeros(len(plan), GEOM_DTYPE), "cs": np.zeros(len(plan), GEOM_DTYPE)}
+    want_cs, want_cell, want_sub, want_pairs = [], [], [[] for _ in range(nsub)], [{} for _ in range(nsub)]
+    for rep in range(2):  # second pass checks reset()
+        pipe.reset()
+        for s in range(len(plan)):
+            off, size = plan.offsets[s], plan.sizes[s]
+            lo, ls, oo, os_ = cs_halo_geometry(off, size, st)
+            geoms["cell"][s], geoms["cs"][s] = (off, size), (oo, os_)
+            cell = dev.synth_labels(size, off, (13, 11, 7), 3, 2, 0, order="F")
+            subs = torch.stack([dev.synth_labels(size, off, (6, 5, 4), 3, 2, 1 + c, 3) for c in range(nsub)])
+            halo = dev.synth_labels(ls, lo, (13, 11, 7), 3, 2, 0, dtype=torch.int32, order="F")
+            pipe.process_chunk(s, off, cell, subs, halo)
+            if rep == 0:
+                hn = synth_labels(ls, lo, (13, 11, 7), 3, 2, 0, dtype=np.uint32)
+                cs = oracle.detect_cs(hn, st)
+                for arrs, origin, dst in ((oracle.find_object_properties_arrays(cs), oo, want_cs),
+                                          (oracle.find_object_properties_arrays(cell.cpu().numpy().view(np.uint64)), off, want_cell)):
+                    dst.append((s, origin, arrs))
+                c_, s_, p_ = oracle.map_subcell_extract_props_arrays(cell.cpu().numpy().view(np.uint64),
+                                                                     subs.cpu().numpy().view(np.uint64))
+                for c in range(nsub):
+                    want_sub[c].append((s, off, s_[c]))
+                    for a, b, n in zip(*[x.tolist() for x in p_[c]]):
+                        want_pairs[c][(a, b)] = want_pairs[c].get((a, b), 0) + n
+        owned, owned_pairs = pipe.finish()
+        final, final_pairs = pipe.reduce_on_device(owned, owned_pairs, geoms)
+
+    def want_log(lst):
+        rows = []
+        for s, origin, (ids, sizes, bbox, rep) in lst:
+            r = np.zeros(len(ids), RECORD_DTYPE)
+            r["id"], r["count"], r["chunk_seq"] = ids, sizes, s
+            r["bb_min"], r["bb_max"], r["rep"] = bbox[:, 0] + origin, bbox[:, 1] + origin, rep + origin
+            rows.append(r)
+        return np.concatenate(rows)
+
+    for kind, lst in (("cs", want_cs), ("cell", want_cell), ("sub0", want_sub[0]), ("sub1", want_sub[1])):
+        w = reduce_records(want_log(lst))
+        glog = dev.records_numpy(owned[kind])
+        g = reduce_records(glog)
+        assert len(glog) == sum(len(x[2][0]) for x in lst), kind
+        for f in ("id", "size", "bounding_box", "rep_coord"):
+            assert np.array_equal(g[f], w[f]), (kind, f)
+        assert all(np.array_equal(a, b) for a, b in zip(g["bbs"], w["bbs"])), kind
+        fin = dev.records_numpy(final[kind])
+        o = np.argsort(fin["id"])
+        assert np.array_equal(fin["id"][o], w["id"]) and np.array_equal(fin["count"][o].astype(np.int64), w["size"])
+        assert np.array_equal(fin["bb_min"][o], w["bounding_box"][:, 0]) and np.array_equal(fin["bb_max"][o], w["bounding_box"][:, 1])
+        assert np.array_equal(fin["rep"][o], w["rep_coord"]), kind
+    for c in range(nsub):
+        g = reduce_pairs(dev.pairs_numpy(owned_pairs[c]))
+        got = dict(zip(zip(g["sub_id"].tolist(), g["cell_id"].tolist()), g["count"].tolist()))
+        assert got == want_pairs[c]
+        f = dev.pairs_numpy(final_pairs[c])
+        assert dict(zip(zip(f["sub_id"].tolist(), f["cell_id"].tolist()), f["count"].tolist())) == want_pairs[c]
+    # bucketing: every record lands in exactly one owner bucket, same owner for equal ids
+    b, counts = dev.bucket_records(owned["cell"], 4)
+    bn, cn = dev.records_numpy(b), counts.tolist()
+    assert sum(cn) == owned["cell"].shape[0]
+    owner_of = {}
+    pos = 0
+    for o, n in enumerate(cn):
+        for i in bn["id"][pos:pos + n].tolist():
+            assert owner_of.setdefault(i, o) == o
+        pos += n
+    assert sorted(bn["id"].tolist()) == sorted(dev.records_numpy(owned["cell"])["id"].tolist())

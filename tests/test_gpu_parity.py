@@ -1,0 +1,192 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (host-buffer entry points behind the reference-named
+Python shims, and the device-buffer entry points), against the CPU oracle and the committed golden vectors.
+Bit-exact: everything here is integer work."""
+import numpy as np
+import pytest
+
+from helpers import assert_props_equal, assert_props_equal_arrays, check_dict_types, map_to_rows
+from test_oracle_pins import (check_known_boundary, check_known_detect_cs, check_known_find_object_properties)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from oracle import oracle
+    from syconn_b200.extraction import block_processing_C as bpc
+    from syconn_b200.extraction import find_object_properties as fop
+    from syconn_b200.extraction import find_object_properties_C as fopc
+    from syconn_b200.synth import synth_labels
+    return dict(oracle=oracle, bpc=bpc, fop=fop, fopc=fopc, synth=synth_labels)
+
+
+def test_reference_known_answers(mods):
+    check_known_find_object_properties(mods["fop"].find_object_properties)
+    check_known_detect_cs(mods["fop"].detect_cs)
+    check_known_boundary(mods["fop"].detect_seg_boundaries)
+
+
+def test_golden_props(mods, golden):
+    g, f = golden, mods["fop"].find_object_properties
+    got = f(g["fop_in"])
+    check_dict_types(got)
+    assert_props_equal_arrays(got, g["fop_ids"], g["fop_sizes"], g["fop_bbox"], g["fop_rep"], "fop")
+    assert_props_equal_arrays(f(g["fop_in"].transpose(2, 1, 0)), g["fopT_ids"], g["fopT_sizes"], g["fopT_bbox"],
+                              g["fopT_rep"], "fop strided")
+    assert_props_equal_arrays(f(g["fop32_in"]), g["fop32_ids"], g["fop32_sizes"], g["fop32_bbox"], g["fop32_rep"], "u32")
+
+
+def test_golden_map(mods, golden):
+    g = golden
+    cp, sp, md = mods["fop"].map_subcell_extract_props(g["map_cell"], g["map_subs"])
+    assert_props_equal_arrays(cp, g["map_cell_ids"], g["map_cell_sizes"], g["map_cell_bbox"], g["map_cell_rep"], "cell")
+    mc = mods["fopc"].map_subcell_C(g["map_cell"], g["map_subs"])
+    for c in range(3):
+        assert_props_equal_arrays((sp[0][c], sp[1][c], sp[2][c]), g[f"map_sub{c}_ids"], g[f"map_sub{c}_sizes"],
+                                  g[f"map_sub{c}_bbox"], g[f"map_sub{c}_rep"], f"sub{c}")
+        assert np.array_equal(map_to_rows(md[c]), g[f"map_pairs{c}"])
+        assert np.array_equal(map_to_rows(mc[c]), g[f"mapC_pairs{c}"])
+
+
+def test_golden_cs(mods, golden):
+    g, fop = golden, mods["fop"]
+    assert np.array_equal(fop.detect_seg_boundaries(g["cs_in"]), g["cs_bdry"])
+    for st in ((13, 13, 7), (7, 7, 3), (5, 5, 3), (3, 3, 3), (1, 1, 1), (3, 5, 7)):
+        assert np.array_equal(fop.detect_cs(g["cs_in"], st), g["cs_out_%d_%d_%d" % st]), st
+    for st in ((5, 5, 3), (3, 3, 3)):
+        assert np.array_equal(fop.detect_cs(g["tie_in"], st), g["tie_out_%d_%d_%d" % st]), st
+    assert np.array_equal(fop.detect_cs(g["many_in"], (5, 5, 3)), g["many_out_5_5_3"])
+    edges = np.ones(g["tie_in"].shape, np.uint32)
+    assert np.array_equal(mods["bpc"].process_block_nonzero(edges, g["tie_in"], (7, 7, 3)), g["pbn_forced_7_7_3"])
+    # x-fastest memory layout (production: ZYX memory seen as XYZ)
+    segF = np.ascontiguousarray(g["cs_in"].transpose(2, 1, 0)).transpose(2, 1, 0)
+    assert np.array_equal(fop.detect_cs(segF), g["cs_out_13_13_7"])
+
+
+def test_edge_cases(mods):
+    fop, fopc, bpc = mods["fop"], mods["fopc"], mods["bpc"]
+    assert fop.find_object_properties(np.zeros((3, 4, 5), np.uint64)) == ({}, {}, {})
+    assert fop.find_object_properties(np.zeros((0, 4, 5), np.uint64)) == ({}, {}, {})
+    r = fop.map_subcell_extract_props(np.zeros((3, 3, 3), np.uint64), np.zeros((2, 3, 3, 3), np.uint64))
+    assert r == ([{}, {}, {}], [[{}, {}], [{}, {}], [{}, {}]], [{}, {}])
+    cell = np.zeros((2, 2, 2), np.uint64)
+    sub = np.zeros((1, 2, 2, 2), np.uint64)
+    sub[0, 1, 1, 0] = 9
+    cp, sp, md = fop.map_subcell_extract_props(cell, sub)
+    assert sp[2][0] == {9: 1} and sp[0][0] == {9: [1, 1, 0]} and md == [{}]
+    w = np.ones((3, 3, 3), np.uint32)
+    w[0, 0, 0], w[2, 2, 2] = 3, 2
+    assert int(bpc.process_block_nonzero(np.ones_like(w), w, (3, 3, 3))[0, 0, 0]) == (1 << 32) + 2
+    assert bpc.kernel(w, 1) == (1 << 32) + 2
+    w[0, 0, 1] = 3
+    assert int(bpc.process_block_nonzero(np.ones_like(w), w, (3, 3, 3))[0, 0, 0]) == (1 << 32) + 3
+    # window with only centre/background -> 0 ; background centre with forced edge -> partner id, high word 0
+    z = np.zeros((3, 3, 3), np.uint32)
+    z[1, 1, 1] = 5
+    assert int(bpc.process_block_nonzero(np.ones_like(z), z, (3, 3, 3))[0, 0, 0]) == 0
+    z[1, 1, 1], z[0, 0, 0] = 0, 9
+    assert int(bpc.process_block_nonzero(np.ones_like(z), z, (3, 3, 3))[0, 0, 0]) == 9
+    # two half spaces, all-ones edge mask
+    h = np.full((9, 9, 5), 5, np.uint32)
+    h[5:] = 9
+    out = bpc.process_block_nonzero(np.ones_like(h), h, (7, 7, 3))
+    assert out.shape == (3, 3, 3) and np.all(out == 0x500000009)
+    # ids above 2^32 in 64-bit volumes and > 2^31 voxel... sizes are plain ints
+    big = np.full((4, 4, 4), 2 ** 63 + 5, np.uint64)
+    rc, bb, sz = fop.find_object_properties(big)
+    assert sz == {2 ** 63 + 5: 64} and bb[2 ** 63 + 5] == [[0, 0, 0], [4, 4, 4]]
+
+
+@pytest.mark.parametrize("seed,shape", [(0, (33, 70, 41)), (1, (64, 64, 64)), (2, (5, 130, 97)), (3, (96, 17, 1))])
+def test_props_vs_oracle_random(mods, seed, shape):
+    rng = np.random.default_rng(seed)
+    oracle, synth = mods["oracle"], mods["synth"]
+    v = synth(shape, pitch=(9, 7, 6), warp_amp=seed, seed=seed)
+    v[rng.random(shape) < 0.02] = rng.integers(0, 2 ** 40)
+    for lay in (v, np.asfortranarray(v), v.transpose(1, 0, 2).copy().transpose(1, 0, 2), v[::-1, :, ::2]):
+        assert_props_equal(mods["fop"].find_object_properties(lay), oracle.find_object_properties(lay), f"{seed}")
+    v32 = (v & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    assert_props_equal(mods["fop"].find_object_properties(v32), oracle.find_object_properties(v32), "u32")
+
+
+def test_props_high_cardinality(mods):
+    """every voxel its own id (hash-table stress, private-table early flush path)."""
+    v = (np.arange(48 * 40 * 36, dtype=np.uint64) * np.uint64(2654435761) + np.uint64(1)).reshape(48, 40, 36)
+    assert_props_equal(mods["fop"].find_object_properties(v), mods["oracle"].find_object_properties(v), "unique ids")
+
+
+@pytest.mark.parametrize("seed,shape,nsub", [(0, (40, 50, 37), 3), (1, (64, 64, 64), 2), (2, (20, 33, 70), 5), (3, (16, 16, 16), 1)])
+def test_map_vs_oracle_random(mods, seed, shape, nsub):
+    rng = np.random.default_rng(seed)
+    oracle, synth = mods["oracle"], mods["synth"]
+    cell = synth(shape, pitch=(10, 9, 7), warp_amp=2, seed=seed)
+    subs = np.stack([synth(shape, pitch=(5, 6, 4), warp_amp=3, seed=seed, kind=1 + c, density16=3 + c) for c in range(nsub)])
+    subs[:, rng.random(shape) < 0.01] = 77
+    for c_arr, s_arr in ((cell, subs), (np.asfortranarray(cell), np.ascontiguousarray(subs.transpose(0, 3, 2, 1)).transpose(0, 3, 2, 1))):
+        o = oracle.map_subcell_extract_props(c_arr, s_arr)
+        g = mods["fop"].map_subcell_extract_props(c_arr, s_arr)
+        assert_props_equal(g[0], o[0], "cell")
+        for c in range(nsub):
+            assert_props_equal([g[1][k][c] for k in range(3)], [o[1][k][c] for k in range(3)], f"sub{c}")
+            assert np.array_equal(map_to_rows(g[2][c]), map_to_rows(o[2][c])), f"pairs {c}"
+        mc, oc = mods["fopc"].map_subcell_C(c_arr, s_arr), oracle.map_subcell_C(c_arr, s_arr)
+        for c in range(nsub):
+            assert np.array_equal(map_to_rows(mc[c]), map_to_rows(oc[c]))
+
+
+@pytest.mark.parametrize("seed,shape,st", [(0, (40, 44, 39), (13, 13, 7)), (1, (30, 30, 30), (7, 7, 3)),
+                                           (2, (21, 37, 50), (5, 5, 3)), (3, (70, 20, 19), (3, 3, 3)),
+                                           (4, (24, 24, 24), (17, 17, 9)), (5, (16, 20, 33), (1, 3, 1))])
+def test_detect_cs_vs_oracle_random(mods, seed, shape, st):
+    rng = np.random.default_rng(seed)
+    oracle, synth = mods["oracle"], mods["synth"]
+    seg = synth(shape, pitch=(8, 9, 5), warp_amp=3, seed=seed, dtype=np.uint32)
+    seg[rng.random(shape) < 0.03] = rng.integers(0, 2 ** 32 - 1)
+    want = oracle.detect_cs(seg, st)
+    assert np.array_equal(mods["fop"].detect_cs(seg, st), want)
+    assert np.array_equal(mods["fop"].detect_cs(np.asfortranarray(seg), st), want)
+    # uint64 input narrowed like .astype(np.uint32)
+    seg64 = seg.astype(np.uint64) | (np.uint64(3) << np.uint64(40))
+    assert np.array_equal(mods["fop"].detect_cs(seg64, st), want)
+    edges = oracle.detect_seg_boundaries(seg).astype(np.uint32)
+    assert np.array_equal(mods["bpc"].process_block_nonzero(edges, seg, st), want)
+    assert np.array_equal(mods["fop"].detect_seg_boundaries(seg), edges.astype(bool))
+
+
+def test_detect_cs_random_labels_overflow_path(mods):
+    """near-random labels: > 32 distinct ids per window (block-cooperative hash fallback)."""
+    rng = np.random.default_rng(7)
+    seg = rng.integers(1, 2 ** 32 - 1, size=(20, 20, 18), dtype=np.uint64).astype(np.uint32)
+    seg[rng.random(seg.shape) < 0.3] = 11
+    for st in ((5, 5, 3), (7, 7, 3)):
+        assert np.array_equal(mods["fop"].detect_cs(seg, st), mods["oracle"].detect_cs(seg, st))
+
+
+def test_device_api_and_synth_twin(mods):
+    """device-buffer entry points on torch tensors; the CUDA generator is bit-identical to the NumPy twin."""
+    import torch
+    from syconn_b200 import device as dev
+    oracle, synth = mods["oracle"], mods["synth"]
+    shape, origin = (50, 45, 70), (-6, 506, 1000)
+    for order in ("C", "F"):
+        for kind, dt, nd in ((0, torch.int64, np.uint64), (2, torch.int64, np.uint64), (0, torch.int32, np.uint32)):
+            t = dev.synth_labels(shape, origin, pitch=(11, 9, 7), warp_amp=4, seed=5, kind=kind, density16=5, dtype=dt, order=order)
+            n = synth(shape, origin, pitch=(11, 9, 7), warp_amp=4, seed=5, kind=kind, density16=5, dtype=nd, order=order)
+            assert np.array_equal(t.cpu().numpy().view(nd), n), (order, kind, dt)
+    lab = dev.synth_labels(shape, origin, pitch=(11, 9, 7), seed=5)
+    tab = dev.IdTable(1 << 12)
+    dev.find_object_properties(tab, lab, origin=origin, chunk_seq=3)
+    recs = dev.records_numpy(tab.export(dev.geoms([[0, 0, 0]] * 3 + [origin], [[1, 1, 1]] * 3 + [shape])))
+    want = oracle.find_object_properties_arrays(lab.cpu().numpy().view(np.uint64))
+    o = np.argsort(recs["id"])
+    w = np.argsort(want[0])
+    assert np.array_equal(recs["id"][o], want[0][w]) and np.array_equal(recs["count"][o].astype(np.int64), want[1][w])
+    assert np.array_equal(recs["bb_min"][o], want[2][w][:, 0] + np.array(origin)) and np.array_equal(recs["bb_max"][o], want[2][w][:, 1] + np.array(origin))
+    assert np.array_equal(recs["rep"][o], want[3][w] + np.array(origin)) and np.all(recs["chunk_seq"] == 3)
+    # fused detect_cs on device, both layouts
+    seg = dev.synth_labels((60, 50, 40), pitch=(12, 10, 6), seed=9, dtype=torch.int32)
+    want = oracle.detect_cs(seg.cpu().numpy().view(np.uint32))
+    assert np.array_equal(dev.detect_cs(seg).cpu().numpy().view(np.uint64), want)
+    segF = dev.synth_labels((60, 50, 40), pitch=(12, 10, 6), seed=9, dtype=torch.int32, order="F")
+    outF = dev.detect_cs(segF)
+    assert outF.stride(0) == 1 and np.array_equal(outF.cpu().numpy().view(np.uint64), want)
