@@ -368,14 +368,15 @@ static bool fast_plan(const CsGeom &C, csfast::FastGeom &F, csfast::FastSmem &L)
         F.off[a] = C.off[a];
     }
     F.VP = TV + C.sten[1] - 1;
-    F.WP = TW + C.sten[2] - 1;
+    F.WP = (TW + C.sten[2] - 1 + 3) & ~3;
     F.CF = C.off[0] + 1;
     F.segs[0] = (C.on[0] + LU - 1) / LU;
     F.segs[1] = (C.on[1] + TV - 1) / TV;
     F.segs[2] = (C.on[2] + TW - 1) / TW;
     F.nsegs = F.segs[0] * F.segs[1] * F.segs[2];
     F.elem_bytes = C.elem_bytes;
-    if (F.VP * F.WP > MAXPER * NT || F.nsegs >= (1ll << 31)) return false;
+    F.vec4 = 0;
+    if (F.VP * F.WP / 4 > MAXQ * NT || GMAX * (TV / 4) * F.WP > MAXIT * NT || F.nsegs >= (1ll << 31)) return false;
     L = fast_layout(F);
     return L.total <= 200 * 1024;
 }
@@ -417,9 +418,20 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
         unsigned *hard = nullptr;
         SYK_CUDA(cudaMallocAsync((void **)&hard, sizeof(unsigned) * (size_t)(F.nsegs + 1), s));
         SYK_CUDA(cudaMemsetAsync(hard, 0, sizeof(unsigned), s));
-        SYK_CUDA(cudaFuncSetAttribute(csfast::k_cs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        long long fgrid = F.nsegs < sms ? F.nsegs : sms;
-        csfast::k_cs_fast<<<(unsigned)fgrid, csfast::NT, L.total, s>>>(arr, (unsigned long long *)out, F, L, hard + 1, hard);
+        // rows of uint32 that are 16-byte aligned everywhere => LDG.128 quads
+        F.vec4 = (elem_bytes == 4 && F.ist[2] == 1 && (F.ist[0] % 4) == 0 && (F.ist[1] % 4) == 0 && ((uintptr_t)arr % 16) == 0) ? 1 : 0;
+        int ctas = (int)((227 * 1024) / (L.total + 2048));
+        if (ctas > 2) ctas = 2;
+        if (ctas < 1) ctas = 1;
+        long long fgrid = (long long)sms * ctas;
+        if (fgrid > F.nsegs) fgrid = F.nsegs;
+        if (F.vec4) {
+            SYK_CUDA(cudaFuncSetAttribute(csfast::k_cs_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            csfast::k_cs_fast<true><<<(unsigned)fgrid, csfast::NT, L.total, s>>>(arr, (unsigned long long *)out, F, L, hard + 1, hard);
+        } else {
+            SYK_CUDA(cudaFuncSetAttribute(csfast::k_cs_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            csfast::k_cs_fast<false><<<(unsigned)fgrid, csfast::NT, L.total, s>>>(arr, (unsigned long long *)out, F, L, hard + 1, hard);
+        }
         SYK_CUDA(cudaGetLastError());
         G.seg_list = hard + 1;
         G.seg_count = hard;

@@ -4,24 +4,26 @@
 //   syk_map_subcell_extract_props   <- syconn/extraction/find_object_properties_C.pyx:112-192 (and map_subcell_C :72-109)
 //
 // Design (HBM-bound integer scan, every voxel is read exactly once):
-//   * lanes of a warp lie along the memory-contiguous axis (w): one coalesced load instruction per row
-//     (256 B of uint64 labels); a lane keeps R consecutive rows (axis v) in registers, so label runs along v
-//     are compressed per lane without any communication;
-//   * one __match_any_sync per pass groups the lanes that hold the same id; the group leader derives count,
-//     bounding box and first-voxel index from the peer mask (popc / ffs / clz) -- no per-voxel atomics;
-//   * the leader updates a WARP-PRIVATE open-addressing table in shared memory (plain LDS/STS, no atomics
-//     except the slot claim);
-//   * per tile (8 x 32 x 32 voxels) the private table is flushed into the global HBM table with one 64-bit
-//     atomicCAS claim + fire-and-forget atomicAdd/atomicMax updates per (tile, id).
+//   * a warp owns a tile of TU x TV rows x 32 lanes; lanes lie along the memory-contiguous axis (w) so every row is one
+//     coalesced 256 B (uint64) request.  Rows are streamed global -> shared with cp.async (LDGSTS), R rows per batch,
+//     double buffered: no registers are tied up by loads in flight and the next batch is always on its way;
+//   * per batch a lane run-length-compresses its R-row column (labels are blobs: 1-3 runs per column); pass k handles
+//     the k-th run of every lane: one __match_any_sync groups the lanes holding the same id, the group leader derives
+//     count / bounding box / first voxel from the peer mask (popc, ffs, clz; warp REDUX only for ragged groups);
+//   * the leader updates a WARP-PRIVATE open-addressing table in shared memory (plain LDS/STS, one CAS to claim);
+//   * per tile the private table is flushed into the global HBM table: one 64-bit atomicCAS claim plus
+//     fire-and-forget atomicAdd/atomicMax per (tile, id).  A full private table degrades to direct global updates.
 // Algorithmic traffic: elem_bytes per voxel and channel (8 B/voxel for uint64 labels).
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "syk_common.cuh"
 
 namespace {
 
-constexpr int TU = 8;    // tile extent along the slowest internal axis
-constexpr int TV = 32;   // tile extent along the row axis
 constexpr int TW = 32;   // tile extent along the lane axis (one voxel per lane)
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int MAX_SUB = 4;
 
 struct ScanGeom {
     long long n[3];       // extents along the internal axes (u, v, w)
@@ -35,7 +37,7 @@ struct ScanGeom {
     long long ntiles;
 };
 
-// ---- warp-private table of per-id partial records ------------------------------------------------------------
+// ---- warp-private tables -----------------------------------------------------------------------------------------
 // rec[slot][0] = {count, rep_local, min_u, min_v}, rec[slot][1] = {min_w, max_u, max_v, max_w}; tile-local, inclusive
 template <int WS>
 struct WarpTab {
@@ -55,51 +57,69 @@ struct TileCtx {
     long long t0[3];       // tile origin along internal axes
 };
 
-template <int WS>
-__device__ __forceinline__ void wtab_clear(WarpTab<WS> &tab, int lane) {
-    for (int i = lane; i < WS; i += 32) tab.keys[i] = 0ull;
-    __syncwarp();
+struct Group {             // one aggregated (id, tile-local box) contribution
+    unsigned cnt, rep, mnu, mnv, mnw, mxu, mxv, mxw;
+};
+
+__device__ __forceinline__ void global_add(const TableView &g, const ScanGeom &G, const TileCtx &T, unsigned long long key,
+                                           const Group &r) {
+    long long mn[3], mx[3], o[3];
+    mn[G.la[0]] = T.t0[0] + r.mnu;
+    mn[G.la[1]] = T.t0[1] + r.mnv;
+    mn[G.la[2]] = T.t0[2] + r.mnw;
+    mx[G.la[0]] = T.t0[0] + r.mxu + 1;
+    mx[G.la[1]] = T.t0[1] + r.mxv + 1;
+    mx[G.la[2]] = T.t0[2] + r.mxw + 1;
+    o[G.la[0]] = T.t0[0];
+    o[G.la[1]] = T.t0[1];
+    o[G.la[2]] = T.t0[2];
+    const unsigned lz = r.rep % (unsigned)T.td[2];
+    const unsigned q = r.rep / (unsigned)T.td[2];
+    const unsigned ly = q % (unsigned)T.td[1];
+    const unsigned lx = q / (unsigned)T.td[1];
+    const unsigned long long lin =
+        ((unsigned long long)(o[0] + lx) * (unsigned long long)G.S[1] + (unsigned long long)(o[1] + ly)) * (unsigned long long)G.S[2] +
+        (unsigned long long)(o[2] + lz);
+    const unsigned long long rep_key = ((unsigned long long)G.chunk_seq << 40) | (SYK_REP_MASK - lin);
+    syk_table_update(g, key, r.cnt, rep_key, (int)(mn[0] + G.origin[0]), (int)(mn[1] + G.origin[1]), (int)(mn[2] + G.origin[2]),
+                     (int)(mx[0] + G.origin[0]), (int)(mx[1] + G.origin[1]), (int)(mx[2] + G.origin[2]));
 }
 
-// leader-only: add one aggregated group to the private table; returns true when a new slot was claimed
+// leader-only.  Returns false when the private table is full (caller then updates the global table directly).
 template <int WS>
-__device__ __forceinline__ bool wtab_add(WarpTab<WS> &tab, unsigned long long key, unsigned cnt, unsigned rep, unsigned mnu,
-                                         unsigned mnv, unsigned mnw, unsigned mxu, unsigned mxv, unsigned mxw) {
-    unsigned slot = syk_hash_id32(key) & (WS - 1);
-    bool inserted = false;
-    for (;;) {
-        unsigned long long k = tab.keys[slot];
-        if (k == key) break;
+__device__ __forceinline__ bool wtab_add(WarpTab<WS> &tab, unsigned long long key, const Group &r) {
+    unsigned slot = ((unsigned)key * 0x9E3779B1u ^ (unsigned)(key >> 32) * 0x85EBCA6Bu) >> (32 - __builtin_ctz(WS));
+    bool inserted = false, found = false;
+    for (int probes = 0; probes < WS; ++probes) {
+        const unsigned long long k = tab.keys[slot];
+        if (k == key) { found = true; break; }
         if (k == 0ull) {
-            unsigned long long prev = atomicCAS(&tab.keys[slot], 0ull, key);
-            if (prev == 0ull) {
-                inserted = true;
-                break;
-            }
-            if (prev == key) break;
+            const unsigned long long prev = atomicCAS(&tab.keys[slot], 0ull, key);
+            if (prev == 0ull) { inserted = true; break; }
+            if (prev == key) { found = true; break; }
         }
         slot = (slot + 1) & (WS - 1);
     }
     if (inserted) {
-        tab.rec[slot][0] = make_uint4(cnt, rep, mnu, mnv);
-        tab.rec[slot][1] = make_uint4(mnw, mxu, mxv, mxw);
-    } else {
-        uint4 a = tab.rec[slot][0], b = tab.rec[slot][1];
-        a.x += cnt;
-        a.y = min(a.y, rep);
-        a.z = min(a.z, mnu);
-        a.w = min(a.w, mnv);
-        b.x = min(b.x, mnw);
-        b.y = max(b.y, mxu);
-        b.z = max(b.z, mxv);
-        b.w = max(b.w, mxw);
-        tab.rec[slot][0] = a;
-        tab.rec[slot][1] = b;
+        tab.rec[slot][0] = make_uint4(r.cnt, r.rep, r.mnu, r.mnv);
+        tab.rec[slot][1] = make_uint4(r.mnw, r.mxu, r.mxv, r.mxw);
+        return true;
     }
-    return inserted;
+    if (!found) return false;
+    uint4 a = tab.rec[slot][0], b = tab.rec[slot][1];
+    a.x += r.cnt;
+    a.y = min(a.y, r.rep);
+    a.z = min(a.z, r.mnu);
+    a.w = min(a.w, r.mnv);
+    b.x = min(b.x, r.mnw);
+    b.y = max(b.y, r.mxu);
+    b.z = max(b.z, r.mxv);
+    b.w = max(b.w, r.mxw);
+    tab.rec[slot][0] = a;
+    tab.rec[slot][1] = b;
+    return true;
 }
 
-// flush the private table into the global table (one claim + 8 fire-and-forget atomics per (tile, id))
 template <int WS>
 __device__ __forceinline__ void wtab_flush(WarpTab<WS> &tab, const TableView &g, const ScanGeom &G, const TileCtx &T, int lane) {
     __syncwarp();
@@ -108,31 +128,9 @@ __device__ __forceinline__ void wtab_flush(WarpTab<WS> &tab, const TableView &g,
         if (key == 0ull) continue;
         const uint4 a = tab.rec[i][0], b = tab.rec[i][1];
         tab.keys[i] = 0ull;
-        // internal (u,v,w) tile-local -> logical global
-        long long mn[3], mx[3];
-        mn[G.la[0]] = T.t0[0] + a.z;
-        mn[G.la[1]] = T.t0[1] + a.w;
-        mn[G.la[2]] = T.t0[2] + b.x;
-        mx[G.la[0]] = T.t0[0] + b.y + 1;
-        mx[G.la[1]] = T.t0[1] + b.z + 1;
-        mx[G.la[2]] = T.t0[2] + b.w + 1;
-        long long o[3];
-        o[G.la[0]] = T.t0[0];
-        o[G.la[1]] = T.t0[1];
-        o[G.la[2]] = T.t0[2];
-        const unsigned rep = a.y;
-        const unsigned lz = rep % (unsigned)T.td[2];
-        const unsigned q = rep / (unsigned)T.td[2];
-        const unsigned ly = q % (unsigned)T.td[1];
-        const unsigned lx = q / (unsigned)T.td[1];
-        const unsigned long long lin =
-            ((unsigned long long)(o[0] + lx) * (unsigned long long)G.S[1] + (unsigned long long)(o[1] + ly)) *
-                (unsigned long long)G.S[2] +
-            (unsigned long long)(o[2] + lz);
-        const unsigned long long rep_key = ((unsigned long long)G.chunk_seq << 40) | (SYK_REP_MASK - lin);
-        syk_table_update(g, key, a.x, rep_key, (int)(mn[0] + G.origin[0]), (int)(mn[1] + G.origin[1]),
-                         (int)(mn[2] + G.origin[2]), (int)(mx[0] + G.origin[0]), (int)(mx[1] + G.origin[1]),
-                         (int)(mx[2] + G.origin[2]));
+        Group r;
+        r.cnt = a.x; r.rep = a.y; r.mnu = a.z; r.mnv = a.w; r.mnw = b.x; r.mxu = b.y; r.mxv = b.z; r.mxw = b.w;
+        global_add(g, G, T, key, r);
     }
     __syncwarp();
 }
@@ -150,133 +148,51 @@ __device__ __forceinline__ void ptab_flush(WarpPairTab<PS> &tab, const PairView 
     __syncwarp();
 }
 
-template <int R>
-__device__ __forceinline__ unsigned long long pick(const unsigned long long (&v)[R], int s) {
-    unsigned long long k = v[0];
-#pragma unroll
-    for (int j = 1; j < R; ++j) k = (s == j) ? v[j] : k;
-    return k;
-}
-
-// Accumulate one batch of R rows (rows lv0 .. lv0+R-1 of the tile at tile-local u = lu) of one label channel.
-template <int R, int WS>
-__device__ __forceinline__ void acc_batch(const unsigned long long (&v)[R], WarpTab<WS> &tab, int &n_used,
-                                          const TableView &g, const ScanGeom &G, const TileCtx &T, unsigned lu, unsigned lv0,
-                                          int lane) {
-    // per-lane run starts along v
-    unsigned bnd = 1u;
-#pragma unroll
-    for (int j = 1; j < R; ++j) bnd |= (v[j] != v[j - 1]) ? (1u << j) : 0u;
-    // drop background runs right away
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-        // a run of zeros still needs its start bit to terminate the previous run; it is skipped below via key == 0
-    }
-    const unsigned rowrep = lu * T.cu + lv0 * T.cv + (unsigned)lane * T.cw;
-    while (__any_sync(FULL, bnd != 0u)) {
-        if (n_used > WS - 32) {  // keep room for up to 32 inserts per pass
-            wtab_flush<WS>(tab, g, G, T, lane);
-            n_used = 0;
-        }
-        int s = R, e = R;
-        unsigned long long key = 0ull;
-        if (bnd) {
-            s = __ffs(bnd) - 1;
-            const unsigned rest = bnd & (bnd - 1u);
-            e = rest ? (__ffs(rest) - 1) : R;
-            key = pick<R>(v, s);
-            bnd = rest;
-        }
-        if (!__any_sync(FULL, key != 0ull)) continue;
-        const unsigned peers = __match_any_sync(FULL, key);
-        const bool partial = (key != 0ull) && !(s == 0 && e == R);
-        const unsigned partial_mask = __ballot_sync(FULL, partial);
-        unsigned cnt, vs, ve, rep;
-        const int first = __ffs(peers) - 1;
-        const int last = 31 - __clz(peers);
-        if ((peers & partial_mask) == 0u) {
-            cnt = (unsigned)R * (unsigned)__popc(peers);
-            vs = 0u;
-            ve = (unsigned)R;
-            rep = rowrep - (unsigned)(lane - first) * T.cw;
-        } else {
-            // some lane of this group holds a partial run: reduce over the peer group
-            cnt = __reduce_add_sync(peers, (unsigned)(e - s));
-            vs = __reduce_min_sync(peers, (unsigned)s);
-            ve = __reduce_max_sync(peers, (unsigned)e);
-            rep = __reduce_min_sync(peers, rowrep + (unsigned)s * T.cv);
-        }
-        bool inserted = false;
-        if (lane == first && key != 0ull) {
-            inserted = wtab_add<WS>(tab, key, cnt, rep, lu, lv0 + vs, (unsigned)first, lu, lv0 + ve - 1u, (unsigned)last);
-        }
-        n_used += __popc(__ballot_sync(FULL, inserted));
-        __syncwarp();
-    }
-}
-
-// Overlap pairs of one organelle channel against the cell channel for one batch of rows.
-template <int R, int PS>
-__device__ __forceinline__ void acc_pairs(const unsigned long long (&sv)[R], const unsigned long long (&cv)[R],
-                                          WarpPairTab<PS> &tab, int &n_used, const PairView &g, int lane) {
-    unsigned bnd = 1u;
-#pragma unroll
-    for (int j = 1; j < R; ++j) bnd |= (sv[j] != sv[j - 1] || cv[j] != cv[j - 1]) ? (1u << j) : 0u;
-    while (__any_sync(FULL, bnd != 0u)) {
-        if (n_used > PS - 32) {
-            ptab_flush<PS>(tab, g, lane);
-            n_used = 0;
-        }
-        int s = R, e = R;
-        unsigned long long ks = 0ull, kc = 0ull;
-        if (bnd) {
-            s = __ffs(bnd) - 1;
-            const unsigned rest = bnd & (bnd - 1u);
-            e = rest ? (__ffs(rest) - 1) : R;
-            ks = pick<R>(sv, s);
-            kc = pick<R>(cv, s);
-            bnd = rest;
-        }
-        const bool active = (ks != 0ull) && (kc != 0ull);
-        if (!active) ks = kc = 0ull;
-        if (!__any_sync(FULL, active)) continue;
-        const unsigned peers = __match_any_sync(FULL, ks) & __match_any_sync(FULL, kc);
-        const bool partial = active && !(s == 0 && e == R);
-        const unsigned partial_mask = __ballot_sync(FULL, partial);
-        unsigned cnt;
-        const int first = __ffs(peers) - 1;
-        if ((peers & partial_mask) == 0u) cnt = (unsigned)R * (unsigned)__popc(peers);
-        else cnt = __reduce_add_sync(peers, (unsigned)(e - s));
-        bool inserted = false;
-        if (lane == first && active) {
-            unsigned slot = syk_hash_id32(ks * 0x9E3779B97F4A7C15ULL + kc) & (PS - 1);
-            for (;;) {
-                const unsigned long long cs = tab.sub[slot];
-                if (cs == ks && tab.cell[slot] == kc) break;
-                if (cs == 0ull) {
-                    const unsigned long long prev = atomicCAS(&tab.sub[slot], 0ull, ks);
-                    if (prev == 0ull) {
-                        tab.cell[slot] = kc;
-                        tab.cnt[slot] = 0u;
-                        inserted = true;
-                        break;
-                    }
-                }
-                slot = (slot + 1) & (PS - 1);
-            }
-            tab.cnt[slot] += cnt;
-        }
-        n_used += __popc(__ballot_sync(FULL, inserted));
-        __syncwarp();
-    }
-}
-
+// ---- async row staging ---------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ unsigned long long ld_stream(const T *p) {
-    return (unsigned long long)__ldcs(p);  // streaming: every voxel is read once
+__device__ __forceinline__ void cp_async_elem(T *smem_dst, const T *gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? (int)sizeof(T) : 0;  // src-size 0 => zero fill
+    if (sizeof(T) == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- TMA (cp.async.bulk.tensor) staging: one instruction per channel and batch, completion on an mbarrier ----------
+struct alignas(64) TmapSet {
+    CUtensorMap m[1 + MAX_SUB];
+};
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SYK_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SYK_DONE;\n"
+        "bra SYK_WAIT;\n"
+        "SYK_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *tm, int c0, int c1, int c2, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(reinterpret_cast<unsigned long long>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
 }
 
-__device__ __forceinline__ void tile_setup(const ScanGeom &G, long long tile, TileCtx &T) {
+__device__ __forceinline__ void tile_setup(const ScanGeom &G, long long tile, int TU, int TV, TileCtx &T) {
     const long long tw = tile % G.tiles[2];
     const long long r = tile / G.tiles[2];
     const long long tv = r % G.tiles[1];
@@ -299,58 +215,126 @@ __device__ __forceinline__ void tile_setup(const ScanGeom &G, long long tile, Ti
     T.cw = c[2];
 }
 
-// ---- find_object_properties ------------------------------------------------------------------------------------
-constexpr int PROPS_WARPS = 8;
-constexpr int PROPS_WS = 128;
-
+// Run-length compress the lane's column buf[0..R)[lane] -> bit j of the result is set when a run starts at row j.
 template <typename T, int R>
-__global__ void __launch_bounds__(PROPS_WARPS * 32) k_props(const T *__restrict__ base, ScanGeom G, TableView g) {
-    __shared__ WarpTab<PROPS_WS> tabs[PROPS_WARPS];
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    WarpTab<PROPS_WS> &tab = tabs[wib];
-    wtab_clear<PROPS_WS>(tab, lane);
-    int n_used = 0;
-    const long long nwarps = (long long)gridDim.x * PROPS_WARPS;
-    for (long long tile = (long long)blockIdx.x * PROPS_WARPS + wib; tile < G.ntiles; tile += nwarps) {
-        TileCtx Tc;
-        tile_setup(G, tile, Tc);
-        const long long w = Tc.t0[2] + lane;
-        const bool wok = w < G.n[2];
-        const T *colp = base + w * G.st[2];
-        constexpr int NB = TU * (TV / R);  // batches per tile
-        unsigned long long cur[R], nxt[R];
-        auto load_batch = [&](int b, unsigned long long (&dst)[R]) {
-            const int lu = b / (TV / R);
-            const int lv0 = (b % (TV / R)) * R;
-            const long long u = Tc.t0[0] + lu;
-            const bool uok = wok && (u < G.n[0]);
+__device__ __forceinline__ unsigned run_starts(const T *buf, int lane, bool &any_nz) {
+    unsigned bnd = 1u;
+    T prev = buf[lane];
+    T orv = prev;
 #pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const long long v = Tc.t0[1] + lv0 + j;
-                dst[j] = (uok && v < G.n[1]) ? ld_stream(colp + u * G.st[0] + v * G.st[1]) : 0ull;
-            }
-        };
-        load_batch(0, cur);
-        for (int b = 0; b < NB; ++b) {
-            if (b + 1 < NB) load_batch(b + 1, nxt);
-            const unsigned lu = (unsigned)(b / (TV / R));
-            const unsigned lv0 = (unsigned)((b % (TV / R)) * R);
-            acc_batch<R, PROPS_WS>(cur, tab, n_used, g, G, Tc, lu, lv0, lane);
-#pragma unroll
-            for (int j = 0; j < R; ++j) cur[j] = nxt[j];
+    for (int j = 1; j < R; ++j) {
+        const T v = buf[j * 32 + lane];
+        bnd |= (v != prev) ? (1u << j) : 0u;
+        orv |= v;
+        prev = v;
+    }
+    any_nz = orv != 0;
+    return bnd;
+}
+
+// Accumulate one staged batch (R rows starting at tile-local row lv0, tile-local u = lu) of one label channel.
+template <typename T, int R, int WS>
+__device__ __forceinline__ void acc_batch(const T *buf, unsigned bnd, WarpTab<WS> &tab, const TableView &g, const ScanGeom &G,
+                                          const TileCtx &Tc, unsigned lu, unsigned lv0, int lane) {
+    const unsigned rowrep = lu * Tc.cu + lv0 * Tc.cv + (unsigned)lane * Tc.cw;
+    while (__any_sync(FULL, bnd != 0u)) {
+        int s = R, e = R;
+        unsigned long long key = 0ull;
+        if (bnd) {
+            s = __ffs(bnd) - 1;
+            const unsigned rest = bnd & (bnd - 1u);
+            e = rest ? (__ffs(rest) - 1) : R;
+            key = (unsigned long long)buf[s * 32 + lane];
+            bnd = rest;
         }
-        wtab_flush<PROPS_WS>(tab, g, G, Tc, lane);
-        n_used = 0;
+        if (!__any_sync(FULL, key != 0ull)) continue;
+        const unsigned peers = __match_any_sync(FULL, key);
+        const bool partial = (key != 0ull) && !(s == 0 && e == R);
+        const unsigned partial_mask = __ballot_sync(FULL, partial);
+        const int first = __ffs(peers) - 1;
+        const int last = 31 - __clz(peers);
+        Group r;
+        if ((peers & partial_mask) == 0u) {  // every lane of the group holds one run spanning the whole batch
+            r.cnt = (unsigned)R * (unsigned)__popc(peers);
+            r.mnv = lv0;
+            r.mxv = lv0 + R - 1;
+            r.rep = rowrep - (unsigned)(lane - first) * Tc.cw;
+        } else {  // ragged group: reduce over the peers
+            r.cnt = __reduce_add_sync(peers, (unsigned)(e - s));
+            r.mnv = lv0 + __reduce_min_sync(peers, (unsigned)s);
+            r.mxv = lv0 + __reduce_max_sync(peers, (unsigned)e) - 1u;
+            r.rep = __reduce_min_sync(peers, rowrep + (unsigned)s * Tc.cv);
+        }
+        if (lane == first && key != 0ull) {
+            r.mnu = r.mxu = lu;
+            r.mnw = (unsigned)first;
+            r.mxw = (unsigned)last;
+            if (!wtab_add<WS>(tab, key, r)) global_add(g, G, Tc, key, r);
+        }
+        __syncwarp();
     }
 }
 
-// ---- map_subcell_extract_props -----------------------------------------------------------------------------------
-constexpr int MAP_WARPS = 4;
-constexpr int MAP_WS = 64;
-constexpr int MAP_PS = 64;
-constexpr int MAX_SUB = 4;
+// Overlap pairs of one organelle channel (sbuf) against the cell channel (cbuf) for one staged batch.
+template <typename T, int R, int PS>
+__device__ __forceinline__ void acc_pairs(const T *sbuf, const T *cbuf, WarpPairTab<PS> &tab, const PairView &g, int lane) {
+    unsigned bnd = 1u;
+    {
+        T ps = sbuf[lane], pc = cbuf[lane];
+#pragma unroll
+        for (int j = 1; j < R; ++j) {
+            const T s = sbuf[j * 32 + lane], c = cbuf[j * 32 + lane];
+            bnd |= (s != ps || c != pc) ? (1u << j) : 0u;
+            ps = s;
+            pc = c;
+        }
+    }
+    while (__any_sync(FULL, bnd != 0u)) {
+        int s = R, e = R;
+        unsigned long long ks = 0ull, kc = 0ull;
+        if (bnd) {
+            s = __ffs(bnd) - 1;
+            const unsigned rest = bnd & (bnd - 1u);
+            e = rest ? (__ffs(rest) - 1) : R;
+            ks = (unsigned long long)sbuf[s * 32 + lane];
+            kc = (unsigned long long)cbuf[s * 32 + lane];
+            bnd = rest;
+        }
+        const bool active = (ks != 0ull) && (kc != 0ull);
+        if (!active) ks = kc = 0ull;
+        if (!__any_sync(FULL, active)) continue;
+        const unsigned peers = __match_any_sync(FULL, ks) & __match_any_sync(FULL, kc);
+        const bool partial = active && !(s == 0 && e == R);
+        const unsigned partial_mask = __ballot_sync(FULL, partial);
+        unsigned cnt;
+        const int first = __ffs(peers) - 1;
+        if ((peers & partial_mask) == 0u) cnt = (unsigned)R * (unsigned)__popc(peers);
+        else cnt = __reduce_add_sync(peers, (unsigned)(e - s));
+        if (lane == first && active) {
+            unsigned slot = ((unsigned)ks * 0x9E3779B1u ^ (unsigned)(ks >> 32) * 0x85EBCA6Bu ^ (unsigned)kc * 0xC2B2AE35u) >>
+                            (32 - __builtin_ctz(PS));
+            bool done = false;
+            for (int probes = 0; probes < PS; ++probes) {
+                const unsigned long long cs = tab.sub[slot];
+                if (cs == ks && tab.cell[slot] == kc) { tab.cnt[slot] += cnt; done = true; break; }
+                if (cs == 0ull) {
+                    const unsigned long long prev = atomicCAS(&tab.sub[slot], 0ull, ks);
+                    if (prev == 0ull) {
+                        tab.cell[slot] = kc;
+                        tab.cnt[slot] = cnt;
+                        done = true;
+                        break;
+                    }
+                }
+                slot = (slot + 1) & (PS - 1);
+            }
+            if (!done) syk_pairs_update(g, ks, kc, (unsigned long long)cnt);  // private table full
+        }
+        __syncwarp();
+    }
+}
 
+// ---- kernels -----------------------------------------------------------------------------------------------------
 struct MapArgs {
     const void *sub[MAX_SUB];
     TableView sub_t[MAX_SUB];
@@ -360,103 +344,152 @@ struct MapArgs {
     int do_sub_props;
 };
 
-template <int R>
-struct MapSmemWarp {
-    WarpTab<MAP_WS> cell;
-};
-
-template <typename T, int R>
-__global__ void __launch_bounds__(MAP_WARPS * 32) k_map(const T *__restrict__ cell, ScanGeom G, TableView cell_t, MapArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout per warp: WarpTab cell | n_sub x WarpTab sub | n_sub x WarpPairTab
+// One kernel for both entry points: NCH = 1 + n_sub staged channels (n_sub == 0 => find_object_properties).
+//   R   rows per batch;  TU x TV rows per tile (TV multiple of R)
+template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS, int NBUF, bool TMA>
+__global__ void __launch_bounds__(WARPS * 32) k_scan(const T *__restrict__ cell, ScanGeom G, TableView cell_t, MapArgs A,
+                                                     const __grid_constant__ TmapSet tm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar[WARPS][2];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const size_t per_warp = sizeof(WarpTab<MAP_WS>) * (1 + A.n_sub) + sizeof(WarpPairTab<MAP_PS>) * A.n_sub;
+    const int nch = 1 + A.n_sub;
+    // per-warp layout: stage[NBUF][nch][R*32] T | WarpTab<WS> cell | n_sub x WarpTab<WSS> | n_sub x WarpPairTab<PS>
+    const size_t stage_bytes = (size_t)NBUF * nch * R * 32 * sizeof(T);
+    const size_t per_warp = (stage_bytes + sizeof(WarpTab<WS>) + (size_t)A.n_sub * (sizeof(WarpTab<WSS>) + sizeof(WarpPairTab<PS>)) + 127) &
+                            ~(size_t)127;
     unsigned char *mine = smem_raw + per_warp * wib;
-    WarpTab<MAP_WS> *ctab = reinterpret_cast<WarpTab<MAP_WS> *>(mine);
-    WarpTab<MAP_WS> *stab = ctab + 1;
-    WarpPairTab<MAP_PS> *ptab = reinterpret_cast<WarpPairTab<MAP_PS> *>(stab + A.n_sub);
-    wtab_clear<MAP_WS>(*ctab, lane);
+    T *stage = reinterpret_cast<T *>(mine);
+    WarpTab<WS> *ctab = reinterpret_cast<WarpTab<WS> *>(mine + stage_bytes);
+    WarpTab<WSS> *stab = reinterpret_cast<WarpTab<WSS> *>(ctab + 1);
+    WarpPairTab<PS> *ptab = reinterpret_cast<WarpPairTab<PS> *>(stab + A.n_sub);
+    for (int i = lane; i < WS; i += 32) ctab->keys[i] = 0ull;
     for (int c = 0; c < A.n_sub; ++c) {
-        wtab_clear<MAP_WS>(stab[c], lane);
-        for (int i = lane; i < MAP_PS; i += 32) {
+        for (int i = lane; i < WSS; i += 32) stab[c].keys[i] = 0ull;
+        for (int i = lane; i < PS; i += 32) {
             ptab[c].sub[i] = 0ull;
             ptab[c].cell[i] = 0ull;
             ptab[c].cnt[i] = 0u;
         }
     }
+    unsigned bar_addr[2] = {(unsigned)__cvta_generic_to_shared(&mbar[wib][0]), (unsigned)__cvta_generic_to_shared(&mbar[wib][1])};
+    unsigned bar_phase[2] = {0u, 0u};
+    if (TMA && lane == 0) {
+        mbar_init(bar_addr[0], 1);
+        mbar_init(bar_addr[1], 1);
+    }
     __syncwarp();
-    int used_c = 0;
-    int used_s[MAX_SUB], used_p[MAX_SUB];
-#pragma unroll
-    for (int c = 0; c < MAX_SUB; ++c) used_s[c] = used_p[c] = 0;
 
-    const long long nwarps = (long long)gridDim.x * MAP_WARPS;
-    for (long long tile = (long long)blockIdx.x * MAP_WARPS + wib; tile < G.ntiles; tile += nwarps) {
-        TileCtx Tc;
-        tile_setup(G, tile, Tc);
-        const long long w = Tc.t0[2] + lane;
-        const bool wok = w < G.n[2];
-        constexpr int NB = TU * (TV / R);
-        for (int b = 0; b < NB; ++b) {
-            const unsigned lu = (unsigned)(b / (TV / R));
-            const unsigned lv0 = (unsigned)((b % (TV / R)) * R);
-            const long long u = Tc.t0[0] + lu;
-            const bool uok = wok && (u < G.n[0]);
-            unsigned long long cv[R];
-            unsigned long long sv[MAX_SUB][R];
+    constexpr int NB = TU * (TV / R);  // batches per tile
+    const long long nwarps = (long long)gridDim.x * WARPS;
+    const long long my_first = (long long)blockIdx.x * WARPS + wib;
+    if (my_first >= G.ntiles) return;
+
+    // issue the async loads of batch b of the tile at tile coordinates (tu, tv, tw) into stage buffer `sb`
+    struct TileId { long long tu, tv, tw; };
+    auto tile_id = [&](long long tile) {
+        TileId t;
+        t.tw = tile % G.tiles[2];
+        const long long rr = tile / G.tiles[2];
+        t.tv = rr % G.tiles[1];
+        t.tu = rr / G.tiles[1];
+        return t;
+    };
+    auto issue = [&](const TileId &t, int b, int sb) {
+        if (TMA) {
+            if (lane == 0) {
+                const int c0 = (int)(t.tw * TW), c1 = (int)(t.tv * TV + (b % (TV / R)) * R), c2 = (int)(t.tu * TU + b / (TV / R));
+                mbar_expect_tx(bar_addr[sb], (unsigned)(nch * R * 32 * sizeof(T)));
+                const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage + (size_t)sb * nch * R * 32);
+                for (int c = 0; c < nch; ++c) tma_load_3d(dst0 + c * R * 32 * (unsigned)sizeof(T), &tm.m[c], c0, c1, c2, bar_addr[sb]);
+            }
+            return;
+        }
+        const long long w = t.tw * TW + lane;
+        const long long u = t.tu * TU + b / (TV / R);
+        const long long v0 = t.tv * TV + (b % (TV / R)) * R;
+        const bool ok = (w < G.n[2]) && (u < G.n[0]);
+        T *dst = stage + (size_t)sb * nch * R * 32 + lane;
+        const T *src = ok ? cell + w * G.st[2] + u * G.st[0] + v0 * G.st[1] : cell;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const bool okj = ok && (v0 + j < G.n[1]);
+            cp_async_elem<T>(dst + j * 32, okj ? src + j * G.st[1] : cell, okj);
+        }
+        for (int c = 0; c < A.n_sub; ++c) {
+            const T *sc = reinterpret_cast<const T *>(A.sub[c]);
+            const T *ss = ok ? sc + w * G.sst[2] + u * G.sst[0] + v0 * G.sst[1] : sc;
+            T *dd = dst + (size_t)(1 + c) * R * 32;
 #pragma unroll
             for (int j = 0; j < R; ++j) {
-                const long long v = Tc.t0[1] + lv0 + j;
-                cv[j] = (uok && v < G.n[1]) ? ld_stream(cell + w * G.st[2] + u * G.st[0] + v * G.st[1]) : 0ull;
-            }
-#pragma unroll
-            for (int c = 0; c < MAX_SUB; ++c) {
-                if (c < A.n_sub) {
-                    const T *sp = reinterpret_cast<const T *>(A.sub[c]) + w * G.sst[2] + u * G.sst[0];
-#pragma unroll
-                    for (int j = 0; j < R; ++j) {
-                        const long long v = Tc.t0[1] + lv0 + j;
-                        sv[c][j] = (uok && v < G.n[1]) ? ld_stream(sp + v * G.sst[1]) : 0ull;
-                    }
-                }
-            }
-            if (A.do_cell_props) acc_batch<R, MAP_WS>(cv, *ctab, used_c, cell_t, G, Tc, lu, lv0, lane);
-#pragma unroll
-            for (int c = 0; c < MAX_SUB; ++c) {
-                if (c < A.n_sub) {
-                    bool nz = false;
-#pragma unroll
-                    for (int j = 0; j < R; ++j) nz |= (sv[c][j] != 0ull);
-                    if (!__any_sync(FULL, nz)) continue;
-                    if (A.do_sub_props) acc_batch<R, MAP_WS>(sv[c], stab[c], used_s[c], A.sub_t[c], G, Tc, lu, lv0, lane);
-                    acc_pairs<R, MAP_PS>(sv[c], cv, ptab[c], used_p[c], A.pair_t[c], lane);
-                }
+                const bool okj = ok && (v0 + j < G.n[1]);
+                cp_async_elem<T>(dd + j * 32, okj ? ss + j * G.sst[1] : sc, okj);
             }
         }
-        if (A.do_cell_props) {
-            wtab_flush<MAP_WS>(*ctab, cell_t, G, Tc, lane);
-            used_c = 0;
-        }
-#pragma unroll
-        for (int c = 0; c < MAX_SUB; ++c) {
-            if (c < A.n_sub) {
-                if (A.do_sub_props) {
-                    wtab_flush<MAP_WS>(stab[c], A.sub_t[c], G, Tc, lane);
-                    used_s[c] = 0;
+        cp_async_commit();
+    };
+
+    int sb = 0;
+    TileId cur = tile_id(my_first), nxt = cur;
+    issue(cur, 0, 0);
+    for (long long tile = my_first; tile < G.ntiles; tile += nwarps) {
+        TileCtx Tc;
+        tile_setup(G, tile, TU, TV, Tc);
+        const bool has_next = tile + nwarps < G.ntiles;
+        if (has_next) nxt = tile_id(tile + nwarps);
+        for (int b = 0; b < NB; ++b) {
+            const bool more = (b + 1 < NB) || has_next;
+            // NBUF == 2: prefetch the next batch (possibly of the next tile) before consuming this one
+            if (NBUF == 2 && more) {
+                if (b + 1 < NB) issue(cur, b + 1, sb ^ 1);
+                else issue(nxt, 0, sb ^ 1);
+            }
+            if (TMA) {
+                mbar_wait(bar_addr[sb], bar_phase[sb]);
+                bar_phase[sb] ^= 1u;
+            } else {
+                if (NBUF == 2 && more) cp_async_wait<1>();
+                else cp_async_wait<0>();
+            }
+            __syncwarp();
+            const unsigned lu = (unsigned)(b / (TV / R));
+            const unsigned lv0 = (unsigned)((b % (TV / R)) * R);
+            const T *cb = stage + (size_t)sb * nch * R * 32;
+            bool nz;
+            if (A.do_cell_props) {
+                const unsigned bnd = run_starts<T, R>(cb, lane, nz);
+                if (__any_sync(FULL, nz)) acc_batch<T, R, WS>(cb, bnd, *ctab, cell_t, G, Tc, lu, lv0, lane);
+            }
+            for (int c = 0; c < A.n_sub; ++c) {
+                const T *sbuf = cb + (size_t)(1 + c) * R * 32;
+                const unsigned bnd = run_starts<T, R>(sbuf, lane, nz);
+                if (!__any_sync(FULL, nz)) continue;  // organelles are sparse: most batches stop here
+                if (A.do_sub_props) acc_batch<T, R, WSS>(sbuf, bnd, stab[c], A.sub_t[c], G, Tc, lu, lv0, lane);
+                acc_pairs<T, R, PS>(sbuf, cb, ptab[c], A.pair_t[c], lane);
+            }
+            __syncwarp();
+            if (NBUF == 1) {  // single buffer: refill it now; the SM's other warps cover the latency
+                if (more) {
+                    if (b + 1 < NB) issue(cur, b + 1, 0);
+                    else issue(nxt, 0, 0);
                 }
+            } else {
+                sb ^= 1;
             }
         }
+        if (A.do_cell_props) wtab_flush<WS>(*ctab, cell_t, G, Tc, lane);
+        if (A.do_sub_props)
+            for (int c = 0; c < A.n_sub; ++c) wtab_flush<WSS>(stab[c], A.sub_t[c], G, Tc, lane);
+        cur = nxt;
     }
-    for (int c = 0; c < A.n_sub; ++c) ptab_flush<MAP_PS>(ptab[c], A.pair_t[c], lane);
+    for (int c = 0; c < A.n_sub; ++c) ptab_flush<PS>(ptab[c], A.pair_t[c], lane);
 }
 
-// choose the lane axis = smallest stride, row axis = next, slow axis = largest
-static void plan_axes(const int64_t shape[3], const int64_t strides[3], const int64_t origin[3], uint32_t chunk_seq,
-                      ScanGeom &G) {
+// choose the lane axis = smallest stride, row axis = next, slow axis = largest; degenerate axes (extent 1) go first
+static void plan_axes(const int64_t shape[3], const int64_t strides[3], const int64_t origin[3], uint32_t chunk_seq, int TU,
+                      int TV, ScanGeom &G) {
     int ax[3] = {0, 1, 2};
     auto key = [&](int a) { return strides[a] < 0 ? -strides[a] : strides[a]; };
-    // sort axes by |stride| descending -> u, v, w ; degenerate axes (extent 1) go first
     for (int i = 0; i < 3; ++i)
         for (int j = i + 1; j < 3; ++j) {
             const bool swap = (shape[ax[j]] == 1 && shape[ax[i]] != 1) ? true
@@ -498,16 +531,82 @@ static int check_geom(const int64_t shape[3], const int64_t strides[3], const in
     return SYK_OK;
 }
 
-static int grid_for(long long ntiles, int warps_per_block, int blocks_per_sm) {
+// ---- TMA tensor maps (driver entry point resolved through the runtime: no link against libcuda) ----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// rank-3 map over the internal axes (w innermost); box = 32 lanes x R rows x 1 plane.  false => use the LDGSTS path
+static bool make_tmap(CUtensorMap *m, const void *base, int elem_bytes, const long long n[3], const long long st[3], int R) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || getenv("SYK_NO_TMA")) return false;
+    if (st[2] != 1 || ((uintptr_t)base & 15)) return false;
+    for (int a = 0; a < 2; ++a)
+        if (st[a] <= 0 || ((st[a] * elem_bytes) & 15) || st[a] * elem_bytes >= (1ll << 40)) return false;
+    for (int a = 0; a < 3; ++a)
+        if (n[a] <= 0 || n[a] >= (1ll << 31)) return false;
+    // the tensor is described with v as dim 1 and u as dim 2 whatever their stride order
+    cuuint64_t dims[3] = {(cuuint64_t)n[2], (cuuint64_t)n[1], (cuuint64_t)n[0]};
+    cuuint64_t strides[2] = {(cuuint64_t)(st[1] * elem_bytes), (cuuint64_t)(st[0] * elem_bytes)};
+    cuuint32_t box[3] = {32u, (cuuint32_t)R, 1u};
+    cuuint32_t es[3] = {1u, 1u, 1u};
+    CUresult r = enc(m, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(base),
+                     dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS, int NBUF, bool TMA>
+static int launch_cfg(const void *cell, const ScanGeom &G, const TableView &cell_t, const MapArgs &A, const TmapSet &tm, cudaStream_t s) {
+    const int nch = 1 + A.n_sub;
+    const size_t per_warp = ((size_t)NBUF * nch * R * 32 * sizeof(T) + sizeof(WarpTab<WS>) +
+                             (size_t)A.n_sub * (sizeof(WarpTab<WSS>) + sizeof(WarpPairTab<PS>)) + 127) & ~(size_t)127;
+    const size_t smem = per_warp * WARPS;
+    auto kern = k_scan<T, R, TU, TV, WARPS, WS, WSS, PS, NBUF, TMA>;
+    SYK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long want = (ntiles + warps_per_block - 1) / warps_per_block;
-    long long cap = (long long)sms * blocks_per_sm;
-    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    int bps = (int)((226 * 1024) / (smem + 1024 + 256));
+    if (bps < 1) bps = 1;
+    if (bps * WARPS > 64) bps = 64 / WARPS;
+    long long want = (G.ntiles + WARPS - 1) / WARPS;
+    long long grid = (long long)sms * bps;
+    if (grid > want) grid = want < 1 ? 1 : want;
+    kern<<<(unsigned)grid, WARPS * 32, smem, s>>>((const T *)cell, G, cell_t, A, tm);
+    SYK_CUDA(cudaGetLastError());
+    return SYK_OK;
+}
+
+template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS>
+static int launch_scan(const void *cell, const ScanGeom &G, const TableView &cell_t, const MapArgs &A, cudaStream_t s) {
+    TmapSet tm;
+    memset(&tm, 0, sizeof(tm));
+    bool tma = make_tmap(&tm.m[0], cell, (int)sizeof(T), G.n, G.st, R);
+    for (int c = 0; c < A.n_sub && tma; ++c) tma = make_tmap(&tm.m[1 + c], A.sub[c], (int)sizeof(T), G.n, G.sst, R);
+    // TMA: one buffer per warp, many resident warps hide the latency; LDGSTS fallback: double buffered
+    if (tma) return launch_cfg<T, R, TU, TV, WARPS, WS, WSS, PS, 1, true>(cell, G, cell_t, A, tm, s);
+    return launch_cfg<T, R, TU, TV, WARPS, WS, WSS, PS, 2, false>(cell, G, cell_t, A, tm, s);
 }
 
 }  // namespace
+
+// props: R=16 rows per batch, tiles of 4 x 32 rows x 32 lanes; map: R=8, tiles of 8 x 16 rows (more channels staged)
+#define PROPS_CFG 16, 4, 32, 8, 64, 32, 32
+#define MAP_CFG 8, 8, 16, 4, 64, 32, 32
 
 SYK_API int syk_find_object_properties(syk_table_t *t, const void *labels_dev, int elem_bytes, const int64_t shape[3],
                                        const int64_t strides[3], const int64_t origin[3], uint32_t chunk_seq, void *stream) {
@@ -520,15 +619,12 @@ SYK_API int syk_find_object_properties(syk_table_t *t, const void *labels_dev, i
     if (shape[0] == 0 || shape[1] == 0 || shape[2] == 0) return SYK_OK;
     SYK_CHECK_ARG(labels_dev != nullptr, "labels_dev is NULL");
     ScanGeom G;
-    plan_axes(shape, strides, origin, chunk_seq, G);
-    const int grid = grid_for(G.ntiles, PROPS_WARPS, 4);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (elem_bytes == 8)
-        k_props<unsigned long long, 4><<<grid, PROPS_WARPS * 32, 0, s>>>((const unsigned long long *)labels_dev, G, view_of(t));
-    else
-        k_props<unsigned int, 4><<<grid, PROPS_WARPS * 32, 0, s>>>((const unsigned int *)labels_dev, G, view_of(t));
-    SYK_CUDA(cudaGetLastError());
-    return SYK_OK;
+    plan_axes(shape, strides, origin, chunk_seq, 4, 32, G);
+    MapArgs A;
+    memset(&A, 0, sizeof(A));
+    A.do_cell_props = 1;
+    if (elem_bytes == 8) return launch_scan<unsigned long long, PROPS_CFG>(labels_dev, G, view_of(t), A, (cudaStream_t)stream);
+    return launch_scan<unsigned int, PROPS_CFG>(labels_dev, G, view_of(t), A, (cudaStream_t)stream);
 }
 
 SYK_API int syk_map_subcell_extract_props(syk_table_t *cell_t, syk_table_t *const *sub_t, syk_pairs_t *const *pair_t,
@@ -545,7 +641,7 @@ SYK_API int syk_map_subcell_extract_props(syk_table_t *cell_t, syk_table_t *cons
     if (shape[0] == 0 || shape[1] == 0 || shape[2] == 0) return SYK_OK;
     SYK_CHECK_ARG(cell_dev != nullptr, "cell_dev is NULL");
     ScanGeom G;
-    plan_axes(shape, cell_strides, origin, chunk_seq, G);
+    plan_axes(shape, cell_strides, origin, chunk_seq, 8, 16, G);
     for (int a = 0; a < 3; ++a) G.sst[a] = n_sub ? sub_strides[G.la[a]] : 0;
     MapArgs A;
     memset(&A, 0, sizeof(A));
@@ -561,20 +657,6 @@ SYK_API int syk_map_subcell_extract_props(syk_table_t *cell_t, syk_table_t *cons
             A.sub_t[c] = view_of(sub_t[c]);
         }
     }
-    const size_t per_warp = sizeof(WarpTab<MAP_WS>) * (1 + n_sub) + sizeof(WarpPairTab<MAP_PS>) * n_sub;
-    const size_t smem = per_warp * MAP_WARPS;
-    cudaStream_t s = (cudaStream_t)stream;
-    int bps = (int)((200 * 1024) / (smem + 1024));
-    if (bps < 1) bps = 1;
-    if (bps > 6) bps = 6;
-    const int grid = grid_for(G.ntiles, MAP_WARPS, bps);
-    if (elem_bytes == 8) {
-        SYK_CUDA(cudaFuncSetAttribute(k_map<unsigned long long, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_map<unsigned long long, 4><<<grid, MAP_WARPS * 32, smem, s>>>((const unsigned long long *)cell_dev, G, view_of(cell_t), A);
-    } else {
-        SYK_CUDA(cudaFuncSetAttribute(k_map<unsigned int, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_map<unsigned int, 4><<<grid, MAP_WARPS * 32, smem, s>>>((const unsigned int *)cell_dev, G, view_of(cell_t), A);
-    }
-    SYK_CUDA(cudaGetLastError());
-    return SYK_OK;
+    if (elem_bytes == 8) return launch_scan<unsigned long long, MAP_CFG>(cell_dev, G, view_of(cell_t), A, (cudaStream_t)stream);
+    return launch_scan<unsigned int, MAP_CFG>(cell_dev, G, view_of(cell_t), A, (cudaStream_t)stream);
 }
