@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsyk.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("SYK_LIB_NAME", "libsyk.so"))
 
 SYK_OK, SYK_EINVAL, SYK_ECUDA, SYK_ENODEV, SYK_EOVERFLOW, SYK_ENOMEM = 0, -1, -2, -3, -4, -5
 

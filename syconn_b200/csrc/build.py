@@ -5,9 +5,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-OUT = os.path.join(PKG, "libsyk.so")
+OUT = os.path.join(PKG, os.environ.get("SYK_LIB_NAME", "libsyk.so"))
 SOURCES = ["syk_table.cu", "syk_props.cu", "syk_cs.cu", "syk_host.cu"]
-HEADERS = ["syk_common.cuh", os.path.join("..", "..", "include", "syk.h")]
+HEADERS = ["syk_common.cuh", "syk_cs_fast.cuh", os.path.join("..", "..", "include", "syk.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
          "--use_fast_math", "-Xptxas", "-v"]
@@ -29,7 +29,7 @@ def build(force=False, verbose=False):
     os.makedirs(bdir, exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(bdir, src.replace(".cu", ".o"))
-        cmd = [NVCC] + FLAGS + ["-c", os.path.join(HERE, src), "-o", obj]
+        cmd = [NVCC] + FLAGS + os.environ.get("SYK_NVCC_EXTRA", "").split() + ["-c", os.path.join(HERE, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)

@@ -370,13 +370,16 @@ static bool fast_plan(const CsGeom &C, csfast::FastGeom &F, csfast::FastSmem &L)
     F.VP = TV + C.sten[1] - 1;
     F.WP = (TW + C.sten[2] - 1 + 3) & ~3;
     F.CF = C.off[0] + 1;
+    F.CR = C.sten[0] + 1;
     F.segs[0] = (C.on[0] + LU - 1) / LU;
     F.segs[1] = (C.on[1] + TV - 1) / TV;
     F.segs[2] = (C.on[2] + TW - 1) / TW;
     F.nsegs = F.segs[0] * F.segs[1] * F.segs[2];
     F.elem_bytes = C.elem_bytes;
     F.vec4 = 0;
-    if (F.VP * F.WP / 4 > MAXQ * NT || GMAX * (TV / 4) * F.WP > MAXIT * NT || F.nsegs >= (1ll << 31)) return false;
+    F.pair_ok = (2 * C.sten[0] * C.sten[1] <= 255) ? 1 : 0;
+    F.out_vec = 0;
+    if (F.VP * F.WP / 4 > MAXQ * NT || GMAX * (TV / 8) * F.WP > MAXIT * NT || F.nsegs >= (1ll << 31)) return false;
     L = fast_layout(F);
     return L.total <= 200 * 1024;
 }
@@ -420,8 +423,9 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
         SYK_CUDA(cudaMemsetAsync(hard, 0, sizeof(unsigned), s));
         // rows of uint32 that are 16-byte aligned everywhere => LDG.128 quads
         F.vec4 = (elem_bytes == 4 && F.ist[2] == 1 && (F.ist[0] % 4) == 0 && (F.ist[1] % 4) == 0 && ((uintptr_t)arr % 16) == 0) ? 1 : 0;
-        int ctas = (int)((227 * 1024) / (L.total + 2048));
-        if (ctas > 2) ctas = 2;
+        F.out_vec = (F.ost[2] == 1 && (F.ost[0] % 2) == 0 && (F.ost[1] % 2) == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
+        int ctas = (int)((227 * 1024) / (L.total + 3072));
+        if (ctas > 3) ctas = 3;
         if (ctas < 1) ctas = 1;
         long long fgrid = (long long)sms * ctas;
         if (fgrid > F.nsegs) fgrid = F.nsegs;
@@ -441,6 +445,13 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
         G.seg_tiles[2] = csfast::TW / OW;
         k_detect_cs<<<(unsigned)((long long)sms * bps), CS_THREADS, smem, s>>>(arr, nullptr, (unsigned long long *)out, G);
         SYK_CUDA(cudaGetLastError());
+        if (getenv("SYK_CS_DEBUG")) {
+            unsigned nh = 0;
+            cudaMemcpyAsync(&nh, hard, sizeof(nh), cudaMemcpyDeviceToHost, s);
+            cudaStreamSynchronize(s);
+            fprintf(stderr, "[syk] detect_cs fast path: %lld segments, %u redone by the generic kernel, smem %d B, vec4=%d out_vec=%d\n",
+                    F.nsegs, nh, L.total, F.vec4, F.out_vec);
+        }
         SYK_CUDA(cudaFreeAsync(hard, s));
         return SYK_OK;
     }

@@ -4,27 +4,36 @@
 // box sums of id-indicator volumes, evaluated only for the ids that actually occur near the tile:
 //   * a CTA owns a TV x TW cross-section of the output and marches along the slowest axis (u) over a segment of LU
 //     output planes; every input plane is read once per CTA (halo re-reads hit L2);
-//   * the ids met on the way get compact slots (shared-memory hash, <= KMAX per segment); 8 ids share one 32-bit
-//     word as 4-bit indicator fields, so one integer add advances 8 box sums at once;
-//   * per plane: sliding sum along v (window sv <= 15 -> 4-bit fields), running sum over the last su planes
-//     (<= 255 -> 8-bit fields, ring buffer of su planes in shared memory), and -- only for boundary voxels, which are
-//     compacted first -- the final sum along w in 16-bit fields, arg-max with the reference tie-break (smallest id);
-//   * segments that meet more than KMAX ids are appended to a device list and redone by the generic kernel.
+//   * the ids met on the way get compact 8-bit slots (shared-memory hash); a slot is recycled once its id has left the
+//     su-plane window, so KMAX bounds the ids NEAR the marching plane, not per segment.  Only the compact planes of the
+//     last su+1 input planes are kept in shared memory (1 byte per voxel);
+//   * 8 ids share one 32-bit word as 4-bit indicator fields, so one integer add advances 8 box sums at once.  Per
+//     plane: sliding sum along v of the entering plane and of the plane that leaves the window (window sv <= 15 ->
+//     4-bit fields), difference added to the running sum over the last su planes (<= 255 -> 8-bit fields), and --
+//     only for boundary voxels, which are compacted first -- the final sum along w in 16-bit fields, arg-max with
+//     the reference tie-break (smallest id);
+//   * the 6-neighbourhood boundary test runs on the compact 8-bit indices, four voxels per 32-bit operation;
+//   * segments that ever hold more than KMAX ids in the window are appended to a device list and redone by the
+//     generic kernel.
 // All arithmetic is integer; results are bit-identical to the generic path.
 #pragma once
 #include "syk_common.cuh"
 
 namespace csfast {
 
+#ifndef SYK_LU
+#define SYK_LU 64
+#endif
 constexpr int TV = 16;
 constexpr int TW = 32;
-constexpr int LU = 32;
+constexpr int LU = SYK_LU;
 constexpr int NT = 256;
-constexpr int GMAX = 3;
-constexpr int KMAX = GMAX * 8;
-constexpr int HASH = 128;
+constexpr int GMAX = 6;
+constexpr int KMAX = GMAX * 8;  // <= 64 (slot masks are 64 bit), <= 127 (compact index + boundary flag in one byte)
+constexpr int HASH = 256;
 constexpr int MAXQ = 2;   // relabel quads (4 voxels along w) per thread: ceil(VP*WP/4 / NT)
-constexpr int MAXIT = 3;  // v-pass items per thread: ceil(GMAX*(TV/4)*WP / NT)
+constexpr int MAXIT = 3;  // v-pass items (8 outputs each) per thread: ceil(GMAX*(TV/8)*WP / NT)
+constexpr int NOQ = TV * TW / 4;  // output quads per plane (128)
 
 struct FastGeom {
     long long n[3];    // input extents (internal axes u, v, w)
@@ -34,14 +43,17 @@ struct FastGeom {
     int sten[3], off[3];
     int VP, WP;        // haloed plane dims: TV + sv - 1, TW + sw - 1 rounded up to a multiple of 4
     int CF;            // centre-flag ring depth
+    int CR;            // compact-plane ring depth (su + 1)
     long long segs[3];
     long long nsegs;
     int elem_bytes;
     int vec4;          // 16-byte aligned uint32 rows: quads are loaded with one LDG.128
+    int pair_ok;       // 2 * su * sv <= 255: two ring sums may be added in 8-bit fields before widening
+    int out_vec;       // output rows 16-byte aligned and contiguous along w: zero runs are stored 16 bytes at a time
 };
 
 struct FastSmem {  // offsets in bytes into dynamic shared memory
-    int raw, comp, ind, ring, slo, shi, cflag, elist, total;
+    int raw, comp, ssum, cflag, elist, total;
 };
 
 inline FastSmem fast_layout(const FastGeom &G) {
@@ -51,72 +63,134 @@ inline FastSmem fast_layout(const FastGeom &G) {
     int o = 0;
     auto take = [&](int bytes) { int at = o; o += (bytes + 15) & ~15; return at; };  // every region 16-byte aligned
     L.raw = take(plane * 4);
-    L.comp = take(3 * plane);
-    L.ind = take(GMAX * plane * 4);
-    L.ring = take(GMAX * G.sten[0] * oplane * 4);   // ring, slo, shi stay contiguous (zeroed together)
-    L.slo = take(GMAX * oplane * 4);
-    L.shi = take(GMAX * oplane * 4);
+    L.comp = take(G.CR * plane);             // ring of compact-index planes, 1 byte per voxel
+    L.ssum = take(GMAX * oplane * 8);        // uint2 {even slots, odd slots} in 8-bit fields
     L.cflag = take(G.CF * TV * TW);
     L.elist = take(TV * TW * 2);
     L.total = o;
     return L;
 }
 
+constexpr unsigned SL_PENDING = 0xFFFFFFFFu;  // key inserted, slot being allocated
+constexpr unsigned SL_DEAD = 0xFFFFFFFEu;     // id left the su-plane window: its slot was recycled
+constexpr unsigned long long ALL_SLOTS = (KMAX >= 64) ? ~0ull : ((1ull << KMAX) - 1ull);
+
 struct Hash {
     unsigned keys[HASH];
-    unsigned char slot[HASH];
-    unsigned ids[KMAX];
-    unsigned char rnk[KMAX];
-    int nslots, newflag, n_edge;
+    unsigned sl[HASH];             // compact slot of the key | SL_PENDING | SL_DEAD
+    int lastp[HASH];               // last plane in which the key was seen
+    unsigned ids[KMAX];            // id held by a slot
+    int owner[KMAX];               // hash index owning the slot
+    unsigned short tb[KMAX];       // ((255 - rank by id) << 8) | slot: tie-break key of the arg-max (smallest id wins)
+    unsigned lut[GMAX][KMAX + 8];  // indicator word of compact index j in group g
+    unsigned long long freemask;   // bit s set: slot s is free (lowest free slot is handed out first)
+    int ovf, newflag, n_edge;
 };
 
-// find the hash index of `lab` (!= 0), inserting it (and allocating a compact slot) when it is new
-__device__ __forceinline__ int hash_find_insert(Hash &H, unsigned lab) {
-    unsigned h = (lab * 2654435761u) >> 25;  // 7 bits
+// hand out the lowest free compact slot to hash entry h (id lab); raises H.ovf when none is left
+__device__ __forceinline__ void slot_alloc(Hash &H, unsigned h, unsigned lab) {
+    for (;;) {
+        const unsigned long long m = *(volatile unsigned long long *)&H.freemask;
+        if (m == 0ull) {
+            H.ovf = 1;
+            return;
+        }
+        const unsigned long long bit = m & (0ull - m);
+        if (atomicAnd(&H.freemask, ~bit) & bit) {
+            const int s = __ffsll((long long)bit) - 1;
+            H.ids[s] = lab;
+            H.owner[s] = (int)h;
+            H.sl[h] = (unsigned)s;
+            H.newflag = 1;
+            return;
+        }
+    }
+}
+
+// find the hash index of `lab` (!= 0) at plane p, inserting it (and allocating a compact slot) when it is new or
+// when its slot was recycled; slots become visible to other threads after the next barrier
+__device__ __forceinline__ int hash_find_insert(Hash &H, unsigned lab, int p) {
+    unsigned h = (lab * 2654435761u) >> (32 - 8);  // HASH == 256
     for (int probes = 0; probes < HASH; ++probes) {
         const unsigned cur = H.keys[h];
-        if (cur == lab) return (int)h;
+        if (cur == lab) {
+            H.lastp[h] = p;
+            if (H.sl[h] == SL_DEAD && atomicCAS(&H.sl[h], SL_DEAD, SL_PENDING) == SL_DEAD) slot_alloc(H, h, lab);
+            return (int)h;
+        }
         if (cur == 0u) {
             const unsigned prev = atomicCAS(&H.keys[h], 0u, lab);
-            if (prev == 0u) {  // winner allocates the slot; others read it after the next barrier
-                const int s = atomicAdd(&H.nslots, 1);
-                if (s < KMAX) {
-                    H.ids[s] = lab;
-                    H.slot[h] = (unsigned char)s;
-                }
-                H.newflag = 1;
+            if (prev == 0u) {
+                H.lastp[h] = p;
+                slot_alloc(H, h, lab);
                 return (int)h;
             }
-            if (prev == lab) return (int)h;
+            if (prev == lab) {
+                H.lastp[h] = p;
+                return (int)h;
+            }
         }
         h = (h + 1) & (HASH - 1);
     }
-    atomicExch(&H.nslots, KMAX + 1);  // hash full => overflow
+    H.ovf = 1;  // hash full
     return 0;
 }
 
+// four consecutive bytes starting at byte column `col` of a row of 8-bit indices (row is 4-byte aligned)
+__device__ __forceinline__ unsigned ld4(const unsigned char *row, int col) {
+    const unsigned *w = reinterpret_cast<const unsigned *>(row) + (col >> 2);
+    const unsigned sh = (unsigned)(col & 3) * 8u;
+    const unsigned lo = w[0];
+    if (sh == 0u) return lo;
+    return __funnelshift_r(lo, w[1], sh);
+}
+__device__ __forceinline__ unsigned nz_bytes(unsigned x) {  // 0x80 in every byte of x that is non-zero
+    return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+}
+
+// sliding v-sum (window sv) of the indicator words of one column of a compact plane: acc[q], q = 0..7
+__device__ __forceinline__ void vsum8(const unsigned char *col, int WP, int sv, const unsigned *lut, unsigned (&acc)[8]) {
+    unsigned head[8];
+    unsigned a = 0u;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        head[r] = lut[col[r * WP]];
+        if (r < sv) a += head[r];
+    }
+    for (int r = 8; r < sv; ++r) a += lut[col[r * WP]];
+    acc[0] = a;
+#pragma unroll
+    for (int q = 1; q < 8; ++q) {
+        a += lut[col[(q + sv - 1) * WP]] - head[q - 1];
+        acc[q] = a;
+    }
+}
+
 template <bool VEC4>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 3)
 k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, FastGeom G, FastSmem L,
           unsigned *__restrict__ hard_list, unsigned *__restrict__ hard_count) {
     extern __shared__ __align__(16) unsigned char sm[];
     unsigned *raw = reinterpret_cast<unsigned *>(sm + L.raw);
     unsigned char *comp = sm + L.comp;
-    unsigned *ind = reinterpret_cast<unsigned *>(sm + L.ind);
-    unsigned *ring = reinterpret_cast<unsigned *>(sm + L.ring);
-    unsigned *slo = reinterpret_cast<unsigned *>(sm + L.slo);
-    unsigned *shi = reinterpret_cast<unsigned *>(sm + L.shi);
+    uint2 *ssum = reinterpret_cast<uint2 *>(sm + L.ssum);
     unsigned char *cflag = sm + L.cflag;
     unsigned short *elist = reinterpret_cast<unsigned short *>(sm + L.elist);
     __shared__ Hash H;
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int su = G.sten[0], sv = G.sten[1], sw = G.sten[2];
     const int ou = G.off[0], ov = G.off[1], ow = G.off[2];
-    const int VP = G.VP, WP = G.WP;
+    const int VP = G.VP, WP = G.WP, CR = G.CR;
     const int plane = VP * WP, oplane = TV * WP;
     const int nquad = plane >> 2, qpr = WP >> 2;  // quads per plane / per row
     const int NP = LU + su - 1;                   // input planes per segment
+
+    for (int i = tid; i < GMAX * (KMAX + 8); i += NT) {
+        const int g = i / (KMAX + 8), j = i - g * (KMAX + 8);
+        const int s = j - 1;
+        H.lut[g][j] = (j != 0 && (s >> 3) == g) ? (1u << ((s & 7) * 4)) : 0u;
+    }
 
     for (long long seg = blockIdx.x; seg < G.nsegs; seg += gridDim.x) {
         const long long tw = seg % G.segs[2];
@@ -125,18 +199,20 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
         const long long tu = r0 / G.segs[1];
         const long long u0 = tu * LU, v0 = tv * TV, w0 = tw * TW;  // output origin == input origin of the haloed block
         __syncthreads();
-        // ---- segment init: zero rings / sums / hash ----
+        // ---- segment init: zero running sums / hash ----
         {
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            uint4 *p4 = reinterpret_cast<uint4 *>(sm + L.ring);
-            const int n4 = (L.cflag - L.ring) / 16;  // ring, slo, shi are contiguous
+            uint4 *p4 = reinterpret_cast<uint4 *>(sm + L.ssum);
+            const int n4 = (L.cflag - L.ssum) / 16;
             for (int i = tid; i < n4; i += NT) p4[i] = z;
             for (int i = tid; i < HASH; i += NT) {
                 H.keys[i] = 0u;
-                H.slot[i] = 0xFF;
+                H.sl[i] = SL_PENDING;
+                H.lastp[i] = -(1 << 20);
             }
             if (tid == 0) {
-                H.nslots = 0;
+                H.freemask = ALL_SLOTS;
+                H.ovf = 0;
                 H.newflag = 0;
                 H.n_edge = 0;
             }
@@ -157,24 +233,31 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                     for (int e = 0; e < 4; ++e) qok[k] |= (gw + e < G.n[2]) ? (1u << e) : 0u;
             }
         }
-        int itoff[MAXIT], itg[MAXIT];  // v-pass items: offset inside a group plane (row vc*4, column c), group
+        int itoff[MAXIT], itg[MAXIT];  // v-pass items: offset inside a plane (row vc*8, column c), group
 #pragma unroll
         for (int k = 0; k < MAXIT; ++k) {
             const int it = tid + k * NT;
             const int c = it % WP;
             const int r = it / WP;
-            itoff[k] = (r % (TV / 4)) * 4 * WP + c;
-            itg[k] = r / (TV / 4);
+            itoff[k] = (r % (TV / 8)) * 8 * WP + c;
+            itg[k] = r / (TV / 8);
         }
-        // boundary-test invariants of my two output voxels (i = tid, tid + NT): which in-plane neighbours exist
-        unsigned nbmask[2];
+        // output-quad invariants (threads 0..NOQ-1): byte masks of existing neighbours / of in-bounds outputs
+        const int oq_b = tid / (TW / 4), oq_c = (tid % (TW / 4)) * 4;
+        unsigned mL = 0u, mR = 0u, mVlo = 0u, mVhi = 0u, mIn = 0u;
+        if (tid < NOQ) {
+            const long long cv = v0 + oq_b + ov;
+            mVlo = cv > 0 ? 0xFFFFFFFFu : 0u;
+            mVhi = cv + 1 < G.n[1] ? 0xFFFFFFFFu : 0u;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int i = tid + k * NT;
-            const int b = i / TW, c = i - b * TW;
-            const long long cv = v0 + b + ov, cw = w0 + c + ow;
-            nbmask[k] = (cv > 0 ? 1u : 0u) | (cv + 1 < G.n[1] ? 2u : 0u) | (cw > 0 ? 4u : 0u) | (cw + 1 < G.n[2] ? 8u : 0u);
+            for (int e = 0; e < 4; ++e) {
+                const long long cw = w0 + oq_c + e + ow;
+                if (cw > 0) mL |= 0xFFu << (8 * e);
+                if (cw + 1 < G.n[2]) mR |= 0xFFu << (8 * e);
+                if (v0 + oq_b < G.on[1] && w0 + oq_c + e < G.on[2]) mIn |= 0x80u << (8 * e);
+            }
         }
+        const long long out_rowoff = (v0 + oq_b) * G.ost[1] + (w0 + oq_c) * G.ost[2];
 
         auto load_quad = [&](int k, long long gu, uint4 &v) {
             v = make_uint4(0u, 0u, 0u, 0u);
@@ -227,41 +310,38 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 hidx[k][0] = hidx[k][1] = hidx[k][2] = hidx[k][3] = -1;
                 if (q < nquad) {
                     const uint4 a = reinterpret_cast<const uint4 *>(raw)[q];
-                    if (a.x != 0u) hidx[k][0] = hash_find_insert(H, a.x);
-                    if (a.y != 0u) hidx[k][1] = (a.y == a.x) ? hidx[k][0] : hash_find_insert(H, a.y);
-                    if (a.z != 0u) hidx[k][2] = (a.z == a.y) ? hidx[k][1] : hash_find_insert(H, a.z);
-                    if (a.w != 0u) hidx[k][3] = (a.w == a.z) ? hidx[k][2] : hash_find_insert(H, a.w);
+                    if (a.x != 0u) hidx[k][0] = hash_find_insert(H, a.x, p);
+                    if (a.y != 0u) hidx[k][1] = (a.y == a.x) ? hidx[k][0] : hash_find_insert(H, a.y, p);
+                    if (a.z != 0u) hidx[k][2] = (a.z == a.y) ? hidx[k][1] : hash_find_insert(H, a.z, p);
+                    if (a.w != 0u) hidx[k][3] = (a.w == a.z) ? hidx[k][2] : hash_find_insert(H, a.w, p);
                 }
             }
             __syncthreads();
-            // B. slots are published: compact-index plane + indicator planes; next raw plane
-            const int K = H.nslots;
-            if (K > KMAX) { aborted = true; break; }
-            if (H.newflag && tid < K) {  // ranks by id (tie-break of the arg-max: smallest id wins)
+            // B. slots are published: compact-index plane; next raw plane
+            if (H.ovf) { aborted = true; break; }
+            const unsigned long long used = ~H.freemask & ALL_SLOTS;  // stable until phase C
+            if (H.newflag && tid < KMAX && ((used >> tid) & 1ull)) {  // ranks by id (arg-max tie-break: smallest id wins)
                 const unsigned me = H.ids[tid];
                 int r = 0;
-                for (int s = 0; s < K; ++s) r += H.ids[s] < me;
-                H.rnk[tid] = (unsigned char)r;
+                for (unsigned long long m = used; m; m &= m - 1ull) r += H.ids[__ffsll((long long)m) - 1] < me;
+                H.tb[tid] = (unsigned short)(((255 - r) << 8) | tid);
             }
-            const int NG = (K + 7) >> 3;
-            unsigned char *cp = comp + (p % 3) * plane;
+            const int NG = used ? ((64 - __clzll((long long)used) + 7) >> 3) : 0;
+            unsigned char *cp = comp + (p % CR) * plane;
 #pragma unroll
             for (int k = 0; k < MAXQ; ++k) {
                 const int q = tid + k * NT;
                 if (q < nquad) {
-                    int j[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) j[e] = hidx[k][e] < 0 ? 0 : (int)H.slot[hidx[k][e]] + 1;
-                    reinterpret_cast<unsigned *>(cp)[q] = (unsigned)j[0] | ((unsigned)j[1] << 8) | ((unsigned)j[2] << 16) | ((unsigned)j[3] << 24);
-                    for (int g = 0; g < NG; ++g) {
-                        unsigned w4[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int s = j[e] - 1;
-                            w4[e] = (j[e] != 0 && (s >> 3) == g) ? (1u << ((s & 7) * 4)) : 0u;
-                        }
-                        reinterpret_cast<uint4 *>(ind + g * plane)[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                    const int h0 = hidx[k][0], h1 = hidx[k][1], h2 = hidx[k][2], h3 = hidx[k][3];
+                    const unsigned j0 = h0 < 0 ? 0u : H.sl[h0] + 1u;
+                    unsigned w4 = j0 * 0x01010101u;  // uniform quad (the common case)
+                    if (!(h1 == h0 && h2 == h0 && h3 == h0)) {
+                        const unsigned j1 = h1 < 0 ? 0u : H.sl[h1] + 1u;
+                        const unsigned j2 = h2 < 0 ? 0u : H.sl[h2] + 1u;
+                        const unsigned j3 = h3 < 0 ? 0u : H.sl[h3] + 1u;
+                        w4 = j0 | (j1 << 8) | (j2 << 16) | (j3 << 24);
                     }
+                    reinterpret_cast<unsigned *>(cp)[q] = w4;
                     reinterpret_cast<uint4 *>(raw)[q] = pre[k];
                 }
             }
@@ -270,48 +350,51 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 H.newflag = 0;
                 H.n_edge = 0;
             }
-            // C1. boundary flags of plane p-1 (needs planes p-2, p-1, p)
-            if (p >= 2 && p - 1 >= ou && p - 1 <= LU - 1 + ou) {
-                const int pc = p - 1;
-                const unsigned char *c0 = comp + ((p - 2) % 3) * plane, *c1 = comp + ((p - 1) % 3) * plane, *c2 = comp + (p % 3) * plane;
-                unsigned char *cf = cflag + (pc % G.CF) * (TV * TW);
-                const long long cu = u0 + pc;
-                const bool has_lo = cu > 0, has_hi = cu + 1 < G.n[0];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int i = tid + k * NT;
-                    const int b = i / TW, c = i - b * TW;
-                    const int q = (b + ov) * WP + (c + ow);
-                    const unsigned j = c1[q];
-                    bool e = false;
-                    if (j != 0u) {
-                        e = (has_lo && c0[q] != j) || (has_hi && c2[q] != j) || ((nbmask[k] & 1u) && c1[q - WP] != j) ||
-                            ((nbmask[k] & 2u) && c1[q + WP] != j) || ((nbmask[k] & 4u) && c1[q - 1] != j) ||
-                            ((nbmask[k] & 8u) && c1[q + 1] != j);
-                    }
-                    cf[i] = (unsigned char)(j | (e ? 0x80u : 0u));
+            // recycle the slots of ids that left the su-plane window (after this step their sum fields are zero again)
+            if (tid < KMAX && ((used >> tid) & 1ull)) {
+                const int h = H.owner[tid];
+                if (H.lastp[h] + su <= p) {
+                    H.sl[h] = SL_DEAD;
+                    atomicOr(&H.freemask, 1ull << tid);
                 }
             }
-            // C2. v-pass (4-bit fields) + running sum over the last su planes (8-bit fields)
+            // C1. boundary flags of plane p-1 (needs planes p-2, p-1, p), four voxels per thread
+            if (tid < NOQ && p >= 2 && p - 1 >= ou && p - 1 <= LU - 1 + ou) {
+                const int pc = p - 1;
+                const unsigned char *c0 = comp + ((p - 2) % CR) * plane, *c1 = comp + ((p - 1) % CR) * plane, *c2 = comp + (p % CR) * plane;
+                const long long cu = u0 + pc;
+                const unsigned mUlo = cu > 0 ? 0xFFFFFFFFu : 0u, mUhi = cu + 1 < G.n[0] ? 0xFFFFFFFFu : 0u;
+                const int rowo = (oq_b + ov) * WP, col = oq_c + ow;
+                const unsigned C = ld4(c1 + rowo, col);
+                unsigned D = ((C ^ ld4(c0 + rowo, col)) & mUlo) | ((C ^ ld4(c2 + rowo, col)) & mUhi);
+                D |= ((C ^ ld4(c1 + rowo - WP, col)) & mVlo) | ((C ^ ld4(c1 + rowo + WP, col)) & mVhi);
+                D |= ((C ^ ld4(c1 + rowo, col - 1)) & mL) | ((C ^ ld4(c1 + rowo, col + 1)) & mR);
+                reinterpret_cast<unsigned *>(cflag + (pc % G.CF) * (TV * TW))[tid] = C | (nz_bytes(D) & nz_bytes(C));
+            }
+            // C2. v-sums (4-bit fields) of the entering plane p and of the leaving plane p - su; their difference
+            //     advances the running sum over the last su planes (8-bit fields)
             {
-                const int slot = p % su;
+                const unsigned char *cn = comp + (p % CR) * plane;
+                const unsigned char *co = comp + ((p + 1) % CR) * plane;  // == (p - su) % CR since CR == su + 1
+                const bool has_old = p >= su;
 #pragma unroll
                 for (int k = 0; k < MAXIT; ++k) {
-                    if (tid + k * NT >= NG * (TV / 4) * WP) break;
+                    if (tid + k * NT >= NG * (TV / 8) * WP) break;
                     const int g = itg[k];
-                    const unsigned *ip = ind + g * plane + itoff[k];
-                    unsigned acc = 0u;
-                    for (int r = 0; r < sv; ++r) acc += ip[r * WP];
-                    unsigned *rp = ring + (g * su + slot) * oplane + itoff[k];
-                    unsigned *lo = slo + g * oplane + itoff[k];
-                    unsigned *hi = shi + g * oplane + itoff[k];
+                    const unsigned *lut = H.lut[g];
+                    unsigned an[8], ao[8];
+                    vsum8(cn + itoff[k], WP, sv, lut, an);
+                    if (has_old) vsum8(co + itoff[k], WP, sv, lut, ao);
+                    uint2 *sp = ssum + g * oplane + itoff[k];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (q) acc += ip[(q + sv - 1) * WP] - ip[(q - 1) * WP];
-                        const unsigned old = rp[q * WP];
-                        rp[q * WP] = acc;
-                        lo[q * WP] += (acc & 0x0F0F0F0Fu) - (old & 0x0F0F0F0Fu);
-                        hi[q * WP] += ((acc >> 4) & 0x0F0F0F0Fu) - ((old >> 4) & 0x0F0F0F0Fu);
+                    for (int q = 0; q < 8; ++q) {
+                        const unsigned a = an[q], o = has_old ? ao[q] : 0u;
+                        if (a != o) {
+                            uint2 s2 = sp[q * WP];
+                            s2.x += (a & 0x0F0F0F0Fu) - (o & 0x0F0F0F0Fu);
+                            s2.y += ((a >> 4) & 0x0F0F0F0Fu) - ((o >> 4) & 0x0F0F0F0Fu);
+                            sp[q * WP] = s2;
+                        }
                     }
                 }
             }
@@ -321,19 +404,22 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             if (uo >= 0 && u0 + uo < G.on[0]) {
                 const unsigned char *cf = cflag + ((uo + ou) % G.CF) * (TV * TW);
                 unsigned long long *orow = out + (u0 + uo) * G.ost[0];
+                if (tid < NOQ && mIn) {
+                    const unsigned E = reinterpret_cast<const unsigned *>(cf)[tid] & mIn;  // 0x80 per in-bounds boundary voxel
+                    unsigned long long *o4 = orow + out_rowoff;
+                    if (E == 0u && mIn == 0x80808080u && G.out_vec) {
+                        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                        reinterpret_cast<uint4 *>(o4)[0] = z;
+                        reinterpret_cast<uint4 *>(o4)[1] = z;
+                    } else {
+                        const int n = __popc(E);
+                        int base = n ? atomicAdd(&H.n_edge, n) : 0;
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int i = tid + k * NT;
-                    const int b = i / TW, c = i - b * TW;
-                    const long long gv = v0 + b, gw = w0 + c;
-                    const bool inside = gv < G.on[1] && gw < G.on[2];
-                    const bool e = inside && (cf[i] & 0x80u);
-                    const unsigned m = __ballot_sync(0xffffffffu, e);
-                    int base = 0;
-                    if (lane == 0 && m) base = atomicAdd(&H.n_edge, __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (e) elist[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
-                    else if (inside) orow[gv * G.ost[1] + gw * G.ost[2]] = 0ull;
+                        for (int e = 0; e < 4; ++e) {
+                            if (E & (0x80u << (8 * e))) elist[base++] = (unsigned short)(tid * 4 + e);
+                            else if (mIn & (0x80u << (8 * e))) o4[e * G.ost[2]] = 0ull;
+                        }
+                    }
                 }
                 __syncthreads();
                 const int ne = H.n_edge;
@@ -343,23 +429,34 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                     const int jc = cf[i] & 0x7F;
                     unsigned best = 0u;
                     for (int g = 0; g < NG; ++g) {
-                        const unsigned *lo = slo + g * oplane + b * WP + c;
-                        const unsigned *hi = shi + g * oplane + b * WP + c;
+                        const uint2 *sp = ssum + g * oplane + b * WP + c;
                         unsigned c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
-                        for (int r = 0; r < sw; ++r) {
-                            const unsigned l = lo[r], h = hi[r];
-                            c0 += l & 0x00FF00FFu;         // slots 0, 4
-                            c1 += (l >> 8) & 0x00FF00FFu;  // slots 2, 6
-                            c2 += h & 0x00FF00FFu;         // slots 1, 5
-                            c3 += (h >> 8) & 0x00FF00FFu;  // slots 3, 7
+                        int r = 0;
+                        if (G.pair_ok) {  // add two ring sums in 8-bit fields first (2*su*sv <= 255), then widen
+                            for (; r + 1 < sw; r += 2) {
+                                const uint2 a = sp[r], d = sp[r + 1];
+                                const unsigned l = a.x + d.x, h = a.y + d.y;
+                                c0 += l & 0x00FF00FFu;
+                                c1 += (l >> 8) & 0x00FF00FFu;
+                                c2 += h & 0x00FF00FFu;
+                                c3 += (h >> 8) & 0x00FF00FFu;
+                            }
                         }
+                        for (; r < sw; ++r) {
+                            const uint2 a = sp[r];
+                            c0 += a.x & 0x00FF00FFu;         // slots 0, 4
+                            c1 += (a.x >> 8) & 0x00FF00FFu;  // slots 2, 6
+                            c2 += a.y & 0x00FF00FFu;         // slots 1, 5
+                            c3 += (a.y >> 8) & 0x00FF00FFu;  // slots 3, 7
+                        }
+                        if ((c0 | c1 | c2 | c3) == 0u) continue;
                         const unsigned cnt[8] = {c0 & 0xFFFFu, c2 & 0xFFFFu, c1 & 0xFFFFu, c3 & 0xFFFFu,
                                                  c0 >> 16,     c2 >> 16,     c1 >> 16,     c3 >> 16};
 #pragma unroll
                         for (int n = 0; n < 8; ++n) {
                             const int s = g * 8 + n;
-                            if (s < K && s + 1 != jc && cnt[n] != 0u) {
-                                const unsigned key = (cnt[n] << 16) | ((255u - H.rnk[s]) << 8) | (unsigned)s;
+                            if (s + 1 != jc && cnt[n] != 0u) {  // free slots have zero counts
+                                const unsigned key = (cnt[n] << 16) | H.tb[s];
                                 best = key > best ? key : best;
                             }
                         }

@@ -478,11 +478,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const T *__restrict__ cell,
             }
         }
         if (A.do_cell_props) wtab_flush<WS>(*ctab, cell_t, G, Tc, lane);
-        if (A.do_sub_props)
-            for (int c = 0; c < A.n_sub; ++c) wtab_flush<WSS>(stab[c], A.sub_t[c], G, Tc, lane);
+        for (int c = 0; c < A.n_sub; ++c) {
+            if (A.do_sub_props) wtab_flush<WSS>(stab[c], A.sub_t[c], G, Tc, lane);
+            ptab_flush<PS>(ptab[c], A.pair_t[c], lane);  // per tile: a full private table would degrade every probe
+        }
         cur = nxt;
     }
-    for (int c = 0; c < A.n_sub; ++c) ptab_flush<PS>(ptab[c], A.pair_t[c], lane);
 }
 
 // choose the lane axis = smallest stride, row axis = next, slow axis = largest; degenerate axes (extent 1) go first

@@ -20,9 +20,12 @@ if what == "props":
         dev.find_object_properties(tab, lab)
 elif what == "map":
     cell = dev.synth_labels((S, S, S), pitch=pitch, seed=1, order=order)
-    subs = torch.stack([dev.synth_labels((S, S, S), pitch=(12, 12, 6), seed=1, kind=1 + c, density16=1) for c in range(3)])
     if order == "F":
-        subs = torch.stack([dev.synth_labels((S, S, S), pitch=(12, 12, 6), seed=1, kind=1 + c, density16=1, order="F") for c in range(3)])
+        subs = torch.empty((3, S, S, S), dtype=torch.int64, device="cuda").permute(0, 3, 2, 1)
+    else:
+        subs = torch.empty((3, S, S, S), dtype=torch.int64, device="cuda")
+    for c in range(3):
+        dev.synth_labels((S, S, S), pitch=(12, 12, 6), seed=1, kind=1 + c, density16=1, out=subs[c])
     ct = dev.IdTable(1 << 18)
     sts = [dev.IdTable(1 << 18) for _ in range(3)]
     pts = [dev.PairTable(1 << 18) for _ in range(3)]
