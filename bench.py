@@ -284,8 +284,13 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_detect_cs (fused detect_seg_boundaries + process_block_nonzero)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (per launch)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_cs_fast"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_cs_fast (fused detect_seg_boundaries + process_block_nonzero)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
                 "share_of_step": float(np.sum(cs_ms)) / ms}
@@ -319,16 +324,26 @@ def e2e_host(args, chunks):
     from syconn_b200.extraction import _host
     from syconn_b200.extraction.find_object_properties import detect_cs
     n = min(args.e2e_chunks, len(chunks))
-    host = []
+
+    def pinned(t):  # host copy in pinned memory (what a loader thread would hand to the plugin)
+        # keep the device tensor's memory order (x fastest) so that the host array is the production ZYX block
+        h = torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        return h
+    host, keep = [], []
     for (s, off, cell, subs, halo) in chunks[:n]:
-        host.append((cell.cpu().numpy().view(np.uint64), subs.cpu().numpy().view(np.uint64), halo.cpu().numpy().view(np.uint32)))
+        hc, hs, hh = pinned(cell), pinned(subs), pinned(halo)
+        oshape = tuple(halo.shape[i] - STENCIL[i] + 1 for i in range(3))
+        ho = torch.empty(oshape, dtype=torch.int64, pin_memory=True)
+        keep.append((hc, hs, hh, ho))
+        host.append((hc.numpy().view(np.uint64), hs.numpy().view(np.uint64), hh.numpy().view(np.uint32), ho.numpy().view(np.uint64)))
     h2d = d2h = 0
 
     def one_pass():
         nonlocal h2d, d2h
         h2d = d2h = 0
-        for cell, subs, halo in host:
-            contacts = detect_cs(halo, STENCIL)
+        for cell, subs, halo, cbuf in host:
+            contacts = detect_cs(halo, STENCIL, out=cbuf)
             h2d += halo.nbytes
             d2h += contacts.nbytes
             r = _host.find_object_properties_records(contacts)
@@ -348,7 +363,7 @@ def e2e_host(args, chunks):
     vox = sum(int(c[0].size) for c in host)
     return {"value": vox / dt / 1e9, "unit": "GVoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "chunks_per_step": n, "api": "syk_detect_cs_host + syk_find_object_properties_host + "
-                                        "syk_map_subcell_extract_props_host (pageable host buffers)"}
+                                        "syk_map_subcell_extract_props_host (pinned host buffers, one synchronous call per stage and chunk)"}
 
 
 if __name__ == "__main__":

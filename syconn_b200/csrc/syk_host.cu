@@ -59,10 +59,28 @@ __global__ void k_synth(void *out, int elem_bytes, long long nx, long long ny, l
     }
 }
 
+// Device scratch of the host entry points comes from the stream-ordered pool (kept warm between calls: a call per
+// chunk must not pay cudaMalloc/cudaFree round trips for gigabyte buffers).
+static void pool_keep_warm() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+}
+static cudaError_t dev_alloc(void **p, size_t bytes) {
+    pool_keep_warm();
+    return cudaMallocAsync(p, bytes ? bytes : 16, (cudaStream_t)0);
+}
 struct DevBuf {
     void *p = nullptr;
     ~DevBuf() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, (cudaStream_t)0);
     }
 };
 
@@ -109,7 +127,7 @@ static int export_to_host(syk_table_t *t, const syk_chunk_geom_t *geom, syk_reco
     *out = nullptr;
     if (n == 0) return SYK_OK;
     DevBuf recs;
-    SYK_CUDA(cudaMalloc(&recs.p, n * sizeof(syk_record_t)));
+    SYK_CUDA(dev_alloc(&recs.p, n * sizeof(syk_record_t)));
     rc = syk_table_export(t, geom, 1, (syk_record_t *)recs.p, n, &n, nullptr);
     if (rc) return rc;
     *out = (syk_record_t *)malloc(n * sizeof(syk_record_t));
@@ -154,7 +172,7 @@ SYK_API int syk_find_object_properties_host(const void *labels_host, int elem_by
     rc = check_dense(shape, strides, 3);
     if (rc) return rc;
     DevBuf lab;
-    SYK_CUDA(cudaMalloc(&lab.p, nvox * elem_bytes));
+    SYK_CUDA(dev_alloc(&lab.p, nvox * elem_bytes));
     SYK_CUDA(cudaMemcpy(lab.p, labels_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
     const int64_t origin[3] = {0, 0, 0};
     syk_chunk_geom_t geom;
@@ -202,11 +220,11 @@ SYK_API int syk_map_subcell_extract_props_host(const void *cell_host, const int6
         if (rc) return rc;
     }
     DevBuf cell, sub;
-    SYK_CUDA(cudaMalloc(&cell.p, nvox * elem_bytes));
+    SYK_CUDA(dev_alloc(&cell.p, nvox * elem_bytes));
     SYK_CUDA(cudaMemcpy(cell.p, cell_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
     const void *subp[4] = {nullptr, nullptr, nullptr, nullptr};
     if (n_sub) {
-        SYK_CUDA(cudaMalloc(&sub.p, nvox * elem_bytes * n_sub));
+        SYK_CUDA(dev_alloc(&sub.p, nvox * elem_bytes * n_sub));
         SYK_CUDA(cudaMemcpy(sub.p, subcell_host, nvox * elem_bytes * n_sub, cudaMemcpyHostToDevice));
         for (int c = 0; c < n_sub; ++c) subp[c] = (const char *)sub.p + (size_t)c * sub_strides[0] * elem_bytes;
     }
@@ -236,7 +254,7 @@ SYK_API int syk_map_subcell_extract_props_host(const void *cell_host, const int6
             uint64_t np = 0;
             DevBuf pb;
             const uint64_t maxp = pt[c]->capacity;
-            SYK_CUDA(cudaMalloc(&pb.p, maxp * sizeof(syk_pair_t)));
+            SYK_CUDA(dev_alloc(&pb.p, maxp * sizeof(syk_pair_t)));
             rc = syk_pairs_export(pt[c], (syk_pair_t *)pb.p, maxp, &np, nullptr);
             if (rc) break;
             n_pairs_out[c] = np;
@@ -287,15 +305,15 @@ static int cs_host_impl(const void *edges_host, int edge_bytes, const int64_t *e
     rc = check_dense(shape, strides, 3);
     if (rc) return rc;
     DevBuf arr, edg, out;
-    SYK_CUDA(cudaMalloc(&arr.p, nvox * elem_bytes));
+    SYK_CUDA(dev_alloc(&arr.p, nvox * elem_bytes));
     SYK_CUDA(cudaMemcpy(arr.p, arr_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
     if (edges_host) {
         rc = check_dense(shape, edge_strides, 3);
         if (rc) return rc;
-        SYK_CUDA(cudaMalloc(&edg.p, nvox * edge_bytes));
+        SYK_CUDA(dev_alloc(&edg.p, nvox * edge_bytes));
         SYK_CUDA(cudaMemcpy(edg.p, edges_host, nvox * edge_bytes, cudaMemcpyHostToDevice));
     }
-    SYK_CUDA(cudaMalloc(&out.p, nout * 8));
+    SYK_CUDA(dev_alloc(&out.p, nout * 8));
     const int64_t ost[3] = {oshape[1] * oshape[2], oshape[2], 1};
     if (edges_host)
         rc = syk_process_block_nonzero(edg.p, edge_bytes, edge_strides, arr.p, elem_bytes, strides, shape, stencil, (uint64_t *)out.p,
@@ -330,9 +348,9 @@ SYK_API int syk_detect_seg_boundaries_host(const void *arr_host, int elem_bytes,
     rc = check_dense(shape, strides, 3);
     if (rc) return rc;
     DevBuf arr, out;
-    SYK_CUDA(cudaMalloc(&arr.p, nvox * elem_bytes));
+    SYK_CUDA(dev_alloc(&arr.p, nvox * elem_bytes));
     SYK_CUDA(cudaMemcpy(arr.p, arr_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
-    SYK_CUDA(cudaMalloc(&out.p, nvox));
+    SYK_CUDA(dev_alloc(&out.p, nvox));
     rc = syk_detect_seg_boundaries(arr.p, elem_bytes, shape, strides, (uint8_t *)out.p, nullptr);
     if (rc) return rc;
     SYK_CUDA(cudaMemcpy(out_host, out.p, nvox, cudaMemcpyDeviceToHost));

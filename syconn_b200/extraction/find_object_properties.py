@@ -25,10 +25,11 @@ def detect_seg_boundaries(arr):
     return out.view(np.bool_)
 
 
-def detect_cs(arr, stencil=None):
+def detect_cs(arr, stencil=None, out=None):
     """syconn/extraction/find_object_properties.py:458-472.  Boundary mask and partner stencil are fused in one
     kernel (``syk_detect_cs_host``); uint64 input is narrowed to uint32 exactly like the caller-side
-    ``.astype(np.uint32)`` (cs_extraction_steps.py:385-387).  ``stencil`` overrides the config default."""
+    ``.astype(np.uint32)`` (cs_extraction_steps.py:385-387).  ``stencil`` overrides the config default; ``out`` may be a
+    preallocated C-contiguous uint64 array of the output shape (e.g. pinned memory)."""
     arr = np.asarray(arr)
     if arr.dtype not in (np.uint32, np.uint64):
         raise ValueError(f"Buffer dtype mismatch, expected 'uint32_t' but got '{arr.dtype}'")
@@ -37,7 +38,9 @@ def detect_cs(arr, stencil=None):
     st = [int(s) for s in stencil]
     assert (st[0] % 2 + st[1] % 2 + st[2] % 2) == 3
     oshape = tuple(max(0, arr.shape[i] - st[i] + 1) for i in range(3))
-    out = np.zeros(oshape, np.uint64)
+    if out is None:
+        out = np.empty(oshape, np.uint64)
+    assert out.shape == oshape and out.dtype == np.uint64 and out.flags.c_contiguous
     if out.size == 0:
         return out
     arr = dense_view(arr)
