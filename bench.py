@@ -241,16 +241,34 @@ def run_ours(args):
     def step(timed):
         pipe.reset()
         pipe.cs_events = cs_events if timed else None   # dominant kernel: bracket every k_detect_cs launch
+        dbg = os.environ.get("SYK_BENCH_DEBUG")
+        if dbg:
+            torch.cuda.synchronize()
+            t_0 = time.perf_counter()
         for (s, off, cell, subs, halo) in chunks:
             pipe.process_chunk(s, off, cell, subs, halo)
+        if dbg:
+            torch.cuda.synchronize()
+            t_1 = time.perf_counter()
         owned, owned_pairs = pipe.finish()
-        return pipe.reduce_on_device(owned, owned_pairs, geoms)
+        if dbg:
+            torch.cuda.synchronize()
+            t_2 = time.perf_counter()
+        r = pipe.reduce_on_device(owned, owned_pairs, geoms)
+        if dbg:
+            torch.cuda.synchronize()
+            print(f"[rank {rank}] chunks {1e3*(t_1-t_0):.1f} ms, finish {1e3*(t_2-t_1):.1f} ms, reduce {1e3*(time.perf_counter()-t_2):.1f} ms",
+                  file=sys.stderr, flush=True)
+        return r
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    if world > 1:  # NCCL sets its channels up lazily over the first exchanges: get that out of the way first
+        for _ in range(3):
+            res = step(False)
     for _ in range(args.warmup):
         res = step(False)
     barrier()

@@ -354,7 +354,7 @@ static void cs_plan(const int64_t shape[3], const int64_t strides[3], const int3
 // The fast path needs: every stencil dim >= 3 (the boundary test of a centre plane uses its two neighbour planes),
 // 4-bit fields for the v-sum (sv <= 15), 8-bit fields for the plane ring sum (su*sv <= 255), 16-bit totals, and the
 // haloed plane / rings must fit the CTA's shared memory.
-static bool fast_plan(const CsGeom &C, csfast::FastGeom &F, csfast::FastSmem &L) {
+static bool fast_plan(const CsGeom &C, csfast::FastGeom &F) {
     using namespace csfast;
     for (int a = 0; a < 3; ++a)
         if (C.sten[a] < 3) return false;
@@ -379,8 +379,8 @@ static bool fast_plan(const CsGeom &C, csfast::FastGeom &F, csfast::FastSmem &L)
     F.vec4 = 0;
     F.pair_ok = (2 * C.sten[0] * C.sten[1] <= 255) ? 1 : 0;
     F.out_vec = 0;
-    if (F.VP * F.WP / 4 > MAXQ * NT || GMAX * (TV / 8) * F.WP > MAXIT * NT || F.nsegs >= (1ll << 31)) return false;
-    L = fast_layout(F);
+    if (F.VP * F.WP / 4 > MAX_NQUAD || F.WP > MAX_WP || F.nsegs >= (1ll << 30)) return false;
+    const csfast::FastSmem L = fast_layout(F, GMAX_T2);
     return L.total <= 200 * 1024;
 }
 
@@ -415,42 +415,58 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
     long long grid = (long long)sms * bps;
     if (grid > G.ntiles) grid = G.ntiles;
     csfast::FastGeom F;
-    csfast::FastSmem L;
-    if (edges == nullptr && !getenv("SYK_CS_GENERIC") && fast_plan(G, F, L)) {
-        // fast path; segments with too many distinct ids are listed and redone by the generic kernel
-        unsigned *hard = nullptr;
-        SYK_CUDA(cudaMallocAsync((void **)&hard, sizeof(unsigned) * (size_t)(F.nsegs + 1), s));
-        SYK_CUDA(cudaMemsetAsync(hard, 0, sizeof(unsigned), s));
+    if (edges == nullptr && !getenv("SYK_CS_GENERIC") && fast_plan(G, F)) {
+        using namespace csfast;
+        // tier 1 (<= 24 ids near the plane, many CTAs/SM) -> tier 2 (<= 64 ids) on the listed segments -> generic kernel
+        unsigned *hard = nullptr;  // [count1, count2, list1[nsegs], list2[nsegs]]
+        SYK_CUDA(cudaMallocAsync((void **)&hard, sizeof(unsigned) * (size_t)(2 * F.nsegs + 2), s));
+        SYK_CUDA(cudaMemsetAsync(hard, 0, 2 * sizeof(unsigned), s));
+        unsigned *cnt1 = hard, *cnt2 = hard + 1, *list1 = hard + 2, *list2 = hard + 2 + F.nsegs;
         // rows of uint32 that are 16-byte aligned everywhere => LDG.128 quads
         F.vec4 = (elem_bytes == 4 && F.ist[2] == 1 && (F.ist[0] % 4) == 0 && (F.ist[1] % 4) == 0 && ((uintptr_t)arr % 16) == 0) ? 1 : 0;
         F.out_vec = (F.ost[2] == 1 && (F.ost[0] % 2) == 0 && (F.ost[1] % 2) == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
-        int ctas = (int)((227 * 1024) / (L.total + 3072));
-        if (ctas > 3) ctas = 3;
-        if (ctas < 1) ctas = 1;
-        long long fgrid = (long long)sms * ctas;
-        if (fgrid > F.nsegs) fgrid = F.nsegs;
+        const FastSmem L1 = fast_layout(F, GMAX_T1), L2 = fast_layout(F, GMAX_T2);
+        constexpr int MINB1 = 6, MINB2 = 2;
+        int ctas1 = (int)((227 * 1024) / (L1.total + (int)sizeof(HashT<GMAX_T1>) + 1280));
+        if (ctas1 > MINB1) ctas1 = MINB1;
+        if (ctas1 < 1) ctas1 = 1;
+        int ctas2 = (int)((227 * 1024) / (L2.total + (int)sizeof(HashT<GMAX_T2>) + 1280));
+        if (ctas2 > MINB2) ctas2 = MINB2;
+        if (ctas2 < 1) ctas2 = 1;
+        long long g1 = (long long)sms * ctas1;
+        if (g1 > F.nsegs) g1 = F.nsegs;
+        const long long g2 = (long long)sms * ctas2;
+        unsigned long long *o = (unsigned long long *)out;
         if (F.vec4) {
-            SYK_CUDA(cudaFuncSetAttribute(csfast::k_cs_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-            csfast::k_cs_fast<true><<<(unsigned)fgrid, csfast::NT, L.total, s>>>(arr, (unsigned long long *)out, F, L, hard + 1, hard);
+            auto k1 = k_cs_fast<true, GMAX_T1, NT_T1, MINB1>;
+            auto k2 = k_cs_fast<true, GMAX_T2, NT_T2, MINB2>;
+            SYK_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
+            SYK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
+            k1<<<(unsigned)g1, NT_T1, L1.total, s>>>(arr, o, F, L1, nullptr, nullptr, list1, cnt1);
+            k2<<<(unsigned)g2, NT_T2, L2.total, s>>>(arr, o, F, L2, list1, cnt1, list2, cnt2);
         } else {
-            SYK_CUDA(cudaFuncSetAttribute(csfast::k_cs_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-            csfast::k_cs_fast<false><<<(unsigned)fgrid, csfast::NT, L.total, s>>>(arr, (unsigned long long *)out, F, L, hard + 1, hard);
+            auto k1 = k_cs_fast<false, GMAX_T1, NT_T1, MINB1>;
+            auto k2 = k_cs_fast<false, GMAX_T2, NT_T2, MINB2>;
+            SYK_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
+            SYK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
+            k1<<<(unsigned)g1, NT_T1, L1.total, s>>>(arr, o, F, L1, nullptr, nullptr, list1, cnt1);
+            k2<<<(unsigned)g2, NT_T2, L2.total, s>>>(arr, o, F, L2, list1, cnt1, list2, cnt2);
         }
         SYK_CUDA(cudaGetLastError());
-        G.seg_list = hard + 1;
-        G.seg_count = hard;
+        G.seg_list = list2;
+        G.seg_count = cnt2;
         for (int a = 0; a < 3; ++a) G.segs[a] = F.segs[a];
-        G.seg_tiles[0] = csfast::LU / OU;
-        G.seg_tiles[1] = csfast::TV / OV;
-        G.seg_tiles[2] = csfast::TW / OW;
-        k_detect_cs<<<(unsigned)((long long)sms * bps), CS_THREADS, smem, s>>>(arr, nullptr, (unsigned long long *)out, G);
+        G.seg_tiles[0] = LU / OU;
+        G.seg_tiles[1] = TV / OV;
+        G.seg_tiles[2] = TW / OW;
+        k_detect_cs<<<(unsigned)((long long)sms * bps), CS_THREADS, smem, s>>>(arr, nullptr, o, G);
         SYK_CUDA(cudaGetLastError());
         if (getenv("SYK_CS_DEBUG")) {
-            unsigned nh = 0;
-            cudaMemcpyAsync(&nh, hard, sizeof(nh), cudaMemcpyDeviceToHost, s);
+            unsigned nh[2] = {0, 0};
+            cudaMemcpyAsync(nh, hard, sizeof(nh), cudaMemcpyDeviceToHost, s);
             cudaStreamSynchronize(s);
-            fprintf(stderr, "[syk] detect_cs fast path: %lld segments, %u redone by the generic kernel, smem %d B, vec4=%d out_vec=%d\n",
-                    F.nsegs, nh, L.total, F.vec4, F.out_vec);
+            fprintf(stderr, "[syk] detect_cs fast path: %lld segments, %u redone by tier 2, %u by the generic kernel; smem %d / %d B, "
+                            "CTAs/SM %d / %d, vec4=%d out_vec=%d\n", F.nsegs, nh[0], nh[1], L1.total, L2.total, ctas1, ctas2, F.vec4, F.out_vec);
         }
         SYK_CUDA(cudaFreeAsync(hard, s));
         return SYK_OK;

@@ -27,13 +27,14 @@ namespace csfast {
 constexpr int TV = 16;
 constexpr int TW = 32;
 constexpr int LU = SYK_LU;
-constexpr int NT = 256;
-constexpr int GMAX = 6;
-constexpr int KMAX = GMAX * 8;  // <= 64 (slot masks are 64 bit), <= 127 (compact index + boundary flag in one byte)
 constexpr int HASH = 256;
-constexpr int MAXQ = 2;   // relabel quads (4 voxels along w) per thread: ceil(VP*WP/4 / NT)
-constexpr int MAXIT = 3;  // v-pass items (8 outputs each) per thread: ceil(GMAX*(TV/8)*WP / NT)
 constexpr int NOQ = TV * TW / 4;  // output quads per plane (128)
+constexpr int MAX_NQUAD = 320;    // host guarantees VP*WP/4 <= MAX_NQUAD
+constexpr int MAX_WP = 48;        // host guarantees WP <= MAX_WP
+// Two tiers of the same kernel: tier 1 keeps at most 24 ids near the marching plane (small shared-memory footprint,
+// many CTAs per SM); the few segments that need more are redone by tier 2 (64 ids), then by the generic kernel.
+constexpr int GMAX_T1 = 3, NT_T1 = 160;
+constexpr int GMAX_T2 = 8, NT_T2 = 320;
 
 struct FastGeom {
     long long n[3];    // input extents (internal axes u, v, w)
@@ -56,7 +57,7 @@ struct FastSmem {  // offsets in bytes into dynamic shared memory
     int raw, comp, ssum, cflag, elist, total;
 };
 
-inline FastSmem fast_layout(const FastGeom &G) {
+inline FastSmem fast_layout(const FastGeom &G, int GMAX) {
     FastSmem L;
     const int plane = G.VP * G.WP;
     const int oplane = TV * G.WP;
@@ -73,9 +74,10 @@ inline FastSmem fast_layout(const FastGeom &G) {
 
 constexpr unsigned SL_PENDING = 0xFFFFFFFFu;  // key inserted, slot being allocated
 constexpr unsigned SL_DEAD = 0xFFFFFFFEu;     // id left the su-plane window: its slot was recycled
-constexpr unsigned long long ALL_SLOTS = (KMAX >= 64) ? ~0ull : ((1ull << KMAX) - 1ull);
-
-struct Hash {
+template <int GMAX>
+struct HashT {
+    static constexpr int KMAX = GMAX * 8;  // <= 64 (slot masks are 64 bit), <= 127 (index + boundary flag in a byte)
+    static constexpr unsigned long long ALL_SLOTS = (KMAX >= 64) ? ~0ull : ((1ull << KMAX) - 1ull);
     unsigned keys[HASH];
     unsigned sl[HASH];             // compact slot of the key | SL_PENDING | SL_DEAD
     int lastp[HASH];               // last plane in which the key was seen
@@ -88,6 +90,7 @@ struct Hash {
 };
 
 // hand out the lowest free compact slot to hash entry h (id lab); raises H.ovf when none is left
+template <typename Hash>
 __device__ __forceinline__ void slot_alloc(Hash &H, unsigned h, unsigned lab) {
     for (;;) {
         const unsigned long long m = *(volatile unsigned long long *)&H.freemask;
@@ -109,7 +112,8 @@ __device__ __forceinline__ void slot_alloc(Hash &H, unsigned h, unsigned lab) {
 
 // find the hash index of `lab` (!= 0) at plane p, inserting it (and allocating a compact slot) when it is new or
 // when its slot was recycled; slots become visible to other threads after the next barrier
-__device__ __forceinline__ int hash_find_insert(Hash &H, unsigned lab, int p) {
+template <typename Hash>
+__device__ __noinline__ int hash_find_insert(Hash &H, unsigned lab, int p) {
     unsigned h = (lab * 2654435761u) >> (32 - 8);  // HASH == 256
     for (int probes = 0; probes < HASH; ++probes) {
         const unsigned cur = H.keys[h];
@@ -166,10 +170,17 @@ __device__ __forceinline__ void vsum8(const unsigned char *col, int WP, int sv, 
     }
 }
 
-template <bool VEC4>
-__global__ void __launch_bounds__(NT, 3)
+// seg_list == nullptr: all G.nsegs segments; otherwise the *seg_count segments named in seg_list (tier 2)
+template <bool VEC4, int GMAX, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, FastGeom G, FastSmem L,
+          const unsigned *__restrict__ seg_list, const unsigned *__restrict__ seg_count,
           unsigned *__restrict__ hard_list, unsigned *__restrict__ hard_count) {
+    using Hash = HashT<GMAX>;
+    constexpr int KMAX = Hash::KMAX;
+    constexpr unsigned long long ALL_SLOTS = Hash::ALL_SLOTS;
+    constexpr int MAXQ = (MAX_NQUAD + NT - 1) / NT;             // relabel quads (4 voxels along w) per thread
+    constexpr int MAXIT = (GMAX * (TV / 8) * MAX_WP + NT - 1) / NT;  // v-pass items (8 outputs each) per thread
     extern __shared__ __align__(16) unsigned char sm[];
     unsigned *raw = reinterpret_cast<unsigned *>(sm + L.raw);
     unsigned char *comp = sm + L.comp;
@@ -192,7 +203,9 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
         H.lut[g][j] = (j != 0 && (s >> 3) == g) ? (1u << ((s & 7) * 4)) : 0u;
     }
 
-    for (long long seg = blockIdx.x; seg < G.nsegs; seg += gridDim.x) {
+    const long long nwork = seg_list ? (long long)(*seg_count) : G.nsegs;
+    for (long long wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+        const long long seg = seg_list ? (long long)seg_list[wi] : wi;
         const long long tw = seg % G.segs[2];
         const long long r0 = seg / G.segs[2];
         const long long tv = r0 % G.segs[1];
@@ -281,6 +294,39 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             v = make_uint4(t[0], t[1], t[2], t[3]);
         };
 
+        // zeros for the non-boundary voxels of output plane p - su + 1 and the compacted list of its boundary voxels
+        // (threads NT-NOQ .. NT-1, so that it overlaps the boundary test of threads 0 .. NOQ-1)
+        const bool early_d = ou >= 2;  // the flags of plane p - ou are then already complete in phase C of step p
+        const int dq = tid - (NT - NOQ);
+        const int dq_b = dq / (TW / 4), dq_c = (dq % (TW / 4)) * 4;
+        unsigned dIn = 0u;
+        if (dq >= 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (v0 + dq_b < G.on[1] && w0 + dq_c + e < G.on[2]) dIn |= 0x80u << (8 * e);
+        }
+        const long long d_rowoff = (v0 + dq_b) * G.ost[1] + (w0 + dq_c) * G.ost[2];
+        auto compact_outputs = [&](int p) {
+            const int uo = p - su + 1;
+            if (dq < 0 || dIn == 0u || uo < 0 || u0 + uo >= G.on[0]) return;
+            const unsigned char *cf = cflag + ((uo + ou) % G.CF) * (TV * TW);
+            const unsigned E = reinterpret_cast<const unsigned *>(cf)[dq] & dIn;  // 0x80 per in-bounds boundary voxel
+            unsigned long long *o4 = out + (u0 + uo) * G.ost[0] + d_rowoff;
+            if (E == 0u && dIn == 0x80808080u && G.out_vec) {
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                reinterpret_cast<uint4 *>(o4)[0] = z;
+                reinterpret_cast<uint4 *>(o4)[1] = z;
+            } else {
+                const int n = __popc(E);
+                int base = n ? atomicAdd(&H.n_edge, n) : 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (E & (0x80u << (8 * e))) elist[base++] = (unsigned short)(dq * 4 + e);
+                    else if (dIn & (0x80u << (8 * e))) o4[e * G.ost[2]] = 0ull;
+                }
+            }
+        };
+
         // prologue: plane 0 -> raw
 #pragma unroll
         for (int k = 0; k < MAXQ; ++k) {
@@ -319,6 +365,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             __syncthreads();
             // B. slots are published: compact-index plane; next raw plane
             if (H.ovf) { aborted = true; break; }
+            if (tid == 0) H.n_edge = 0;  // everybody is past the previous plane's boundary-voxel loop
             const unsigned long long used = ~H.freemask & ALL_SLOTS;  // stable until phase C
             if (H.newflag && tid < KMAX && ((used >> tid) & 1ull)) {  // ranks by id (arg-max tie-break: smallest id wins)
                 const unsigned me = H.ids[tid];
@@ -346,10 +393,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 }
             }
             __syncthreads();
-            if (tid == 0) {
-                H.newflag = 0;
-                H.n_edge = 0;
-            }
+            if (tid == 0) H.newflag = 0;
             // recycle the slots of ids that left the su-plane window (after this step their sum fields are zero again)
             if (tid < KMAX && ((used >> tid) & 1ull)) {
                 const int h = H.owner[tid];
@@ -358,6 +402,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                     atomicOr(&H.freemask, 1ull << tid);
                 }
             }
+            if (early_d) compact_outputs(p);
             // C1. boundary flags of plane p-1 (needs planes p-2, p-1, p), four voxels per thread
             if (tid < NOQ && p >= 2 && p - 1 >= ou && p - 1 <= LU - 1 + ou) {
                 const int pc = p - 1;
@@ -377,7 +422,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 const unsigned char *cn = comp + (p % CR) * plane;
                 const unsigned char *co = comp + ((p + 1) % CR) * plane;  // == (p - su) % CR since CR == su + 1
                 const bool has_old = p >= su;
-#pragma unroll
+#pragma unroll 1
                 for (int k = 0; k < MAXIT; ++k) {
                     if (tid + k * NT >= NG * (TV / 8) * WP) break;
                     const int g = itg[k];
@@ -398,30 +443,14 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                     }
                 }
             }
+            if (!early_d) __syncthreads();
+            if (!early_d) compact_outputs(p);
             __syncthreads();
-            // D. outputs of plane uo = p - su + 1: zeros for non-boundary voxels, compacted list of boundary voxels
+            // D. boundary voxels of plane uo = p - su + 1: final sum along w and arg-max
             const int uo = p - su + 1;
             if (uo >= 0 && u0 + uo < G.on[0]) {
                 const unsigned char *cf = cflag + ((uo + ou) % G.CF) * (TV * TW);
                 unsigned long long *orow = out + (u0 + uo) * G.ost[0];
-                if (tid < NOQ && mIn) {
-                    const unsigned E = reinterpret_cast<const unsigned *>(cf)[tid] & mIn;  // 0x80 per in-bounds boundary voxel
-                    unsigned long long *o4 = orow + out_rowoff;
-                    if (E == 0u && mIn == 0x80808080u && G.out_vec) {
-                        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                        reinterpret_cast<uint4 *>(o4)[0] = z;
-                        reinterpret_cast<uint4 *>(o4)[1] = z;
-                    } else {
-                        const int n = __popc(E);
-                        int base = n ? atomicAdd(&H.n_edge, n) : 0;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (E & (0x80u << (8 * e))) elist[base++] = (unsigned short)(tid * 4 + e);
-                            else if (mIn & (0x80u << (8 * e))) o4[e * G.ost[2]] = 0ull;
-                        }
-                    }
-                }
-                __syncthreads();
                 const int ne = H.n_edge;
                 for (int e = tid; e < ne; e += NT) {
                     const int i = elist[e];

@@ -281,11 +281,28 @@ __host__ __device__ __forceinline__ uint32_t syk_owner_of(uint64_t id, uint32_t 
     return (uint32_t)((syk_mix64(id ^ 0x5bd1e9955bd1e995ULL) >> 20) % n_owners);
 }
 
+// Block-level staging: the number of owners is tiny (<= #GPUs), so per-row global atomics would all hit the same few
+// addresses.  Each block counts into shared memory and issues one global atomic per owner.
+constexpr int BUCKET_MAX_SMEM_OWNERS = 64;
+
 template <typename R>
 __global__ void k_bucket_count(const R *recs, uint64_t n, uint32_t n_owners, unsigned long long *counts) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    atomicAdd(&counts[syk_owner_of(owner_key(recs[i]), n_owners)], 1ull);
+    __shared__ unsigned int local[BUCKET_MAX_SMEM_OWNERS];
+    const bool use_smem = n_owners <= BUCKET_MAX_SMEM_OWNERS;
+    if (use_smem) {
+        for (unsigned i = threadIdx.x; i < n_owners; i += blockDim.x) local[i] = 0u;
+        __syncthreads();
+    }
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t o = syk_owner_of(owner_key(recs[i]), n_owners);
+        if (use_smem) atomicAdd(&local[o], 1u);
+        else atomicAdd(&counts[o], 1ull);
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < n_owners; i += blockDim.x)
+            if (local[i]) atomicAdd(&counts[i], (unsigned long long)local[i]);
+    }
 }
 // counts[0..n) -> cursors[0..n) = exclusive prefix
 __global__ void k_bucket_scan(const unsigned long long *counts, unsigned long long *cursors, uint32_t n_owners) {
@@ -297,13 +314,37 @@ __global__ void k_bucket_scan(const unsigned long long *counts, unsigned long lo
         }
     }
 }
+// every block handles one contiguous slice: count per owner in shared memory, reserve the block's ranges with one
+// global atomic per owner, then scatter (order inside a bucket is unspecified)
 template <typename R>
 __global__ void k_bucket_scatter(const R *recs, uint64_t n, uint32_t n_owners, unsigned long long *cursors, R *out) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const R r = recs[i];
-    unsigned long long pos = atomicAdd(&cursors[syk_owner_of(owner_key(r), n_owners)], 1ull);
-    out[pos] = r;
+    __shared__ unsigned int local[BUCKET_MAX_SMEM_OWNERS];
+    __shared__ unsigned long long base[BUCKET_MAX_SMEM_OWNERS];
+    const bool use_smem = n_owners <= BUCKET_MAX_SMEM_OWNERS;
+    const uint64_t per_block = (n + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = (uint64_t)blockIdx.x * per_block;
+    const uint64_t hi = lo + per_block < n ? lo + per_block : n;
+    if (!use_smem) {
+        for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const R r = recs[i];
+            out[atomicAdd(&cursors[syk_owner_of(owner_key(r), n_owners)], 1ull)] = r;
+        }
+        return;
+    }
+    for (unsigned i = threadIdx.x; i < n_owners; i += blockDim.x) local[i] = 0u;
+    __syncthreads();
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&local[syk_owner_of(owner_key(recs[i]), n_owners)], 1u);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < n_owners; i += blockDim.x) {
+        base[i] = local[i] ? atomicAdd(&cursors[i], (unsigned long long)local[i]) : 0ull;
+        local[i] = 0u;
+    }
+    __syncthreads();
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const R r = recs[i];
+        const uint32_t o = syk_owner_of(owner_key(r), n_owners);
+        out[base[o] + atomicAdd(&local[o], 1u)] = r;
+    }
 }
 
 template <typename R>
@@ -314,7 +355,8 @@ static int bucket_impl(const R *recs, uint64_t n, uint32_t n_owners, R *out, uin
     if (n == 0) return SYK_OK;
     unsigned long long *cursors = nullptr;
     SYK_CUDA(cudaMallocAsync((void **)&cursors, sizeof(unsigned long long) * n_owners, s));
-    unsigned blocks = (unsigned)((n + 255) / 256);
+    unsigned blocks = (unsigned)((n + 1023) / 1024);
+    if (blocks > 148 * 4) blocks = 148 * 4;
     k_bucket_count<R><<<blocks, 256, 0, s>>>(recs, n, n_owners, (unsigned long long *)counts_dev);
     k_bucket_scan<<<1, 32, 0, s>>>((unsigned long long *)counts_dev, cursors, n_owners);
     k_bucket_scatter<R><<<blocks, 256, 0, s>>>(recs, n, n_owners, cursors, out);
