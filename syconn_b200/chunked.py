@@ -207,20 +207,66 @@ class ExtractionPipeline:
             if n[len(self.kinds) + c] > self.pair_log_capacity:
                 raise dev._lib.SykError(dev._lib.SYK_EOVERFLOW, "pair log too small")
         owned, owned_pairs = {}, []
+        if self.world == 1:
+            for i, k in enumerate(self.kinds):
+                owned[k] = self.logs[k][:n[i]]
+            for c in range(self.n_sub):
+                owned_pairs.append(self.pair_logs[c][:n[len(self.kinds) + c]])
+            return owned, owned_pairs
+        # ---- hash-owner exchange: ONE count exchange and one all-to-all per payload width for all logs together ----
+        W, nk = self.world, len(self.kinds)
+        bucketed, cnts = [], []
         for i, k in enumerate(self.kinds):
-            recs = self.logs[k][:n[i]]
-            if self.world > 1:
-                b, counts = dev.bucket_records(recs, self.world)
-                recs = exchange_buckets(b, counts.tolist(), self.group)
-                self.launches += 3
-            owned[k] = recs
+            b, c = dev.bucket_records(self.logs[k][:n[i]], W)
+            bucketed.append(b)
+            cnts.append(c)
         for c in range(self.n_sub):
-            p = self.pair_logs[c][:n[len(self.kinds) + c]]
-            if self.world > 1:
-                b, counts = dev.bucket_pairs(p, self.world)
-                p = exchange_buckets(b, counts.tolist(), self.group)
-                self.launches += 3
-            owned_pairs.append(p)
+            b, cc = dev.bucket_pairs(self.pair_logs[c][:n[nk + c]], W)
+            bucketed.append(b)
+            cnts.append(cc)
+        self.launches += 3 * len(bucketed)
+        send_mat = torch.stack(cnts, dim=1).contiguous()            # [dest, log] rows this rank sends
+        recv_mat = torch.empty_like(send_mat)                       # [source, log] rows this rank receives
+        dist.all_to_all_single(recv_mat, send_mat, group=self.group)
+        send_h, recv_h = send_mat.tolist(), recv_mat.tolist()       # one host sync for both matrices
+
+        def exchange(log_ids):
+            """all-to-all of the given logs (same row width): send buffer ordered by destination, then by log."""
+            parts, in_split = [], []
+            offs = {j: 0 for j in log_ids}
+            for d in range(W):
+                tot = 0
+                for j in log_ids:
+                    m = send_h[d][j]
+                    if m:
+                        parts.append(bucketed[j][offs[j]:offs[j] + m])
+                    offs[j] += m
+                    tot += m
+                in_split.append(tot)
+            width = bucketed[log_ids[0]].shape[1]
+            send = torch.cat(parts) if parts else torch.empty((0, width), dtype=torch.int64, device="cuda")
+            out_split = [sum(recv_h[src][j] for j in log_ids) for src in range(W)]
+            recv = torch.empty((sum(out_split), width), dtype=torch.int64, device="cuda")
+            dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split, group=self.group)
+            # split the received rows back into logs
+            per_log = {j: [] for j in log_ids}
+            pos = 0
+            for src in range(W):
+                for j in log_ids:
+                    m = recv_h[src][j]
+                    if m:
+                        per_log[j].append(recv[pos:pos + m])
+                    pos += m
+            return {j: (torch.cat(v) if v else torch.empty((0, width), dtype=torch.int64, device="cuda"))
+                    for j, v in per_log.items()}
+
+        got = exchange(list(range(nk)))
+        for i, k in enumerate(self.kinds):
+            owned[k] = got[i]
+        if self.n_sub:
+            gotp = exchange(list(range(nk, nk + self.n_sub)))
+            owned_pairs = [gotp[nk + c] for c in range(self.n_sub)]
+        self.launches += 3
         return owned, owned_pairs
 
     def reduce_on_device(self, owned, owned_pairs, geoms_by_kind=None, capacity=None):
