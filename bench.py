@@ -357,30 +357,50 @@ def e2e_host(args, chunks):
         host.append((hc.numpy().view(np.uint64), hs.numpy().view(np.uint64), hh.numpy().view(np.uint32), ho.numpy().view(np.uint64)))
     h2d = d2h = 0
 
-    def one_pass():
+    def one_pass(fused=False):
         nonlocal h2d, d2h
         h2d = d2h = 0
         for cell, subs, halo, cbuf in host:
-            contacts = detect_cs(halo, STENCIL, out=cbuf)
-            h2d += halo.nbytes
-            d2h += contacts.nbytes
-            r = _host.find_object_properties_records(contacts)
-            h2d += contacts.nbytes
-            d2h += r.nbytes
+            if fused:  # extension: contact volume + its properties in one call (no second PCIe trip of the contacts)
+                contacts, props = detect_cs(halo, STENCIL, out=cbuf, return_props=True)
+                h2d += halo.nbytes
+                d2h += contacts.nbytes + 64 * len(props[2])
+            else:      # the reference worker's call sequence, cs_extraction_steps.py:391,439
+                contacts = detect_cs(halo, STENCIL, out=cbuf)
+                h2d += halo.nbytes
+                d2h += contacts.nbytes
+                r = _host.find_object_properties_records(contacts)
+                h2d += contacts.nbytes
+                d2h += r.nbytes
             cr, sr, pr = _host.map_subcell_records(cell, subs)
             h2d += cell.nbytes + subs.nbytes
             d2h += cr.nbytes + sum(x.nbytes for x in sr) + sum(x.nbytes for x in pr)
     one_pass()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
     reps = max(1, min(args.steps, 3))
+    ts = []
     for _ in range(reps):
+        t0 = time.perf_counter()
         one_pass()
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / reps
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    dt = float(np.median(ts))
     vox = sum(int(c[0].size) for c in host)
-    return {"value": vox / dt / 1e9, "unit": "GVoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "chunks_per_step": n, "api": "syk_detect_cs_host + syk_find_object_properties_host + "
+    h2d0, d2h0 = h2d, d2h
+    one_pass(True)
+    torch.cuda.synchronize()
+    tf = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        one_pass(True)
+        torch.cuda.synchronize()
+        tf.append(time.perf_counter() - t0)
+    dtf = float(np.median(tf))
+    fused = {"value": vox / dtf / 1e9, "unit": "GVoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+             "api": "syk_detect_cs_props_host (extension) + syk_map_subcell_extract_props_host"}
+    h2d, d2h = h2d0, d2h0
+    return {"value": vox / dt / 1e9, "fused_variant": fused, "unit": "GVoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "chunks_per_step": n, "pass_seconds": [round(t, 4) for t in ts], "api": "syk_detect_cs_host + syk_find_object_properties_host + "
                                         "syk_map_subcell_extract_props_host (pinned host buffers, one synchronous call per stage and chunk)"}
 
 

@@ -162,6 +162,10 @@ int syk_map_subcell_extract_props_host(const void *cell_host, const int64_t cell
                                        uint64_t *n_pairs_out /*[n_sub]*/);
 int syk_detect_cs_host(const void *arr_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
                        const int32_t stencil[3], uint64_t *out_host /* C-contiguous [shape-stencil+1] */);
+/* detect_cs followed by find_object_properties(contacts) -- the pair of calls of cs_extraction_steps.py:391,439 --
+ * without moving the contact volume over PCIe twice */
+int syk_detect_cs_props_host(const void *arr_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                             const int32_t stencil[3], uint64_t *out_host, syk_record_t **records_out, uint64_t *n_out);
 int syk_process_block_nonzero_host(const void *edges_host, int edge_bytes, const int64_t edge_strides[3],
                                    const void *arr_host, int elem_bytes, const int64_t arr_strides[3],
                                    const int64_t shape[3], const int32_t stencil[3], uint64_t *out_host);

@@ -28,7 +28,7 @@ EXPORTS = [
     "syk_pairs_bucket",
     "syk_find_object_properties", "syk_map_subcell_extract_props", "syk_detect_seg_boundaries",
     "syk_process_block_nonzero", "syk_detect_cs", "syk_synth_labels",
-    "syk_find_object_properties_host", "syk_map_subcell_extract_props_host", "syk_detect_cs_host",
+    "syk_find_object_properties_host", "syk_map_subcell_extract_props_host", "syk_detect_cs_host", "syk_detect_cs_props_host",
     "syk_process_block_nonzero_host", "syk_detect_seg_boundaries_host", "syk_free",
 ]
 
@@ -86,6 +86,7 @@ def load():
     L.syk_map_subcell_extract_props_host.argtypes = [vp, i64p, vp, i64p, ci, ci, i64p, ci, u64, C.POINTER(vp), u64p,
                                                      C.POINTER(vp), u64p, C.POINTER(vp), u64p]
     L.syk_detect_cs_host.argtypes = [vp, ci, i64p, i64p, i32p, vp]
+    L.syk_detect_cs_props_host.argtypes = [vp, ci, i64p, i64p, i32p, vp, C.POINTER(vp), u64p]
     L.syk_process_block_nonzero_host.argtypes = [vp, ci, i64p, vp, ci, i64p, i64p, i32p, vp]
     L.syk_detect_seg_boundaries_host.argtypes = [vp, ci, i64p, i64p, vp]
     L.syk_free.argtypes = [vp]

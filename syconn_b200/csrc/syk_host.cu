@@ -288,7 +288,8 @@ SYK_API int syk_map_subcell_extract_props_host(const void *cell_host, const int6
 }
 
 static int cs_host_impl(const void *edges_host, int edge_bytes, const int64_t *edge_strides, const void *arr_host, int elem_bytes,
-                        const int64_t shape[3], const int64_t strides[3], const int32_t stencil[3], uint64_t *out_host) {
+                        const int64_t shape[3], const int64_t strides[3], const int32_t stencil[3], uint64_t *out_host,
+                        syk_record_t **records_out = nullptr, uint64_t *n_out = nullptr) {
     int rc = syk_require_device();
     if (rc) return rc;
     SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
@@ -321,8 +322,36 @@ static int cs_host_impl(const void *edges_host, int edge_bytes, const int64_t *e
     else
         rc = syk_detect_cs(arr.p, elem_bytes, shape, strides, stencil, (uint64_t *)out.p, ost, nullptr);
     if (rc) return rc;
+    if (records_out) {  // properties of the contact volume while it is still on the device (cs_extraction_steps.py:439)
+        const int64_t origin[3] = {0, 0, 0};
+        syk_chunk_geom_t geom;
+        for (int a = 0; a < 3; ++a) {
+            geom.origin[a] = 0;
+            geom.shape[a] = oshape[a];
+        }
+        uint64_t cap = pick_capacity(0, nout);
+        for (;;) {
+            syk_table_t *t = nullptr;
+            rc = syk_table_create(&t, cap);
+            if (rc) return rc;
+            rc = syk_find_object_properties(t, out.p, 8, oshape, ost, origin, 0, nullptr);
+            if (!rc) rc = export_to_host(t, &geom, records_out, n_out);
+            syk_table_destroy(t);
+            if (rc != SYK_EOVERFLOW || cap >= nout * 2) break;
+            cap *= 4;
+        }
+        if (rc) return rc;
+    }
     SYK_CUDA(cudaMemcpy(out_host, out.p, nout * 8, cudaMemcpyDeviceToHost));
     return SYK_OK;
+}
+
+SYK_API int syk_detect_cs_props_host(const void *arr_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                                     const int32_t stencil[3], uint64_t *out_host, syk_record_t **records_out, uint64_t *n_out) {
+    SYK_CHECK_ARG(records_out && n_out, "output pointers are NULL");
+    *records_out = nullptr;
+    *n_out = 0;
+    return cs_host_impl(nullptr, 0, nullptr, arr_host, elem_bytes, shape, strides, stencil, out_host, records_out, n_out);
 }
 
 SYK_API int syk_detect_cs_host(const void *arr_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3],

@@ -193,10 +193,12 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *tm,
 }
 
 __device__ __forceinline__ void tile_setup(const ScanGeom &G, long long tile, int TU, int TV, TileCtx &T) {
-    const long long tw = tile % G.tiles[2];
-    const long long r = tile / G.tiles[2];
-    const long long tv = r % G.tiles[1];
-    const long long tu = r / G.tiles[1];
+    // ntiles < 2^31 (checked on the host): 32-bit divisions
+    const unsigned t32 = (unsigned)tile, n2 = (unsigned)G.tiles[2], n1 = (unsigned)G.tiles[1];
+    const unsigned r = t32 / n2;
+    const long long tw = t32 - r * n2;
+    const long long tu = r / n1;
+    const long long tv = r - (unsigned)tu * n1;
     T.t0[0] = tu * TU;
     T.t0[1] = tv * TV;
     T.t0[2] = tw * TW;
@@ -389,10 +391,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const T *__restrict__ cell,
     struct TileId { long long tu, tv, tw; };
     auto tile_id = [&](long long tile) {
         TileId t;
-        t.tw = tile % G.tiles[2];
-        const long long rr = tile / G.tiles[2];
-        t.tv = rr % G.tiles[1];
-        t.tu = rr / G.tiles[1];
+        const unsigned t32 = (unsigned)tile, n2 = (unsigned)G.tiles[2], n1 = (unsigned)G.tiles[1];
+        const unsigned rr = t32 / n2;
+        t.tw = t32 - rr * n2;
+        t.tu = rr / n1;
+        t.tv = rr - (unsigned)t.tu * n1;
         return t;
     };
     auto issue = [&](const TileId &t, int b, int sb) {
@@ -529,6 +532,7 @@ static int check_geom(const int64_t shape[3], const int64_t strides[3], const in
         if (origin) SYK_CHECK_ARG(origin[a] > -(1ll << 29) && origin[a] + shape[a] < (1ll << 29), "coordinates exceed 2^29");
     }
     SYK_CHECK_ARG(nvox < (double)((1ull << 40) - 2), "more than 2^40 voxels per call");
+    SYK_CHECK_ARG(nvox / 1024.0 < 2.0e9, "too many tiles per call");
     return SYK_OK;
 }
 
@@ -599,6 +603,7 @@ static int launch_scan(const void *cell, const ScanGeom &G, const TableView &cel
     bool tma = make_tmap(&tm.m[0], cell, (int)sizeof(T), G.n, G.st, R);
     for (int c = 0; c < A.n_sub && tma; ++c) tma = make_tmap(&tm.m[1 + c], A.sub[c], (int)sizeof(T), G.n, G.sst, R);
     // TMA: one buffer per warp, many resident warps hide the latency; LDGSTS fallback: double buffered
+    // (measured: one buffer + 32 resident warps/SM beats double buffering with 16-20 warps, and R=16 beats R=8)
     if (tma) return launch_cfg<T, R, TU, TV, WARPS, WS, WSS, PS, 1, true>(cell, G, cell_t, A, tm, s);
     return launch_cfg<T, R, TU, TV, WARPS, WS, WSS, PS, 2, false>(cell, G, cell_t, A, tm, s);
 }

@@ -25,11 +25,13 @@ def detect_seg_boundaries(arr):
     return out.view(np.bool_)
 
 
-def detect_cs(arr, stencil=None, out=None):
+def detect_cs(arr, stencil=None, out=None, return_props=False):
     """syconn/extraction/find_object_properties.py:458-472.  Boundary mask and partner stencil are fused in one
     kernel (``syk_detect_cs_host``); uint64 input is narrowed to uint32 exactly like the caller-side
     ``.astype(np.uint32)`` (cs_extraction_steps.py:385-387).  ``stencil`` overrides the config default; ``out`` may be a
-    preallocated C-contiguous uint64 array of the output shape (e.g. pinned memory)."""
+    preallocated C-contiguous uint64 array of the output shape (e.g. pinned memory).  ``return_props=True`` also returns
+    ``find_object_properties(contacts)`` (the next call of the reference worker, cs_extraction_steps.py:439), computed
+    while the contact volume is still on the GPU: ``(contacts, (rep_coords, bounding_box, sizes))``."""
     arr = np.asarray(arr)
     if arr.dtype not in (np.uint32, np.uint64):
         raise ValueError(f"Buffer dtype mismatch, expected 'uint32_t' but got '{arr.dtype}'")
@@ -42,8 +44,15 @@ def detect_cs(arr, stencil=None, out=None):
         out = np.empty(oshape, np.uint64)
     assert out.shape == oshape and out.dtype == np.uint64 and out.flags.c_contiguous
     if out.size == 0:
-        return out
+        return (out, ({}, {}, {})) if return_props else out
     arr = dense_view(arr)
+    if return_props:
+        import ctypes as C
+        from ._host import records_to_dicts
+        rec, n = C.c_void_p(), C.c_uint64()
+        _lib.check(_lib.load().syk_detect_cs_props_host(arr.ctypes.data, arr.itemsize, _lib.i64(arr.shape), _lib.i64(estrides(arr)),
+                                                        _lib.i32(st), out.ctypes.data, C.byref(rec), C.byref(n)))
+        return out, records_to_dicts(_lib.take_array(rec.value, n.value, _lib.RECORD_DTYPE))
     _lib.check(_lib.load().syk_detect_cs_host(arr.ctypes.data, arr.itemsize, _lib.i64(arr.shape), _lib.i64(estrides(arr)),
                                               _lib.i32(st), out.ctypes.data))
     return out

@@ -153,6 +153,15 @@ def test_detect_cs_vs_oracle_random(mods, seed, shape, st):
     assert np.array_equal(mods["fop"].detect_seg_boundaries(seg), edges.astype(bool))
 
 
+def test_detect_cs_with_props_extension(mods):
+    """detect_cs(..., return_props=True) == (detect_cs, find_object_properties(contacts)) of the reference worker."""
+    seg = mods["synth"]((60, 52, 47), pitch=(14, 12, 8), warp_amp=3, seed=11, dtype=np.uint32)
+    cs, props = mods["fop"].detect_cs(seg, (7, 7, 3), return_props=True)
+    want = mods["oracle"].detect_cs(seg, (7, 7, 3))
+    assert np.array_equal(cs, want)
+    assert_props_equal(props, mods["oracle"].find_object_properties(want), "cs props")
+
+
 def test_detect_cs_random_labels_overflow_path(mods):
     """near-random labels: > 32 distinct ids per window (block-cooperative hash fallback)."""
     rng = np.random.default_rng(7)
