@@ -12,6 +12,7 @@
 // ---- error plumbing -----------------------------------------------------------------------------------------
 void syk_set_error(const char *fmt, ...);
 int syk_require_device();
+void syk_pool_keep_warm();  // raise the release threshold of the default stream-ordered pool (once)
 
 #define SYK_CUDA(call)                                                                             \
     do {                                                                                           \

@@ -61,20 +61,8 @@ __global__ void k_synth(void *out, int elem_bytes, long long nx, long long ny, l
 
 // Device scratch of the host entry points comes from the stream-ordered pool (kept warm between calls: a call per
 // chunk must not pay cudaMalloc/cudaFree round trips for gigabyte buffers).
-static void pool_keep_warm() {
-    static bool done = false;
-    if (done) return;
-    done = true;
-    int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long thr = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-    cudaGetLastError();
-}
 static cudaError_t dev_alloc(void **p, size_t bytes) {
-    pool_keep_warm();
+    syk_pool_keep_warm();
     return cudaMallocAsync(p, bytes ? bytes : 16, (cudaStream_t)0);
 }
 struct DevBuf {

@@ -29,6 +29,21 @@ int syk_require_device() {
     return SYK_OK;
 }
 
+// Tables and host-call scratch come from the stream-ordered pool and are kept there between calls: a call per chunk
+// must not pay cudaMalloc/cudaFree round trips for buffers of hundreds of megabytes.
+void syk_pool_keep_warm() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+}
+
 SYK_API int syk_version(void) { return SYK_VERSION; }
 SYK_API const char *syk_last_error(void) { return g_err; }
 SYK_API int syk_device_count(void) {
@@ -62,7 +77,8 @@ SYK_API int syk_table_create(syk_table_t **out, uint64_t capacity) {
     if (!t) return SYK_ENOMEM;
     t->capacity = round_pow2(capacity);
     SYK_CUDA(cudaGetDevice(&t->device));
-    cudaError_t e = cudaMalloc(&t->slots, t->capacity * sizeof(SykSlot));
+    syk_pool_keep_warm();
+    cudaError_t e = cudaMallocAsync((void **)&t->slots, t->capacity * sizeof(SykSlot), (cudaStream_t)0);
     if (e != cudaSuccess) {
         syk_set_error("cudaMalloc of %llu table slots failed: %s", (unsigned long long)t->capacity, cudaGetErrorString(e));
         free(t);
@@ -70,7 +86,7 @@ SYK_API int syk_table_create(syk_table_t **out, uint64_t capacity) {
     }
     SYK_CUDA(cudaMalloc(&t->flags, 4 * sizeof(int)));
     SYK_CUDA(cudaMalloc(&t->counter, 4 * sizeof(unsigned long long)));
-    SYK_CUDA(cudaMemset(t->slots, 0, t->capacity * sizeof(SykSlot)));
+    SYK_CUDA(cudaMemsetAsync(t->slots, 0, t->capacity * sizeof(SykSlot), (cudaStream_t)0));
     SYK_CUDA(cudaMemset(t->flags, 0, 4 * sizeof(int)));
     SYK_CUDA(cudaMemset(t->counter, 0, 4 * sizeof(unsigned long long)));
     *out = t;
@@ -79,7 +95,7 @@ SYK_API int syk_table_create(syk_table_t **out, uint64_t capacity) {
 
 SYK_API int syk_table_destroy(syk_table_t *t) {
     if (!t) return SYK_OK;
-    cudaFree(t->slots);
+    cudaFreeAsync(t->slots, (cudaStream_t)0);
     cudaFree(t->flags);
     cudaFree(t->counter);
     free(t);
@@ -383,7 +399,8 @@ SYK_API int syk_pairs_create(syk_pairs_t **out, uint64_t capacity) {
     if (!t) return SYK_ENOMEM;
     t->capacity = round_pow2(capacity);
     SYK_CUDA(cudaGetDevice(&t->device));
-    cudaError_t e = cudaMalloc(&t->slots, t->capacity * sizeof(SykPairSlot));
+    syk_pool_keep_warm();
+    cudaError_t e = cudaMallocAsync((void **)&t->slots, t->capacity * sizeof(SykPairSlot), (cudaStream_t)0);
     if (e != cudaSuccess) {
         syk_set_error("cudaMalloc of %llu pair slots failed: %s", (unsigned long long)t->capacity, cudaGetErrorString(e));
         free(t);
@@ -391,14 +408,14 @@ SYK_API int syk_pairs_create(syk_pairs_t **out, uint64_t capacity) {
     }
     SYK_CUDA(cudaMalloc(&t->flags, 4 * sizeof(int)));
     SYK_CUDA(cudaMalloc(&t->counter, 4 * sizeof(unsigned long long)));
-    SYK_CUDA(cudaMemset(t->slots, 0, t->capacity * sizeof(SykPairSlot)));
+    SYK_CUDA(cudaMemsetAsync(t->slots, 0, t->capacity * sizeof(SykPairSlot), (cudaStream_t)0));
     SYK_CUDA(cudaMemset(t->flags, 0, 4 * sizeof(int)));
     *out = t;
     return SYK_OK;
 }
 SYK_API int syk_pairs_destroy(syk_pairs_t *t) {
     if (!t) return SYK_OK;
-    cudaFree(t->slots);
+    cudaFreeAsync(t->slots, (cudaStream_t)0);
     cudaFree(t->flags);
     cudaFree(t->counter);
     free(t);

@@ -1,0 +1,142 @@
+"""Full-size (BASELINE configs) checks through size-independent properties -- the oracle is far too slow at 512^3.
+Everything runs through the C ABI (device-buffer entry points) on torch tensors; torch is only the checker here."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from syconn_b200 import device
+    return device
+
+
+def _records(dev, lab, origin=(0, 0, 0), cap=1 << 19):
+    tab = dev.IdTable(cap)
+    dev.find_object_properties(tab, lab, origin=origin)
+    return dev.records_numpy(tab.export(dev.geoms([origin], [tuple(lab.shape)])))
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_props_512_cube_100k_ids(dev, order):
+    """BASELINE config 2: 512^3 uint64, ~1e5 ids."""
+    S = 512
+    lab = dev.synth_labels((S, S, S), pitch=(11, 11, 11), seed=1, order=order)
+    rec = _records(dev, lab)
+    ids, counts = torch.unique(lab, return_counts=True)
+    keep = ids != 0
+    ids, counts = ids[keep].cpu().numpy().view(np.uint64), counts[keep].cpu().numpy()
+    o = np.argsort(rec["id"])
+    assert 90_000 < len(ids) < 120_000
+    assert np.array_equal(rec["id"][o], ids)                                    # same id set, background excluded
+    assert np.array_equal(rec["count"][o].astype(np.int64), counts)             # exact voxel counts
+    assert int(rec["count"].sum()) == int((lab != 0).sum())                     # checksum of checksums
+    assert (rec["bb_min"] >= 0).all() and (rec["bb_max"] <= S).all() and (rec["bb_max"] > rec["bb_min"]).all()
+    assert ((rec["rep"] >= rec["bb_min"]) & (rec["rep"] < rec["bb_max"])).all()
+    r = torch.from_numpy(rec["rep"].astype(np.int64)).cuda()
+    at_rep = lab[r[:, 0], r[:, 1], r[:, 2]].cpu().numpy().view(np.uint64)
+    assert np.array_equal(at_rep, rec["id"])                                    # rep_coord lies inside its object
+    # rep_coord is the FIRST voxel in (x, y, z) scan order: no voxel of the id at a smaller linear index
+    lin = (r[:, 0] * S + r[:, 1]) * S + r[:, 2]
+    flat = lab.reshape(-1) if order == "C" else lab.contiguous().reshape(-1)
+    first = torch.full((int(flat.numel()),), 0, dtype=torch.bool, device="cuda")
+    # first occurrence per id via a stable unique over the flattened logical order
+    u, inv = torch.unique(flat, return_inverse=True)
+    pos = torch.full((len(u),), flat.numel(), dtype=torch.int64, device="cuda")
+    pos.scatter_reduce_(0, inv, torch.arange(flat.numel(), device="cuda"), reduce="amin")
+    want = dict(zip(u.cpu().numpy().view(np.uint64).tolist(), pos.cpu().numpy().tolist()))
+    got = dict(zip(rec["id"].tolist(), lin.cpu().numpy().tolist()))
+    assert all(got[k] == want[k] for k in got)
+    del first
+
+
+def test_chunked_equals_whole_volume(dev):
+    """sizes / bounding boxes of a 512^3 volume computed in one call == fold of its eight 256^3 chunks."""
+    from syconn_b200.chunked import ChunkPlan, reduce_records
+    S, E = 512, 256
+    lab = dev.synth_labels((S, S, S), pitch=(32, 32, 16), seed=3, order="F")
+    whole = _records(dev, lab)
+    plan = ChunkPlan((S, S, S), (E, E, E))
+    logs = []
+    for s, off in enumerate(plan.offsets):
+        sub = lab[off[0]:off[0] + E, off[1]:off[1] + E, off[2]:off[2] + E]
+        tab = dev.IdTable(1 << 16)
+        dev.find_object_properties(tab, sub, origin=off, chunk_seq=s)
+        g = dev.geoms([off] * (s + 1), [(E, E, E)] * (s + 1))
+        logs.append(dev.records_numpy(tab.export(g)))
+    red = reduce_records(np.concatenate(logs))
+    o = np.argsort(whole["id"])
+    assert np.array_equal(red["id"], whole["id"][o])
+    assert np.array_equal(red["size"], whole["count"][o].astype(np.int64))
+    assert np.array_equal(red["bounding_box"][:, 0], whole["bb_min"][o]) and np.array_equal(red["bounding_box"][:, 1], whole["bb_max"][o])
+
+
+def test_detect_cs_chunk_sized_properties(dev):
+    """BASELINE config 1/4 geometry (536x536x530 uint32 -> 524^3): structural invariants of the contact volume."""
+    st = (13, 13, 7)
+    seg = dev.synth_labels((536, 536, 530), origin=(500, -12, 1015), pitch=(32, 32, 16), seed=0, dtype=torch.int32, order="F")
+    out = dev.detect_cs(seg, st)
+    assert tuple(out.shape) == (524, 524, 524)
+    edges = dev.detect_seg_boundaries(seg)[6:-6, 6:-6, 3:-3]
+    center = seg[6:-6, 6:-6, 3:-3].to(torch.int64) & 0xFFFFFFFF
+    nz = out != 0
+    assert bool((nz <= (edges != 0)).all())                       # contacts only on boundary voxels
+    lo, hi = (out >> 32) & 0xFFFFFFFF, out & 0xFFFFFFFF
+    assert bool((lo[nz] < hi[nz]).all()) and bool((lo[nz] != 0).all())   # packed (min << 32) + max, both ids non-zero
+    assert bool(((lo == center) | (hi == center))[nz].all())      # the centre id is one of the partners
+    # a boundary voxel without contact has no foreign non-zero id in its window: check the direct 6-neighbourhood
+    nb_foreign = torch.zeros_like(nz)
+    c = seg.to(torch.int64) & 0xFFFFFFFF
+    core = c[6:-6, 6:-6, 3:-3]
+    for ax, (a, b) in enumerate(((6, 6), (6, 6), (3, 3))):
+        for d in (-1, 1):
+            sl = [slice(6, -6), slice(6, -6), slice(3, -3)]
+            sl[ax] = slice(a + d, c.shape[ax] - b + d)
+            n = c[tuple(sl)]
+            nb_foreign |= (n != 0) & (n != core) & (core != 0)
+    assert bool((nb_foreign <= nz).all())
+    # determinism / idempotence of the launch
+    assert torch.equal(out, dev.detect_cs(seg, st))
+    # generic kernel (the fallback path) gives the same volume
+    import os
+    os.environ["SYK_CS_GENERIC"] = "1"
+    try:
+        part = seg[:140, :140, :140].contiguous().permute(2, 1, 0).contiguous().permute(2, 1, 0)
+        g = dev.detect_cs(part, st)
+    finally:
+        del os.environ["SYK_CS_GENERIC"]
+    assert torch.equal(g, dev.detect_cs(part, st))
+
+
+def test_map_512_checksums(dev):
+    """BASELINE config 3 chunk (512^3, 3 organelle channels): overlap counts against torch."""
+    S = 512
+    cell = dev.synth_labels((S, S, S), pitch=(32, 32, 16), seed=0, order="F")
+    subs = torch.empty((3, S, S, S), dtype=torch.int64, device="cuda").permute(0, 3, 2, 1)
+    for c in range(3):
+        dev.synth_labels((S, S, S), pitch=(12, 12, 6), seed=0, kind=1 + c, density16=1, out=subs[c])
+    ct, sts, pts = dev.IdTable(1 << 16), [dev.IdTable(1 << 17) for _ in range(3)], [dev.PairTable(1 << 17) for _ in range(3)]
+    dev.map_subcell_extract_props(ct, sts, pts, cell, subs)
+    g = dev.geoms([(0, 0, 0)], [(S, S, S)])
+    crec = dev.records_numpy(ct.export(g))
+    assert int(crec["count"].sum()) == int((cell != 0).sum())
+    for c in range(3):
+        srec = dev.records_numpy(sts[c].export(g))
+        pairs = dev.pairs_numpy(pts[c].export())
+        assert int(srec["count"].sum()) == int((subs[c] != 0).sum())
+        assert int(pairs["count"].sum()) == int(((subs[c] != 0) & (cell != 0)).sum())   # every overlap voxel counted once
+        assert len(np.unique(np.stack([pairs["sub_id"], pairs["cell_id"]]), axis=1).T) == len(pairs)  # no duplicate pair
+        # per-organelle overlap <= organelle size
+        sz = dict(zip(srec["id"].tolist(), srec["count"].tolist()))
+        tot = {}
+        for s_, n_ in zip(pairs["sub_id"].tolist(), pairs["count"].tolist()):
+            tot[s_] = tot.get(s_, 0) + n_
+        assert all(tot[k] <= sz[k] for k in tot)
+        # spot check: the biggest pair against torch
+        j = int(np.argmax(pairs["count"]))
+        s_id, c_id = int(pairs["sub_id"][j]), int(pairs["cell_id"][j])
+        s_t = torch.tensor(np.array([s_id], np.uint64).view(np.int64), device="cuda")
+        c_t = torch.tensor(np.array([c_id], np.uint64).view(np.int64), device="cuda")
+        assert int(((subs[c] == s_t) & (cell == c_t)).sum()) == int(pairs["count"][j])

@@ -199,3 +199,38 @@ def test_device_api_and_synth_twin(mods):
     segF = dev.synth_labels((60, 50, 40), pitch=(12, 10, 6), seed=9, dtype=torch.int32, order="F")
     outF = dev.detect_cs(segF)
     assert outF.stride(0) == 1 and np.array_equal(outF.cpu().numpy().view(np.uint64), want)
+
+
+def test_randomized_sweep_vs_oracle(mods):
+    """Seeded sweep over shapes, memory layouts, dtypes, label alphabets and stencils (all three stages)."""
+    rng = np.random.default_rng(2024)
+    oracle, fop, fopc = mods["oracle"], mods["fop"], mods["fopc"]
+    perms = [(0, 1, 2), (2, 1, 0), (1, 0, 2), (0, 2, 1)]
+    for case in range(24):
+        shape = tuple(int(s) for s in rng.integers(1, 40, size=3))
+        nlab = int(rng.choice([2, 5, 40, 5000]))
+        dt = np.uint64 if case % 3 else np.uint32
+        hi = 2 ** 40 if dt == np.uint64 else 2 ** 32 - 1
+        alphabet = np.concatenate([[0], rng.integers(1, hi, size=nlab)]).astype(dt)
+        blocky = mods["synth"](shape, pitch=tuple(int(p) for p in rng.integers(2, 9, size=3)), warp_amp=int(rng.integers(0, 6)),
+                                       seed=case)
+        vol = alphabet[(blocky % np.uint64(len(alphabet))).astype(np.int64)]
+        noise = rng.random(shape) < 0.05
+        vol[noise] = alphabet[rng.integers(0, len(alphabet), size=int(noise.sum()))]
+        perm = perms[case % 4]
+        lay = np.ascontiguousarray(vol.transpose(perm)).transpose(np.argsort(perm))  # same logical array, other memory order
+        assert np.array_equal(lay, vol)
+        assert_props_equal(fop.find_object_properties(lay), oracle.find_object_properties(vol), f"case {case} props")
+        nsub = int(rng.integers(1, 4))
+        subs = np.stack([np.where(rng.random(shape) < 0.3, alphabet[rng.integers(0, len(alphabet), size=shape)], 0).astype(dt)
+                         for _ in range(nsub)])
+        g, o = fop.map_subcell_extract_props(lay, subs), oracle.map_subcell_extract_props(vol, subs)
+        assert_props_equal(g[0], o[0], f"case {case} cell")
+        for c in range(nsub):
+            assert_props_equal([g[1][k][c] for k in range(3)], [o[1][k][c] for k in range(3)], f"case {case} sub{c}")
+            assert np.array_equal(map_to_rows(g[2][c]), map_to_rows(o[2][c])), f"case {case} pairs{c}"
+        st = tuple(int(s) for s in rng.choice([1, 3, 5, 7, 9, 13], size=3))
+        if all(shape[i] >= st[i] for i in range(3)):
+            seg = lay.astype(np.uint32) if dt == np.uint32 else lay
+            want = oracle.detect_cs(np.ascontiguousarray(vol), st)
+            assert np.array_equal(fop.detect_cs(seg, st), want), f"case {case} detect_cs {st} {shape}"
