@@ -60,6 +60,14 @@ typedef struct syk_pair {
     uint64_t _pad;
 } syk_pair_t;
 
+/* One synaptic voxel of a contact site (extract_cs_syntype, block_processing_C.pyx:119-157): 32 bytes */
+typedef struct syk_synvox {
+    uint64_t id;     /* contact-site id of the voxel */
+    uint64_t lin;    /* linear index (x*Sy + y)*Sz + z inside the call's volume (scan order of the reference) */
+    uint64_t flags;  /* bit 0: asym_mask == 1, bit 1: sym_mask == 1 */
+    uint64_t _pad;
+} syk_synvox_t;
+
 /* geometry of one chunk call, needed to decode rep_key -> rep[3] */
 typedef struct syk_chunk_geom {
     int64_t origin[3];
@@ -89,7 +97,8 @@ int syk_table_export(syk_table_t *t, const syk_chunk_geom_t *geoms_host, uint32_
                      uint64_t max_records, uint64_t *n_out_host, void *stream);
 /* Asynchronous variant for chunk loops: appends the table's records to a device log at position *counter_dev
  * (a device uint64 that accumulates across calls; records beyond max_records are dropped but still counted, so
- * the host can detect a short log).  geom is the calling chunk's geometry (one entry, indexed by any chunk_seq). */
+ * the host can detect a short log; if the source table overflowed, bit 62 of the counter is set).  geom is the calling
+ * chunk's geometry (one entry, applied to every chunk_seq). */
 int syk_table_append_records(syk_table_t *t, const syk_chunk_geom_t *geom_host, syk_record_t *log_dev, uint64_t max_records,
                              uint64_t *counter_dev, void *stream);
 /* fold records into a table: count summed, bbox min/max, rep = max rep_key
@@ -143,6 +152,16 @@ int syk_process_block_nonzero(const void *edges_dev, int edge_bytes, const int64
 int syk_detect_cs(const void *arr_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
                   const int32_t stencil[3], uint64_t *out_dev, const int64_t out_strides[3], void *stream);
 
+/* extract_cs_syntype(cs_seg, syn_mask, asym_mask, sym_mask, offset) -- block_processing_C.pyx:78-158 ("next" row f1)
+ * cs_t accumulates the contact-site props; every voxel with cs != 0 and syn_mask != 0 is appended to vox_dev
+ * (order unspecified; sort by (id, lin) to obtain the reference's per-id voxel lists).  The synaptic props, the
+ * asym / sym counts and the voxel lists all follow from these tuples.  Masks are uint8 volumes of the same shape. */
+int syk_extract_cs_syntype(syk_table_t *cs_t, const void *cs_dev, int elem_bytes, const int64_t shape[3],
+                           const int64_t cs_strides[3], const uint8_t *syn_dev, const int64_t syn_strides[3],
+                           const uint8_t *asym_dev, const int64_t asym_strides[3], const uint8_t *sym_dev,
+                           const int64_t sym_strides[3], const int64_t origin[3], uint32_t chunk_seq, syk_synvox_t *vox_dev,
+                           uint64_t max_vox, uint64_t *counter_dev, void *stream);
+
 /* ---- synthetic label volumes (bench/test inputs; bit-identical to syconn_b200/synth.py) ------------------ */
 /* kind 0: cell supervoxels (ids < 2^32, ~3% background); kind 1..: organelle channel (sparse 64-bit ids) */
 int syk_synth_labels(void *out_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
@@ -169,6 +188,10 @@ int syk_detect_cs_props_host(const void *arr_host, int elem_bytes, const int64_t
 int syk_process_block_nonzero_host(const void *edges_host, int edge_bytes, const int64_t edge_strides[3],
                                    const void *arr_host, int elem_bytes, const int64_t arr_strides[3],
                                    const int64_t shape[3], const int32_t stencil[3], uint64_t *out_host);
+int syk_extract_cs_syntype_host(const void *cs_host, int elem_bytes, const int64_t shape[3], const int64_t cs_strides[3],
+                                const uint8_t *syn_host, const int64_t syn_strides[3], const uint8_t *asym_host,
+                                const int64_t asym_strides[3], const uint8_t *sym_host, const int64_t sym_strides[3],
+                                syk_record_t **cs_records_out, uint64_t *n_cs_out, syk_synvox_t **vox_out, uint64_t *n_vox_out);
 int syk_detect_seg_boundaries_host(const void *arr_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
                                    uint8_t *out_host);
 void syk_free(void *p);

@@ -61,6 +61,14 @@ def lib():
         L.orc_result_npairs.argtypes = [p, C.c_int]
         L.orc_result_npairs.restype = C.c_uint64
         L.orc_result_pairs.argtypes = [p, C.c_int, p, p, p]
+        L.orc_extract_cs_syntype.argtypes = [p, C.c_int, i64p, p, i64p, p, i64p, p, i64p, i64p]
+        L.orc_extract_cs_syntype.restype = p
+        L.orc_syntype_result.argtypes = [p]
+        L.orc_syntype_result.restype = p
+        L.orc_syntype_nvox.argtypes = [p]
+        L.orc_syntype_nvox.restype = C.c_uint64
+        L.orc_syntype_voxels.argtypes = [p, p, p, p, p]
+        L.orc_syntype_free.argtypes = [p]
         _lib = L
     return _lib
 
@@ -210,6 +218,40 @@ def detect_cs(arr, stencil=CS_FILTERSIZE):
     edges = detect_seg_boundaries(arr).astype(np.uint32, copy=False)
     arr = np.asarray(arr).astype(np.uint32, copy=False)
     return process_block_nonzero(edges, arr, stencil)
+
+
+def extract_cs_syntype(cs_seg, syn_mask, asym_mask, sym_mask, offset):
+    """syconn/extraction/block_processing_C.pyx:78-158 ("next" row f1) ->
+    ([rc, bb, size], [rc_syn, bb_syn, size_syn], cs_asym, cs_sym, voxels_syn)."""
+    cs_seg = np.asarray(cs_seg)
+    _check_label_dtype(cs_seg, "cs_seg")
+    masks = [np.asarray(m) for m in (syn_mask, asym_mask, sym_mask)]
+    for m in masks:
+        if m.dtype != np.uint8:
+            raise ValueError("Buffer dtype mismatch, expected 'uint8_t'")
+    L = lib()
+    h = L.orc_extract_cs_syntype(cs_seg.ctypes.data, cs_seg.itemsize, _i64(_estrides(cs_seg)), masks[0].ctypes.data,
+                                 _i64(_estrides(masks[0])), masks[1].ctypes.data, _i64(_estrides(masks[1])),
+                                 masks[2].ctypes.data, _i64(_estrides(masks[2])), _i64(cs_seg.shape))
+    try:
+        res = L.orc_syntype_result(h)
+        cs_p, syn_p = _objs_to_dicts(_objs(L, res, 0)), _objs_to_dicts(_objs(L, res, 1))
+        n = int(L.orc_syntype_nvox(h))
+        key, xyz = np.empty(n, np.uint64), np.empty((n, 3), np.int32)
+        asym, sym = np.empty(n, np.uint8), np.empty(n, np.uint8)
+        if n:
+            L.orc_syntype_voxels(h, key.ctypes.data, xyz.ctypes.data, asym.ctypes.data, sym.ctypes.data)
+    finally:
+        L.orc_syntype_free(h)
+    off = [int(o) for o in offset]
+    vox, cs_asym, cs_sym = {}, {}, {}
+    for k, c, a, s_ in zip(key.tolist(), xyz.tolist(), asym.tolist(), sym.tolist()):
+        vox.setdefault(k, []).append([c[0] + off[0], c[1] + off[1], c[2] + off[2]])
+        if a:
+            cs_asym[k] = cs_asym.get(k, 0) + 1
+        if s_:
+            cs_sym[k] = cs_sym.get(k, 0) + 1
+    return [cs_p[0], cs_p[1], cs_p[2]], [syn_p[0], syn_p[1], syn_p[2]], cs_asym, cs_sym, vox
 
 
 # ------------------------------------------------------------------------------------------ merges (a6)

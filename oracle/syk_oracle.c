@@ -316,3 +316,59 @@ ORC_API orc_result_t *orc_map_subcell_extract_props(const void *cell, const int6
     free(pm); free(pcap);
     return r;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * extract_cs_syntype -- syconn/extraction/block_processing_C.pyx:78-158   ("next" row f1)
+ * One scan in (x,y,z) order.  Per contact id (cs_seg != 0): props as find_object_properties (table 0).
+ * Where syn_mask != 0 additionally: props of the synaptic part (table 1), the voxel (in scan order, with
+ * `offset` added by the Python side), and counts of asym_mask == 1 / sym_mask == 1 voxels.
+ * Result handle: tabs[0] = cs props, tabs[1] = syn props; the syn voxel tuples are returned through
+ * orc_syntype_voxels (key, x, y, z, asym==1, sym==1) in scan order.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { uint64_t key; int32_t x, y, z; uint8_t asym, sym; } synvox_t;
+typedef struct { orc_result_t *res; synvox_t *vox; uint64_t nvox, cap; } orc_syntype_t;
+
+ORC_API orc_syntype_t *orc_extract_cs_syntype(const void *cs, int elem_bytes, const int64_t cst[3], const uint8_t *syn,
+                                              const int64_t sst[3], const uint8_t *asym, const int64_t ast[3],
+                                              const uint8_t *sym, const int64_t yst[3], const int64_t shape[3]) {
+    orc_syntype_t *r = (orc_syntype_t *)calloc(1, sizeof(orc_syntype_t));
+    r->res = (orc_result_t *)calloc(1, sizeof(orc_result_t));
+    r->res->nch = 2;
+    r->res->tabs = (objtab_t *)malloc(2 * sizeof(objtab_t));
+    objtab_init(&r->res->tabs[0]);
+    objtab_init(&r->res->tabs[1]);
+    r->res->pairs = (pairrec_t **)calloc(1, sizeof(pairrec_t *));
+    r->res->npairs = (uint64_t *)calloc(1, sizeof(uint64_t));
+    r->cap = 1024;
+    r->vox = (synvox_t *)malloc(r->cap * sizeof(synvox_t));
+    for (int64_t x = 0; x < shape[0]; ++x)
+        for (int64_t y = 0; y < shape[1]; ++y)
+            for (int64_t z = 0; z < shape[2]; ++z) {
+                const uint64_t key = ld_label(cs, elem_bytes, x * cst[0] + y * cst[1] + z * cst[2]);
+                if (key == 0) continue;
+                objtab_add(&r->res->tabs[0], key, (int32_t)x, (int32_t)y, (int32_t)z);
+                if (syn[x * sst[0] + y * sst[1] + z * sst[2]] == 0) continue;
+                objtab_add(&r->res->tabs[1], key, (int32_t)x, (int32_t)y, (int32_t)z);
+                if (r->nvox == r->cap) { r->cap *= 2; r->vox = (synvox_t *)realloc(r->vox, r->cap * sizeof(synvox_t)); }
+                synvox_t *v = &r->vox[r->nvox++];
+                v->key = key; v->x = (int32_t)x; v->y = (int32_t)y; v->z = (int32_t)z;
+                v->asym = asym[x * ast[0] + y * ast[1] + z * ast[2]] == 1;
+                v->sym = sym[x * yst[0] + y * yst[1] + z * yst[2]] == 1;
+            }
+    return r;
+}
+ORC_API orc_result_t *orc_syntype_result(orc_syntype_t *r) { return r->res; }
+ORC_API uint64_t orc_syntype_nvox(const orc_syntype_t *r) { return r->nvox; }
+ORC_API void orc_syntype_voxels(const orc_syntype_t *r, uint64_t *key, int32_t *xyz, uint8_t *asym, uint8_t *sym) {
+    for (uint64_t i = 0; i < r->nvox; ++i) {
+        key[i] = r->vox[i].key; xyz[3 * i] = r->vox[i].x; xyz[3 * i + 1] = r->vox[i].y; xyz[3 * i + 2] = r->vox[i].z;
+        asym[i] = r->vox[i].asym; sym[i] = r->vox[i].sym;
+    }
+}
+ORC_API void orc_syntype_free(orc_syntype_t *r) {
+    if (!r) return;
+    /* tabs[0..1] only: nch == 2 but there is a single (empty) pair slot */
+    objtab_free(&r->res->tabs[0]); objtab_free(&r->res->tabs[1]);
+    free(r->res->tabs); free(r->res->pairs); free(r->res->npairs); free(r->res);
+    free(r->vox); free(r);
+}

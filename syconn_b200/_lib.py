@@ -16,6 +16,7 @@ SYK_OK, SYK_EINVAL, SYK_ECUDA, SYK_ENODEV, SYK_EOVERFLOW, SYK_ENOMEM = 0, -1, -2
 # numpy views of the C structs (include/syk.h)
 RECORD_DTYPE = np.dtype([("id", "<u8"), ("count", "<u8"), ("rep_key", "<u8"), ("bb_min", "<i4", (3,)),
                          ("bb_max", "<i4", (3,)), ("rep", "<i4", (3,)), ("chunk_seq", "<u4")])
+SYNVOX_DTYPE = np.dtype([("id", "<u8"), ("lin", "<u8"), ("flags", "<u8"), ("_pad", "<u8")])
 PAIR_DTYPE = np.dtype([("sub_id", "<u8"), ("cell_id", "<u8"), ("count", "<u8"), ("_pad", "<u8")])
 GEOM_DTYPE = np.dtype([("origin", "<i8", (3,)), ("shape", "<i8", (3,))])
 assert RECORD_DTYPE.itemsize == 64 and PAIR_DTYPE.itemsize == 32 and GEOM_DTYPE.itemsize == 48
@@ -27,9 +28,9 @@ EXPORTS = [
     "syk_pairs_create", "syk_pairs_destroy", "syk_pairs_clear", "syk_pairs_export", "syk_pairs_append", "syk_pairs_merge",
     "syk_pairs_bucket",
     "syk_find_object_properties", "syk_map_subcell_extract_props", "syk_detect_seg_boundaries",
-    "syk_process_block_nonzero", "syk_detect_cs", "syk_synth_labels",
+    "syk_process_block_nonzero", "syk_detect_cs", "syk_extract_cs_syntype", "syk_synth_labels",
     "syk_find_object_properties_host", "syk_map_subcell_extract_props_host", "syk_detect_cs_host", "syk_detect_cs_props_host",
-    "syk_process_block_nonzero_host", "syk_detect_seg_boundaries_host", "syk_free",
+    "syk_process_block_nonzero_host", "syk_extract_cs_syntype_host", "syk_detect_seg_boundaries_host", "syk_free",
 ]
 
 
@@ -81,6 +82,9 @@ def load():
     L.syk_detect_seg_boundaries.argtypes = [vp, ci, i64p, i64p, vp, vp]
     L.syk_process_block_nonzero.argtypes = [vp, ci, i64p, vp, ci, i64p, i64p, i32p, vp, i64p, vp]
     L.syk_detect_cs.argtypes = [vp, ci, i64p, i64p, i32p, vp, i64p, vp]
+    L.syk_extract_cs_syntype.argtypes = [vp, vp, ci, i64p, i64p, vp, i64p, vp, i64p, vp, i64p, i64p, u32, vp, u64, vp, vp]
+    L.syk_extract_cs_syntype_host.argtypes = [vp, ci, i64p, i64p, vp, i64p, vp, i64p, vp, i64p, C.POINTER(vp), u64p,
+                                              C.POINTER(vp), u64p]
     L.syk_synth_labels.argtypes = [vp, ci, i64p, i64p, i64p, i32p, C.c_int32, u64, ci, ci, vp]
     L.syk_find_object_properties_host.argtypes = [vp, ci, i64p, i64p, u64, C.POINTER(vp), u64p]
     L.syk_map_subcell_extract_props_host.argtypes = [vp, i64p, vp, i64p, ci, ci, i64p, ci, u64, C.POINTER(vp), u64p,

@@ -200,6 +200,8 @@ class ExtractionPipeline:
         Returns {kind: int64 tensor [n, 8]} of this rank's owned per-(id, chunk) records and the owned pair logs."""
         dev = self.dev
         n = self.counters.tolist()  # the only host sync of the step
+        if any(v >> 62 for v in n):
+            raise dev._lib.SykError(dev._lib.SYK_EOVERFLOW, "a per-chunk table overflowed: raise chunk_table_capacity")
         for i, k in enumerate(self.kinds):
             if n[i] > self.log_capacity:
                 raise dev._lib.SykError(dev._lib.SYK_EOVERFLOW, f"record log '{k}' too small ({n[i]} > {self.log_capacity})")

@@ -478,6 +478,87 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
 
 }  // namespace
 
+// extract_cs_syntype: stream compaction of the synaptic voxels (cs != 0 && syn != 0); lanes along the fastest cs axis
+__global__ void k_syn_voxels(const void *__restrict__ cs, int elem_bytes, long long n0, long long n1, long long n2,  // internal u,v,w
+                             long long c0, long long c1, long long c2, const unsigned char *__restrict__ syn, long long s0,
+                             long long s1, long long s2, const unsigned char *__restrict__ asym, long long a0, long long a1,
+                             long long a2, const unsigned char *__restrict__ sym, long long y0, long long y1, long long y2,
+                             long long l0, long long l1, long long l2,  // linear-index coefficients of the internal axes
+                             syk_synvox_t *__restrict__ out, unsigned long long max_out, unsigned long long *counter) {
+    const long long total = n0 * n1 * n2;
+    const unsigned lane = threadIdx.x & 31;
+    const long long start = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane;
+    for (long long base = start; base < total; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + lane;
+        unsigned long long key = 0ull;
+        long long u = 0, v = 0, w = 0;
+        if (i < total) {
+            w = i % n2;
+            const long long r = i / n2;
+            v = r % n1;
+            u = r / n1;
+            const long long ci = u * c0 + v * c1 + w * c2;
+            key = elem_bytes == 8 ? __ldg((const unsigned long long *)cs + ci) : (unsigned long long)__ldg((const unsigned *)cs + ci);
+        }
+        bool hit = false;
+        if (key != 0ull) hit = __ldg(syn + u * s0 + v * s1 + w * s2) != 0;
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (!m) continue;
+        unsigned long long pos0 = 0;
+        if (lane == 0) pos0 = atomicAdd(counter, (unsigned long long)__popc(m));
+        pos0 = __shfl_sync(FULL, pos0, 0);
+        if (hit) {
+            const unsigned long long pos = pos0 + __popc(m & ((1u << lane) - 1u));
+            if (pos < max_out) {
+                syk_synvox_t t;
+                t.id = key;
+                t.lin = (unsigned long long)(u * l0 + v * l1 + w * l2);
+                t.flags = (__ldg(asym + u * a0 + v * a1 + w * a2) == 1 ? 1ull : 0ull) | (__ldg(sym + u * y0 + v * y1 + w * y2) == 1 ? 2ull : 0ull);
+                t._pad = 0;
+                out[pos] = t;
+            }
+        }
+    }
+}
+
+SYK_API int syk_extract_cs_syntype(syk_table_t *cs_t, const void *cs_dev, int elem_bytes, const int64_t shape[3],
+                                   const int64_t cs_strides[3], const uint8_t *syn_dev, const int64_t syn_strides[3],
+                                   const uint8_t *asym_dev, const int64_t asym_strides[3], const uint8_t *sym_dev,
+                                   const int64_t sym_strides[3], const int64_t origin[3], uint32_t chunk_seq, syk_synvox_t *vox_dev,
+                                   uint64_t max_vox, uint64_t *counter_dev, void *stream) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    SYK_CHECK_ARG(shape && cs_strides && syn_strides && asym_strides && sym_strides, "NULL geometry argument");
+    SYK_CHECK_ARG(counter_dev != nullptr && (vox_dev != nullptr || max_vox == 0), "NULL output");
+    if (cs_t) {
+        rc = syk_find_object_properties(cs_t, cs_dev, elem_bytes, shape, cs_strides, origin, chunk_seq, stream);
+        if (rc) return rc;
+    }
+    const long long total = shape[0] * shape[1] * shape[2];
+    if (total == 0) return SYK_OK;
+    SYK_CHECK_ARG(cs_dev && syn_dev && asym_dev && sym_dev, "NULL buffer");
+    int ax[3] = {0, 1, 2};  // internal order: largest |cs stride| first, lanes along the smallest
+    auto key = [&](int a) { return cs_strides[a] < 0 ? -cs_strides[a] : cs_strides[a]; };
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j)
+            if (key(ax[j]) > key(ax[i])) {
+                int t = ax[i];
+                ax[i] = ax[j];
+                ax[j] = t;
+            }
+    const long long lin[3] = {shape[1] * shape[2], shape[2], 1};
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_syn_voxels<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        cs_dev, elem_bytes, shape[ax[0]], shape[ax[1]], shape[ax[2]], cs_strides[ax[0]], cs_strides[ax[1]], cs_strides[ax[2]], syn_dev,
+        syn_strides[ax[0]], syn_strides[ax[1]], syn_strides[ax[2]], asym_dev, asym_strides[ax[0]], asym_strides[ax[1]],
+        asym_strides[ax[2]], sym_dev, sym_strides[ax[0]], sym_strides[ax[1]], sym_strides[ax[2]], lin[ax[0]], lin[ax[1]], lin[ax[2]],
+        vox_dev, max_vox, (unsigned long long *)counter_dev);
+    SYK_CUDA(cudaGetLastError());
+    return SYK_OK;
+}
+
 SYK_API int syk_detect_seg_boundaries(const void *arr_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
                                       uint8_t *out_dev, void *stream) {
     int rc = syk_require_device();

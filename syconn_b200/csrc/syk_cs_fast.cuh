@@ -33,7 +33,7 @@ constexpr int MAX_NQUAD = 320;    // host guarantees VP*WP/4 <= MAX_NQUAD
 constexpr int MAX_WP = 48;        // host guarantees WP <= MAX_WP
 // Two tiers of the same kernel: tier 1 keeps at most 24 ids near the marching plane (small shared-memory footprint,
 // many CTAs per SM); the few segments that need more are redone by tier 2 (64 ids), then by the generic kernel.
-constexpr int GMAX_T1 = 3, NT_T1 = 160;
+constexpr int GMAX_T1 = 3, NT_T1 = 192;
 constexpr int GMAX_T2 = 8, NT_T2 = 320;
 
 struct FastGeom {

@@ -355,6 +355,77 @@ SYK_API int syk_process_block_nonzero_host(const void *edges_host, int edge_byte
     return cs_host_impl(edges_host, edge_bytes, edge_strides, arr_host, elem_bytes, shape, arr_strides, stencil, out_host);
 }
 
+SYK_API int syk_extract_cs_syntype_host(const void *cs_host, int elem_bytes, const int64_t shape[3], const int64_t cs_strides[3],
+                                        const uint8_t *syn_host, const int64_t syn_strides[3], const uint8_t *asym_host,
+                                        const int64_t asym_strides[3], const uint8_t *sym_host, const int64_t sym_strides[3],
+                                        syk_record_t **cs_records_out, uint64_t *n_cs_out, syk_synvox_t **vox_out, uint64_t *n_vox_out) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    SYK_CHECK_ARG(cs_records_out && n_cs_out && vox_out && n_vox_out, "output pointers are NULL");
+    *cs_records_out = nullptr;
+    *vox_out = nullptr;
+    *n_cs_out = *n_vox_out = 0;
+    const uint64_t nvox = (uint64_t)shape[0] * shape[1] * shape[2];
+    if (nvox == 0) return SYK_OK;
+    if ((rc = check_dense(shape, cs_strides, 3)) || (rc = check_dense(shape, syn_strides, 3)) ||
+        (rc = check_dense(shape, asym_strides, 3)) || (rc = check_dense(shape, sym_strides, 3)))
+        return rc;
+    DevBuf cs, syn, asym, sym, vox, cnt;
+    SYK_CUDA(dev_alloc(&cs.p, nvox * elem_bytes));
+    SYK_CUDA(dev_alloc(&syn.p, nvox));
+    SYK_CUDA(dev_alloc(&asym.p, nvox));
+    SYK_CUDA(dev_alloc(&sym.p, nvox));
+    SYK_CUDA(dev_alloc(&cnt.p, 16));
+    SYK_CUDA(cudaMemcpy(cs.p, cs_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
+    SYK_CUDA(cudaMemcpy(syn.p, syn_host, nvox, cudaMemcpyHostToDevice));
+    SYK_CUDA(cudaMemcpy(asym.p, asym_host, nvox, cudaMemcpyHostToDevice));
+    SYK_CUDA(cudaMemcpy(sym.p, sym_host, nvox, cudaMemcpyHostToDevice));
+    const int64_t origin[3] = {0, 0, 0};
+    syk_chunk_geom_t geom;
+    for (int a = 0; a < 3; ++a) {
+        geom.origin[a] = 0;
+        geom.shape[a] = shape[a];
+    }
+    uint64_t cap = pick_capacity(0, nvox);
+    uint64_t max_vox = nvox / 16 + 4096;
+    for (;;) {
+        syk_table_t *t = nullptr;
+        rc = syk_table_create(&t, cap);
+        if (rc) return rc;
+        if (vox.p) {
+            cudaFreeAsync(vox.p, (cudaStream_t)0);
+            vox.p = nullptr;
+        }
+        SYK_CUDA(dev_alloc(&vox.p, max_vox * sizeof(syk_synvox_t)));
+        SYK_CUDA(cudaMemsetAsync(cnt.p, 0, 16, (cudaStream_t)0));
+        rc = syk_extract_cs_syntype(t, cs.p, elem_bytes, shape, cs_strides, (const uint8_t *)syn.p, syn_strides, (const uint8_t *)asym.p,
+                                    asym_strides, (const uint8_t *)sym.p, sym_strides, origin, 0, (syk_synvox_t *)vox.p, max_vox,
+                                    (uint64_t *)cnt.p, nullptr);
+        unsigned long long nv = 0;
+        if (!rc) SYK_CUDA(cudaMemcpy(&nv, cnt.p, sizeof(nv), cudaMemcpyDeviceToHost));
+        if (!rc && nv > max_vox) {  // voxel buffer too small: retry with the exact size
+            syk_table_destroy(t);
+            max_vox = nv;
+            continue;
+        }
+        if (!rc) rc = export_to_host(t, &geom, cs_records_out, n_cs_out);
+        syk_table_destroy(t);
+        if (rc == SYK_EOVERFLOW && cap < nvox * 2) {
+            cap *= 4;
+            continue;
+        }
+        if (rc) return rc;
+        *n_vox_out = nv;
+        if (nv) {
+            *vox_out = (syk_synvox_t *)malloc(nv * sizeof(syk_synvox_t));
+            if (!*vox_out) return SYK_ENOMEM;
+            SYK_CUDA(cudaMemcpy(*vox_out, vox.p, nv * sizeof(syk_synvox_t), cudaMemcpyDeviceToHost));
+        }
+        return SYK_OK;
+    }
+}
+
 SYK_API int syk_detect_seg_boundaries_host(const void *arr_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
                                            uint8_t *out_host) {
     int rc = syk_require_device();

@@ -231,6 +231,12 @@ SYK_API int syk_table_export(syk_table_t *t, const syk_chunk_geom_t *geoms_host,
     return SYK_OK;
 }
 
+// append mode has no host round trip: a table that overflowed poisons the log counter (bit 62) so that the host
+// sees an impossible record count when it finally reads it
+__global__ void k_poison_on_overflow(const int *flags, unsigned long long *counter) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && flags[0]) atomicOr(counter, 1ull << 62);
+}
+
 SYK_API int syk_table_append_records(syk_table_t *t, const syk_chunk_geom_t *geom_host, syk_record_t *log_dev,
                                      uint64_t max_records, uint64_t *counter_dev, void *stream) {
     SYK_CHECK_ARG(t != nullptr && log_dev != nullptr && counter_dev != nullptr, "NULL argument");
@@ -242,6 +248,7 @@ SYK_API int syk_table_append_records(syk_table_t *t, const syk_chunk_geom_t *geo
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_table_export<<<blocks, 256, 0, s>>>(t->slots, t->capacity, log_dev, max_records, (unsigned long long *)counter_dev, gd,
                                           gd ? 0xFFFFFFFFu : 0u);
+    k_poison_on_overflow<<<1, 32, 0, s>>>(t->flags, (unsigned long long *)counter_dev);
     SYK_CUDA(cudaGetLastError());
     if (gd) SYK_CUDA(cudaFreeAsync(gd, s));
     return SYK_OK;
@@ -491,6 +498,7 @@ SYK_API int syk_pairs_append(syk_pairs_t *t, syk_pair_t *log_dev, uint64_t max_p
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_pairs_export<<<blocks, 256, 0, (cudaStream_t)stream>>>(t->slots, t->capacity, log_dev, max_pairs,
                                                              (unsigned long long *)counter_dev);
+    k_poison_on_overflow<<<1, 32, 0, (cudaStream_t)stream>>>(t->flags, (unsigned long long *)counter_dev);
     SYK_CUDA(cudaGetLastError());
     return SYK_OK;
 }

@@ -35,6 +35,57 @@ def process_block_nonzero(edges, arr, stencil1=(7, 7, 3)):
     return out
 
 
+def extract_cs_syntype(cs_seg, syn_mask, asym_mask, sym_mask, offset):
+    """syconn/extraction/block_processing_C.pyx:78-158: per contact-site id the cs props, the props of its synaptic part
+    (``syn_mask != 0``), the number of ``asym_mask == 1`` / ``sym_mask == 1`` synaptic voxels and the synaptic voxel
+    list (scan order, ``offset`` added).  Returns
+    ``[rc, bb, size], [rc_syn, bb_syn, size_syn], cs_asym, cs_sym, voxels_syn`` like the reference."""
+    import ctypes as C
+    from ._host import check_label_array, records_to_dicts
+    cs_seg = check_label_array(cs_seg, "cs_seg", 3)
+    masks = []
+    for name, m in (("syn_mask", syn_mask), ("asym_mask", asym_mask), ("sym_mask", sym_mask)):
+        m = np.asarray(m)
+        if m.dtype != np.uint8:
+            raise ValueError(f"Buffer dtype mismatch, expected 'uint8_t' but got '{m.dtype}' ({name})")
+        assert m.shape == cs_seg.shape, "cs_seg, syn_mask, sym_mask and asym_mask must all have the same shape"
+        masks.append(dense_view(m))
+    cs_seg = dense_view(cs_seg)
+    L = _lib.load()
+    rec, n_rec, vox, n_vox = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+    _lib.check(L.syk_extract_cs_syntype_host(
+        cs_seg.ctypes.data, cs_seg.itemsize, _lib.i64(cs_seg.shape), _lib.i64(estrides(cs_seg)),
+        masks[0].ctypes.data, _lib.i64(estrides(masks[0])), masks[1].ctypes.data, _lib.i64(estrides(masks[1])),
+        masks[2].ctypes.data, _lib.i64(estrides(masks[2])), C.byref(rec), C.byref(n_rec), C.byref(vox), C.byref(n_vox)))
+    cs_props = records_to_dicts(_lib.take_array(rec.value, n_rec.value, _lib.RECORD_DTYPE))
+    v = _lib.take_array(vox.value, n_vox.value, _lib.SYNVOX_DTYPE)
+    rc_syn, bb_syn, size_syn, cs_asym, cs_sym, voxels = {}, {}, {}, {}, {}, {}
+    if len(v):
+        v = v[np.lexsort((v["lin"], v["id"]))]                   # per id, reference scan order
+        sy, sz = cs_seg.shape[1], cs_seg.shape[2]
+        lin = v["lin"].astype(np.int64)
+        xyz = np.stack([lin // (sy * sz), (lin // sz) % sy, lin % sz], axis=1)
+        ids, start = np.unique(v["id"], return_index=True)
+        end = np.append(start[1:], len(v))
+        mn = np.minimum.reduceat(xyz, start, axis=0)
+        mx = np.maximum.reduceat(xyz, start, axis=0) + 1
+        n_asym = np.add.reduceat((v["flags"] & 1).astype(np.int64), start)
+        n_sym = np.add.reduceat(((v["flags"] >> 1) & 1).astype(np.int64), start)
+        off = np.array([int(offset[0]), int(offset[1]), int(offset[2])], np.int64)
+        shifted = (xyz + off).tolist()
+        for i, k in enumerate(ids.tolist()):
+            s, e = int(start[i]), int(end[i])
+            rc_syn[k] = xyz[s].tolist()
+            bb_syn[k] = [mn[i].tolist(), mx[i].tolist()]
+            size_syn[k] = e - s
+            voxels[k] = shifted[s:e]
+            if n_asym[i]:
+                cs_asym[k] = int(n_asym[i])
+            if n_sym[i]:
+                cs_sym[k] = int(n_sym[i])
+    return [cs_props[0], cs_props[1], cs_props[2]], [rc_syn, bb_syn, size_syn], cs_asym, cs_sym, voxels
+
+
 def kernel(chunk, center_id):
     """syconn/extraction/block_processing_C.pyx:21-49: one window -> packed partner id (Python int)."""
     chunk = _u32_3d(chunk, "chunk")

@@ -125,6 +125,25 @@ def main():
     segF = np.ascontiguousarray(seg.transpose(2, 1, 0)).transpose(2, 1, 0)
     assert np.array_equal(np.asarray(fop.detect_cs(segF)), out["cs_out_13_13_7"])
 
+    # ---- extract_cs_syntype ("next" row f1) ----------------------------------------------------------------------
+    cs = out["cs_out_7_7_3"].copy()                               # a real contact volume (uint64 packed ids)
+    syn = ((rng.random(cs.shape) < 0.35) * rng.integers(1, 3, size=cs.shape)).astype(np.uint8)
+    asym = rng.integers(0, 3, size=cs.shape).astype(np.uint8)
+    sym = rng.integers(0, 3, size=cs.shape).astype(np.uint8)
+    off = np.array([7, -4, 120])
+    r = ref.extract_cs_syntype(cs, syn, asym, sym, off)
+    out["syn_cs"], out["syn_mask"], out["syn_asym"], out["syn_sym"], out["syn_off"] = cs, syn, asym, sym, off
+    for k, a in zip(("ids", "sizes", "bbox", "rep"), props_arrays(r[0])):
+        out["syn_csprops_" + k] = a
+    for k, a in zip(("ids", "sizes", "bbox", "rep"), props_arrays(r[1])):
+        out["syn_synprops_" + k] = a
+    out["syn_asymcnt"] = np.array(sorted(dict(r[2]).items()), np.uint64).reshape(-1, 2)
+    out["syn_symcnt"] = np.array(sorted(dict(r[3]).items()), np.uint64).reshape(-1, 2)
+    vox = dict(r[4])
+    out["syn_vox_ids"] = np.array(sorted(vox), np.uint64)
+    out["syn_vox_len"] = np.array([len(vox[int(k)]) for k in out["syn_vox_ids"]], np.int64)
+    out["syn_vox_xyz"] = np.array([c for k in out["syn_vox_ids"] for c in vox[int(k)]], np.int64).reshape(-1, 3)
+
     np.savez_compressed(os.path.join(OUT, "hotpath_golden.npz"), **out)
     print("wrote", len(out), "arrays,", os.path.getsize(os.path.join(OUT, "hotpath_golden.npz")), "bytes")
 

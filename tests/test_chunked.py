@@ -195,3 +195,17 @@ def test_pipeline_small_volume_vs_oracle():
             assert owner_of.setdefault(i, o) == o
         pos += n
     assert sorted(bn["id"].tolist()) == sorted(dev.records_numpy(owned["cell"])["id"].tolist())
+
+
+@pytest.mark.gpu
+def test_pipeline_reports_table_overflow():
+    """A chunk with more ids than the per-chunk table holds must fail loudly, never drop records silently."""
+    from syconn_b200 import _lib, device as dev
+    from syconn_b200.chunked import ExtractionPipeline
+    pipe = ExtractionPipeline(0, (3, 3, 3), chunk_table_capacity=1024, log_capacity=1 << 14, pair_log_capacity=16)
+    cell = (torch.arange(24 * 24 * 24, dtype=torch.int64, device="cuda") + 1).reshape(24, 24, 24)   # 13824 ids
+    subs = torch.empty((0, 24, 24, 24), dtype=torch.int64, device="cuda")
+    pipe.reset()
+    pipe.process_chunk(0, (0, 0, 0), cell, subs, None)
+    with pytest.raises(_lib.SykError):
+        pipe.finish()

@@ -234,3 +234,24 @@ def test_randomized_sweep_vs_oracle(mods):
             seg = lay.astype(np.uint32) if dt == np.uint32 else lay
             want = oracle.detect_cs(np.ascontiguousarray(vol), st)
             assert np.array_equal(fop.detect_cs(seg, st), want), f"case {case} detect_cs {st} {shape}"
+
+
+def test_extract_cs_syntype(mods, golden):
+    """"next" row f1: block_processing_C.extract_cs_syntype against the reference's golden vector and the oracle."""
+    from helpers import check_syntype_against_golden
+    g, bpc, oracle = golden, mods["bpc"], mods["oracle"]
+    check_syntype_against_golden(bpc.extract_cs_syntype(g["syn_cs"], g["syn_mask"], g["syn_asym"], g["syn_sym"], g["syn_off"]), g)
+    rng = np.random.default_rng(5)
+    for shape, dt in (((33, 40, 29), np.uint64), ((20, 64, 17), np.uint32), ((5, 5, 5), np.uint64)):
+        cs = (mods["synth"](shape, pitch=(6, 5, 4), seed=3) % np.uint64(7)).astype(dt) * dt(3)
+        syn = ((rng.random(shape) < 0.3) * rng.integers(1, 4, size=shape)).astype(np.uint8)
+        asym, sym = rng.integers(0, 3, size=shape).astype(np.uint8), rng.integers(0, 3, size=shape).astype(np.uint8)
+        for lay in (lambda a: a, np.asfortranarray):
+            got = bpc.extract_cs_syntype(lay(cs), lay(syn), asym, lay(sym), [1, 2, 3])
+            want = oracle.extract_cs_syntype(cs, syn, asym, sym, [1, 2, 3])
+            assert_props_equal(tuple(got[0]), tuple(want[0]), "cs")
+            assert_props_equal(tuple(got[1]), tuple(want[1]), "syn")
+            assert got[2] == want[2] and got[3] == want[3] and got[4] == want[4]
+    empty = bpc.extract_cs_syntype(np.zeros((4, 4, 4), np.uint64), np.ones((4, 4, 4), np.uint8), np.ones((4, 4, 4), np.uint8),
+                                   np.ones((4, 4, 4), np.uint8), [0, 0, 0])
+    assert empty == ([{}, {}, {}], [{}, {}, {}], {}, {}, {})

@@ -156,3 +156,9 @@ def test_oracle_vs_reference_live(seed):
         if all(shape[i] >= st[i] for i in range(3)):
             assert np.array_equal(oracle.process_block_nonzero(edges, seg, st),
                                   np.asarray(ref.process_block_nonzero(edges, seg, st)))
+
+
+def test_oracle_vs_golden_syntype(golden):
+    from helpers import check_syntype_against_golden
+    g = golden
+    check_syntype_against_golden(oracle.extract_cs_syntype(g["syn_cs"], g["syn_mask"], g["syn_asym"], g["syn_sym"], g["syn_off"]), g)
