@@ -402,7 +402,6 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                     atomicOr(&H.freemask, 1ull << tid);
                 }
             }
-            if (early_d) compact_outputs(p);
             // C1. boundary flags of plane p-1 (needs planes p-2, p-1, p), four voxels per thread
             if (tid < NOQ && p >= 2 && p - 1 >= ou && p - 1 <= LU - 1 + ou) {
                 const int pc = p - 1;
@@ -443,8 +442,8 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                     }
                 }
             }
-            if (!early_d) __syncthreads();
-            if (!early_d) compact_outputs(p);
+            if (!early_d) __syncthreads();  // the flags of plane p - ou were written in this very phase
+            compact_outputs(p);
             __syncthreads();
             // D. boundary voxels of plane uo = p - su + 1: final sum along w and arg-max
             const int uo = p - su + 1;

@@ -217,39 +217,39 @@ __device__ __forceinline__ void tile_setup(const ScanGeom &G, long long tile, in
     T.cw = c[2];
 }
 
-// Run-length compress the lane's column buf[0..R)[lane] -> bit j of the result is set when a run starts at row j.
+// Run-length compress the lane's column buf[0..R)[lane]: bit j of the result (`bnd`) is set when a run starts at row j,
+// bit j of `nzs` when that run is foreground (label != 0).  Background runs never cost a pass.
 template <typename T, int R>
-__device__ __forceinline__ unsigned run_starts(const T *buf, int lane, bool &any_nz) {
+__device__ __forceinline__ unsigned run_starts(const T *buf, int lane, unsigned &nzs) {
     unsigned bnd = 1u;
     T prev = buf[lane];
-    T orv = prev;
+    nzs = prev != 0 ? 1u : 0u;
 #pragma unroll
     for (int j = 1; j < R; ++j) {
         const T v = buf[j * 32 + lane];
-        bnd |= (v != prev) ? (1u << j) : 0u;
-        orv |= v;
+        const unsigned ch = (v != prev) ? (1u << j) : 0u;
+        bnd |= ch;
+        nzs |= (v != 0) ? ch : 0u;
         prev = v;
     }
-    any_nz = orv != 0;
     return bnd;
 }
 
 // Accumulate one staged batch (R rows starting at tile-local row lv0, tile-local u = lu) of one label channel.
 template <typename T, int R, int WS>
-__device__ __forceinline__ void acc_batch(const T *buf, unsigned bnd, WarpTab<WS> &tab, const TableView &g, const ScanGeom &G,
-                                          const TileCtx &Tc, unsigned lu, unsigned lv0, int lane) {
+__device__ __forceinline__ void acc_batch(const T *buf, unsigned bnd, unsigned nzs, WarpTab<WS> &tab, const TableView &g,
+                                          const ScanGeom &G, const TileCtx &Tc, unsigned lu, unsigned lv0, int lane) {
     const unsigned rowrep = lu * Tc.cu + lv0 * Tc.cv + (unsigned)lane * Tc.cw;
-    while (__any_sync(FULL, bnd != 0u)) {
+    while (__any_sync(FULL, nzs != 0u)) {  // pass k: the k-th FOREGROUND run of every lane
         int s = R, e = R;
         unsigned long long key = 0ull;
-        if (bnd) {
-            s = __ffs(bnd) - 1;
-            const unsigned rest = bnd & (bnd - 1u);
-            e = rest ? (__ffs(rest) - 1) : R;
+        if (nzs) {
+            s = __ffs(nzs) - 1;
+            const unsigned above = bnd & (0xFFFFFFFEu << s);  // run boundaries after row s
+            e = above ? (__ffs(above) - 1) : R;
             key = (unsigned long long)buf[s * 32 + lane];
-            bnd = rest;
+            nzs &= nzs - 1u;
         }
-        if (!__any_sync(FULL, key != 0ull)) continue;
         const unsigned peers = __match_any_sync(FULL, key);
         const bool partial = (key != 0ull) && !(s == 0 && e == R);
         const unsigned partial_mask = __ballot_sync(FULL, partial);
@@ -280,31 +280,32 @@ __device__ __forceinline__ void acc_batch(const T *buf, unsigned bnd, WarpTab<WS
 // Overlap pairs of one organelle channel (sbuf) against the cell channel (cbuf) for one staged batch.
 template <typename T, int R, int PS>
 __device__ __forceinline__ void acc_pairs(const T *sbuf, const T *cbuf, WarpPairTab<PS> &tab, const PairView &g, int lane) {
-    unsigned bnd = 1u;
+    unsigned bnd = 1u, act;  // run starts of the (organelle, cell) pair column / those with both ids non-zero
     {
         T ps = sbuf[lane], pc = cbuf[lane];
+        act = (ps != 0 && pc != 0) ? 1u : 0u;
 #pragma unroll
         for (int j = 1; j < R; ++j) {
             const T s = sbuf[j * 32 + lane], c = cbuf[j * 32 + lane];
-            bnd |= (s != ps || c != pc) ? (1u << j) : 0u;
+            const unsigned ch = (s != ps || c != pc) ? (1u << j) : 0u;
+            bnd |= ch;
+            act |= (s != 0 && c != 0) ? ch : 0u;
             ps = s;
             pc = c;
         }
     }
-    while (__any_sync(FULL, bnd != 0u)) {
+    while (__any_sync(FULL, act != 0u)) {
         int s = R, e = R;
         unsigned long long ks = 0ull, kc = 0ull;
-        if (bnd) {
-            s = __ffs(bnd) - 1;
-            const unsigned rest = bnd & (bnd - 1u);
-            e = rest ? (__ffs(rest) - 1) : R;
+        if (act) {
+            s = __ffs(act) - 1;
+            const unsigned above = bnd & (0xFFFFFFFEu << s);
+            e = above ? (__ffs(above) - 1) : R;
             ks = (unsigned long long)sbuf[s * 32 + lane];
             kc = (unsigned long long)cbuf[s * 32 + lane];
-            bnd = rest;
+            act &= act - 1u;
         }
-        const bool active = (ks != 0ull) && (kc != 0ull);
-        if (!active) ks = kc = 0ull;
-        if (!__any_sync(FULL, active)) continue;
+        const bool active = ks != 0ull;
         const unsigned peers = __match_any_sync(FULL, ks) & __match_any_sync(FULL, kc);
         const bool partial = active && !(s == 0 && e == R);
         const unsigned partial_mask = __ballot_sync(FULL, partial);
@@ -344,18 +345,21 @@ struct MapArgs {
     int n_sub;
     int do_cell_props;
     int do_sub_props;
+    int org_mode;  // organelle-first scan: the staged channel is ONE organelle volume (its props go to cell_t), sub[0] is the
+                   // cell volume, read on demand only where the organelle is non-zero (organelles are sparse)
 };
 
 // One kernel for both entry points: NCH = 1 + n_sub staged channels (n_sub == 0 => find_object_properties).
 //   R   rows per batch;  TU x TV rows per tile (TV multiple of R)
 template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS, int NBUF, bool TMA>
-__global__ void __launch_bounds__(WARPS * 32) k_scan(const T *__restrict__ cell, ScanGeom G, TableView cell_t, MapArgs A,
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : 3) k_scan(const T *__restrict__ cell, ScanGeom G, TableView cell_t, MapArgs A,
                                                      const __grid_constant__ TmapSet tm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long mbar[WARPS][2];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int nch = 1 + A.n_sub;
+    const int nstage = A.org_mode ? 1 : nch;  // channels staged by TMA / cp.async (org mode fills channel 1 on demand)
     // per-warp layout: stage[NBUF][nch][R*32] T | WarpTab<WS> cell | n_sub x WarpTab<WSS> | n_sub x WarpPairTab<PS>
     const size_t stage_bytes = (size_t)NBUF * nch * R * 32 * sizeof(T);
     const size_t per_warp = (stage_bytes + sizeof(WarpTab<WS>) + (size_t)A.n_sub * (sizeof(WarpTab<WSS>) + sizeof(WarpPairTab<PS>)) + 127) &
@@ -402,9 +406,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const T *__restrict__ cell,
         if (TMA) {
             if (lane == 0) {
                 const int c0 = (int)(t.tw * TW), c1 = (int)(t.tv * TV + (b % (TV / R)) * R), c2 = (int)(t.tu * TU + b / (TV / R));
-                mbar_expect_tx(bar_addr[sb], (unsigned)(nch * R * 32 * sizeof(T)));
+                mbar_expect_tx(bar_addr[sb], (unsigned)(nstage * R * 32 * sizeof(T)));
                 const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage + (size_t)sb * nch * R * 32);
-                for (int c = 0; c < nch; ++c) tma_load_3d(dst0 + c * R * 32 * (unsigned)sizeof(T), &tm.m[c], c0, c1, c2, bar_addr[sb]);
+                for (int c = 0; c < nstage; ++c) tma_load_3d(dst0 + c * R * 32 * (unsigned)sizeof(T), &tm.m[c], c0, c1, c2, bar_addr[sb]);
             }
             return;
         }
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const T *__restrict__ cell,
             const bool okj = ok && (v0 + j < G.n[1]);
             cp_async_elem<T>(dst + j * 32, okj ? src + j * G.st[1] : cell, okj);
         }
-        for (int c = 0; c < A.n_sub; ++c) {
+        for (int c = 0; c < nstage - 1; ++c) {
             const T *sc = reinterpret_cast<const T *>(A.sub[c]);
             const T *ss = ok ? sc + w * G.sst[2] + u * G.sst[0] + v0 * G.sst[1] : sc;
             T *dd = dst + (size_t)(1 + c) * R * 32;
@@ -458,17 +462,37 @@ __global__ void __launch_bounds__(WARPS * 32) k_scan(const T *__restrict__ cell,
             const unsigned lu = (unsigned)(b / (TV / R));
             const unsigned lv0 = (unsigned)((b % (TV / R)) * R);
             const T *cb = stage + (size_t)sb * nch * R * 32;
-            bool nz;
+            unsigned nzs = 0u;
             if (A.do_cell_props) {
-                const unsigned bnd = run_starts<T, R>(cb, lane, nz);
-                if (__any_sync(FULL, nz)) acc_batch<T, R, WS>(cb, bnd, *ctab, cell_t, G, Tc, lu, lv0, lane);
+                const unsigned bnd = run_starts<T, R>(cb, lane, nzs);
+                acc_batch<T, R, WS>(cb, bnd, nzs, *ctab, cell_t, G, Tc, lu, lv0, lane);
             }
-            for (int c = 0; c < A.n_sub; ++c) {
-                const T *sbuf = cb + (size_t)(1 + c) * R * 32;
-                const unsigned bnd = run_starts<T, R>(sbuf, lane, nz);
-                if (!__any_sync(FULL, nz)) continue;  // organelles are sparse: most batches stop here
-                if (A.do_sub_props) acc_batch<T, R, WSS>(sbuf, bnd, stab[c], A.sub_t[c], G, Tc, lu, lv0, lane);
-                acc_pairs<T, R, PS>(sbuf, cb, ptab[c], A.pair_t[c], lane);
+            if (A.org_mode) {
+                // staged channel 0 = organelle (props done above as the "cell" channel); overlap with the real cell
+                // volume, fetched only where the organelle is non-zero
+                if (!A.do_cell_props) run_starts<T, R>(cb, lane, nzs);
+                if (__any_sync(FULL, nzs != 0u)) {
+                    T *cbuf = stage + (size_t)sb * nch * R * 32 + R * 32;
+                    const long long w = cur.tw * TW + lane, u = cur.tu * TU + lu, v0 = cur.tv * TV + lv0;
+                    const T *cp = reinterpret_cast<const T *>(A.sub[0]) + w * G.sst[2] + u * G.sst[0] + v0 * G.sst[1];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        T cval = 0;
+                        if (cb[j * 32 + lane] != 0) cval = __ldg(cp + j * G.sst[1]);
+                        cbuf[j * 32 + lane] = cval;
+                    }
+                    __syncwarp();
+                    acc_pairs<T, R, PS>(cb, cbuf, ptab[0], A.pair_t[0], lane);
+                }
+            } else {
+                for (int c = 0; c < A.n_sub; ++c) {
+                    const T *sbuf = cb + (size_t)(1 + c) * R * 32;
+                    unsigned snz;
+                    const unsigned bnd = run_starts<T, R>(sbuf, lane, snz);
+                    if (!__any_sync(FULL, snz != 0u)) continue;  // organelles are sparse: most batches stop here
+                    if (A.do_sub_props) acc_batch<T, R, WSS>(sbuf, bnd, snz, stab[c], A.sub_t[c], G, Tc, lu, lv0, lane);
+                    acc_pairs<T, R, PS>(sbuf, cb, ptab[c], A.pair_t[c], lane);
+                }
             }
             __syncwarp();
             if (NBUF == 1) {  // single buffer: refill it now; the SM's other warps cover the latency
@@ -601,7 +625,7 @@ static int launch_scan(const void *cell, const ScanGeom &G, const TableView &cel
     TmapSet tm;
     memset(&tm, 0, sizeof(tm));
     bool tma = make_tmap(&tm.m[0], cell, (int)sizeof(T), G.n, G.st, R);
-    for (int c = 0; c < A.n_sub && tma; ++c) tma = make_tmap(&tm.m[1 + c], A.sub[c], (int)sizeof(T), G.n, G.sst, R);
+    for (int c = 0; c < A.n_sub && tma && !A.org_mode; ++c) tma = make_tmap(&tm.m[1 + c], A.sub[c], (int)sizeof(T), G.n, G.sst, R);
     // TMA: one buffer per warp, many resident warps hide the latency; LDGSTS fallback: double buffered
     // (measured: one buffer + 32 resident warps/SM beats double buffering with 16-20 warps, and R=16 beats R=8)
     if (tma) return launch_cfg<T, R, TU, TV, WARPS, WS, WSS, PS, 1, true>(cell, G, cell_t, A, tm, s);
@@ -613,6 +637,7 @@ static int launch_scan(const void *cell, const ScanGeom &G, const TableView &cel
 // props: R=16 rows per batch, tiles of 4 x 32 rows x 32 lanes; map: R=8, tiles of 8 x 16 rows (more channels staged)
 #define PROPS_CFG 16, 4, 32, 8, 64, 32, 32
 #define MAP_CFG 8, 8, 16, 4, 64, 32, 32
+#define ORG_CFG 8, 8, 16, 8, 64, 32, 32
 
 SYK_API int syk_find_object_properties(syk_table_t *t, const void *labels_dev, int elem_bytes, const int64_t shape[3],
                                        const int64_t strides[3], const int64_t origin[3], uint32_t chunk_seq, void *stream) {
@@ -646,6 +671,35 @@ SYK_API int syk_map_subcell_extract_props(syk_table_t *cell_t, syk_table_t *cons
     SYK_CHECK_ARG(n_sub == 0 || (subcell_dev && sub_strides && pair_t), "subcell arguments are NULL");
     if (shape[0] == 0 || shape[1] == 0 || shape[2] == 0) return SYK_OK;
     SYK_CHECK_ARG(cell_dev != nullptr, "cell_dev is NULL");
+    for (int c = 0; c < n_sub; ++c) {
+        SYK_CHECK_ARG(subcell_dev[c] != nullptr && pair_t[c] != nullptr, "subcell channel / pair table is NULL");
+        if (sub_t) SYK_CHECK_ARG(sub_t[c] != nullptr, "sub table is NULL");
+    }
+    if (!getenv("SYK_MAP_FUSED")) {
+        // Organelle-first decomposition (organelles are sparse): the cell props are one dense scan; every organelle channel
+        // is streamed on its own, and the cell volume is touched again only where that organelle is non-zero.
+        if (cell_t) {
+            rc = syk_find_object_properties(cell_t, cell_dev, elem_bytes, shape, cell_strides, origin, chunk_seq, stream);
+            if (rc) return rc;
+        }
+        for (int c = 0; c < n_sub; ++c) {
+            ScanGeom G;
+            plan_axes(shape, sub_strides, origin, chunk_seq, 8, 16, G);
+            for (int a = 0; a < 3; ++a) G.sst[a] = cell_strides[G.la[a]];
+            MapArgs A;
+            memset(&A, 0, sizeof(A));
+            A.n_sub = 1;
+            A.org_mode = 1;
+            A.do_cell_props = sub_t != nullptr;  // props of the staged (organelle) channel
+            A.sub[0] = cell_dev;
+            A.pair_t[0] = view_of(pair_t[c]);
+            const TableView tv = view_of(sub_t ? sub_t[c] : nullptr);
+            rc = elem_bytes == 8 ? launch_scan<unsigned long long, ORG_CFG>(subcell_dev[c], G, tv, A, (cudaStream_t)stream)
+                                 : launch_scan<unsigned int, ORG_CFG>(subcell_dev[c], G, tv, A, (cudaStream_t)stream);
+            if (rc) return rc;
+        }
+        return SYK_OK;
+    }
     ScanGeom G;
     plan_axes(shape, cell_strides, origin, chunk_seq, 8, 16, G);
     for (int a = 0; a < 3; ++a) G.sst[a] = n_sub ? sub_strides[G.la[a]] : 0;
@@ -655,13 +709,9 @@ SYK_API int syk_map_subcell_extract_props(syk_table_t *cell_t, syk_table_t *cons
     A.do_cell_props = cell_t != nullptr;
     A.do_sub_props = sub_t != nullptr;
     for (int c = 0; c < n_sub; ++c) {
-        SYK_CHECK_ARG(subcell_dev[c] != nullptr && pair_t[c] != nullptr, "subcell channel / pair table is NULL");
         A.sub[c] = subcell_dev[c];
         A.pair_t[c] = view_of(pair_t[c]);
-        if (sub_t) {
-            SYK_CHECK_ARG(sub_t[c] != nullptr, "sub table is NULL");
-            A.sub_t[c] = view_of(sub_t[c]);
-        }
+        if (sub_t) A.sub_t[c] = view_of(sub_t[c]);
     }
     if (elem_bytes == 8) return launch_scan<unsigned long long, MAP_CFG>(cell_dev, G, view_of(cell_t), A, (cudaStream_t)stream);
     return launch_scan<unsigned int, MAP_CFG>(cell_dev, G, view_of(cell_t), A, (cudaStream_t)stream);
