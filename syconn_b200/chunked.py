@@ -152,7 +152,7 @@ class ExtractionPipeline:
         g["shape"][0] = shape
         self.dev.check(L.syk_table_append_records(table.h, g.ctypes.data, log.data_ptr(), log.shape[0],
                                                   self.counters[kind_idx:].data_ptr(), self.dev._stream_ptr()))
-        self.launches += 1
+        self.launches += 2  # k_table_export + k_poison_on_overflow
 
     def process_chunk(self, seq, offset, cell, subcell, cell_halo):
         """One chunk: ``cell`` [X,Y,Z] and ``subcell`` [C,X,Y,Z] 64-bit labels at ``offset``; ``cell_halo`` the
@@ -174,19 +174,19 @@ class ExtractionPipeline:
             self.t_cs.clear()
             dev.find_object_properties(self.t_cs, self.cs_out, origin=out_off, chunk_seq=seq)
             self._append(self.t_cs, 1, self.logs["cs"], out_off, self.cs_out.shape)
-            self.launches += 3
+            self.launches += 3 + 1  # k_cs_fast tier 1, tier 2, k_detect_cs (list mode) + k_scan on the contact volume
         # stages 2+3: cell / organelle properties and overlap mapping (sd_proc.py:646-684)
         self.t_cell.clear()
         for t in self.t_sub + self.t_pair:
             t.clear()
         dev.map_subcell_extract_props(self.t_cell, self.t_sub, self.t_pair, cell, subcell, origin=offset, chunk_seq=seq)
-        self.launches += 2 + 2 * self.n_sub
+        self.launches += 1 + self.n_sub  # k_scan on the cell volume + one organelle-first k_scan per channel
         self._append(self.t_cell, 0, self.logs["cell"], offset, cell.shape)
         for c in range(self.n_sub):
             self._append(self.t_sub[c], 2 + c, self.logs[f"sub{c}"], offset, cell.shape)
             dev.check(L.syk_pairs_append(self.t_pair[c].h, self.pair_logs[c].data_ptr(), self.pair_logs[c].shape[0],
                                          self.counters[len(self.kinds) + c:].data_ptr(), dev._stream_ptr()))
-            self.launches += 1
+            self.launches += 2  # k_pairs_export + k_poison_on_overflow
 
     def _cs_buffer(self, cell_halo):
         oshape = [cell_halo.shape[i] - self.stencil[i] + 1 for i in range(3)]
@@ -287,7 +287,7 @@ class ExtractionPipeline:
             t.merge_records(recs)
             g = np.zeros(0, GEOM_DTYPE) if geoms_by_kind is None else geoms_by_kind["cs" if k == "cs" else "cell"]
             out[k] = t.export(g, max_records=max(recs.shape[0], 1))
-            self.launches += 3
+            self.launches += 2  # k_merge_records + k_table_export
         for c, p in enumerate(owned_pairs):
             need = max(1 << 16, 4 * p.shape[0]) if capacity is None else capacity
             t = self._final.get(("pairs", c))
@@ -297,5 +297,5 @@ class ExtractionPipeline:
                 t.clear()
             t.merge(p)
             outp.append(t.export(max_pairs=max(p.shape[0], 1)))
-            self.launches += 3
+            self.launches += 2  # k_pairs_merge + k_pairs_export
         return out, outp
