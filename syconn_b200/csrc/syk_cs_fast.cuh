@@ -29,7 +29,7 @@ constexpr int TW = 32;
 constexpr int LU = SYK_LU;
 constexpr int HASH = 256;
 constexpr int NOQ = TV * TW / 4;  // output quads per plane (128)
-constexpr int MAX_NQUAD = 320;    // host guarantees VP*WP/4 <= MAX_NQUAD
+constexpr int MAX_NQUAD = 384;    // host guarantees VP*WP/4 <= MAX_NQUAD
 constexpr int MAX_WP = 48;        // host guarantees WP <= MAX_WP
 // Two tiers of the same kernel: tier 1 keeps at most 24 ids near the marching plane (small shared-memory footprint,
 // many CTAs per SM); the few segments that need more are redone by tier 2 (64 ids), then by the generic kernel.

@@ -136,7 +136,8 @@ def test_map_vs_oracle_random(mods, seed, shape, nsub):
 
 @pytest.mark.parametrize("seed,shape,st", [(0, (40, 44, 39), (13, 13, 7)), (1, (30, 30, 30), (7, 7, 3)),
                                            (2, (21, 37, 50), (5, 5, 3)), (3, (70, 20, 19), (3, 3, 3)),
-                                           (4, (24, 24, 24), (17, 17, 9)), (5, (16, 20, 33), (1, 3, 1))])
+                                           (4, (24, 24, 24), (17, 17, 9)), (5, (16, 20, 33), (1, 3, 1)),
+                                           (6, (48, 40, 36), (15, 15, 9)), (7, (40, 36, 44), (9, 15, 15))])
 def test_detect_cs_vs_oracle_random(mods, seed, shape, st):
     rng = np.random.default_rng(seed)
     oracle, synth = mods["oracle"], mods["synth"]
