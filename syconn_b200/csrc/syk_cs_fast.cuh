@@ -33,7 +33,13 @@ constexpr int MAX_NQUAD = 384;    // host guarantees VP*WP/4 <= MAX_NQUAD
 constexpr int MAX_WP = 48;        // host guarantees WP <= MAX_WP
 // Two tiers of the same kernel: tier 1 keeps at most 24 ids near the marching plane (small shared-memory footprint,
 // many CTAs per SM); the few segments that need more are redone by tier 2 (64 ids), then by the generic kernel.
-constexpr int GMAX_T1 = 3, NT_T1 = 192;
+#ifndef SYK_NT1
+#define SYK_NT1 192
+#endif
+#ifndef SYK_MINB1
+#define SYK_MINB1 6
+#endif
+constexpr int GMAX_T1 = 3, NT_T1 = SYK_NT1;
 constexpr int GMAX_T2 = 8, NT_T2 = 320;
 
 struct FastGeom {
@@ -195,7 +201,6 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
     const int VP = G.VP, WP = G.WP, CR = G.CR;
     const int plane = VP * WP, oplane = TV * WP;
     const int nquad = plane >> 2, qpr = WP >> 2;  // quads per plane / per row
-    const int NP = LU + su - 1;                   // input planes per segment
 
     for (int i = tid; i < GMAX * (KMAX + 8); i += NT) {
         const int g = i / (KMAX + 8), j = i - g * (KMAX + 8);
@@ -211,6 +216,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
         const long long tv = r0 % G.segs[1];
         const long long tu = r0 / G.segs[1];
         const long long u0 = tu * LU, v0 = tv * TV, w0 = tw * TW;  // output origin == input origin of the haloed block
+        const int NP = (int)min((long long)(LU + su - 1), G.n[0] - u0);  // input planes of the segment (the last one is short)
         __syncthreads();
         // ---- segment init: zero running sums / hash ----
         {
