@@ -312,10 +312,10 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 if (v0 + dq_b < G.on[1] && w0 + dq_c + e < G.on[2]) dIn |= 0x80u << (8 * e);
         }
         const long long d_rowoff = (v0 + dq_b) * G.ost[1] + (w0 + dq_c) * G.ost[2];
-        auto compact_outputs = [&](int p) {
+        auto compact_outputs = [&](int p, int rf) {  // rf == p % CF
             const int uo = p - su + 1;
             if (dq < 0 || dIn == 0u || uo < 0 || u0 + uo >= G.on[0]) return;
-            const unsigned char *cf = cflag + ((uo + ou) % G.CF) * (TV * TW);
+            const unsigned char *cf = cflag + (rf + 1 == G.CF ? 0 : rf + 1) * (TV * TW);  // plane uo + ou == p - ou; CF == ou + 1
             const unsigned E = reinterpret_cast<const unsigned *>(cf)[dq] & dIn;  // 0x80 per in-bounds boundary voxel
             unsigned long long *o4 = out + (u0 + uo) * G.ost[0] + d_rowoff;
             if (E == 0u && dIn == 0x80808080u && G.out_vec) {
@@ -345,8 +345,10 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
         }
         __syncthreads();
         bool aborted = false;
-        for (int p = 0; p < NP; ++p) {
+        int rp = 0, rf = 0;  // p % CR, p % CF (ring positions, kept without divisions)
+        for (int p = 0; p < NP; ++p, rp = (rp + 1 == CR ? 0 : rp + 1), rf = (rf + 1 == G.CF ? 0 : rf + 1)) {
             const long long gu = u0 + p;
+            const int rp1 = rp ? rp - 1 : CR - 1, rp2 = rp1 ? rp1 - 1 : CR - 1, rpn = rp + 1 == CR ? 0 : rp + 1;
             // A. prefetch plane p+1 into registers; relabel pass 1 (find / insert the key of every voxel of plane p)
             uint4 pre[MAXQ];
             int hidx[MAXQ][4];
@@ -380,7 +382,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 H.tb[tid] = (unsigned short)(((255 - r) << 8) | tid);
             }
             const int NG = used ? ((64 - __clzll((long long)used) + 7) >> 3) : 0;
-            unsigned char *cp = comp + (p % CR) * plane;
+            unsigned char *cp = comp + rp * plane;
 #pragma unroll
             for (int k = 0; k < MAXQ; ++k) {
                 const int q = tid + k * NT;
@@ -411,7 +413,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             // C1. boundary flags of plane p-1 (needs planes p-2, p-1, p), four voxels per thread
             if (tid < NOQ && p >= 2 && p - 1 >= ou && p - 1 <= LU - 1 + ou) {
                 const int pc = p - 1;
-                const unsigned char *c0 = comp + ((p - 2) % CR) * plane, *c1 = comp + ((p - 1) % CR) * plane, *c2 = comp + (p % CR) * plane;
+                const unsigned char *c0 = comp + rp2 * plane, *c1 = comp + rp1 * plane, *c2 = comp + rp * plane;
                 const long long cu = u0 + pc;
                 const unsigned mUlo = cu > 0 ? 0xFFFFFFFFu : 0u, mUhi = cu + 1 < G.n[0] ? 0xFFFFFFFFu : 0u;
                 const int rowo = (oq_b + ov) * WP, col = oq_c + ow;
@@ -419,13 +421,13 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 unsigned D = ((C ^ ld4(c0 + rowo, col)) & mUlo) | ((C ^ ld4(c2 + rowo, col)) & mUhi);
                 D |= ((C ^ ld4(c1 + rowo - WP, col)) & mVlo) | ((C ^ ld4(c1 + rowo + WP, col)) & mVhi);
                 D |= ((C ^ ld4(c1 + rowo, col - 1)) & mL) | ((C ^ ld4(c1 + rowo, col + 1)) & mR);
-                reinterpret_cast<unsigned *>(cflag + (pc % G.CF) * (TV * TW))[tid] = C | (nz_bytes(D) & nz_bytes(C));
+                reinterpret_cast<unsigned *>(cflag + (rf ? rf - 1 : G.CF - 1) * (TV * TW))[tid] = C | (nz_bytes(D) & nz_bytes(C));
             }
             // C2. v-sums (4-bit fields) of the entering plane p and of the leaving plane p - su; their difference
             //     advances the running sum over the last su planes (8-bit fields)
             {
-                const unsigned char *cn = comp + (p % CR) * plane;
-                const unsigned char *co = comp + ((p + 1) % CR) * plane;  // == (p - su) % CR since CR == su + 1
+                const unsigned char *cn = comp + rp * plane;
+                const unsigned char *co = comp + rpn * plane;  // plane p - su, since CR == su + 1
                 const bool has_old = p >= su;
 #pragma unroll 1
                 for (int k = 0; k < MAXIT; ++k) {
@@ -449,12 +451,12 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 }
             }
             if (!early_d) __syncthreads();  // the flags of plane p - ou were written in this very phase
-            compact_outputs(p);
+            compact_outputs(p, rf);
             __syncthreads();
             // D. boundary voxels of plane uo = p - su + 1: final sum along w and arg-max
             const int uo = p - su + 1;
             if (uo >= 0 && u0 + uo < G.on[0]) {
-                const unsigned char *cf = cflag + ((uo + ou) % G.CF) * (TV * TW);
+                const unsigned char *cf = cflag + (rf + 1 == G.CF ? 0 : rf + 1) * (TV * TW);
                 unsigned long long *orow = out + (u0 + uo) * G.ost[0];
                 const int ne = H.n_edge;
                 for (int e = tid; e < ne; e += NT) {
