@@ -437,21 +437,24 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
         if (g1 > F.nsegs) g1 = F.nsegs;
         const long long g2 = (long long)sms * ctas2;
         unsigned long long *o = (unsigned long long *)out;
+        // tier 1 is specialised for the production stencil [13, 13, 7] in both memory orders (x fastest: internal
+        // (u, v, w) = (7, 13, 13); C order: (13, 13, 7)); any other stencil runs the same kernel with run-time geometry
+        void (*k1)(const void *, unsigned long long *, FastGeom, FastSmem, const unsigned *, const unsigned *, unsigned *, unsigned *);
+        void (*k2)(const void *, unsigned long long *, FastGeom, FastSmem, const unsigned *, const unsigned *, unsigned *, unsigned *);
+        const bool s7 = F.sten[0] == 7 && F.sten[1] == 13 && F.sten[2] == 13 && !getenv("SYK_CS_NOSPEC");
+        const bool s13 = F.sten[0] == 13 && F.sten[1] == 13 && F.sten[2] == 7 && !getenv("SYK_CS_NOSPEC");
         if (F.vec4) {
-            auto k1 = k_cs_fast<true, GMAX_T1, NT_T1, MINB1>;
-            auto k2 = k_cs_fast<true, GMAX_T2, NT_T2, MINB2>;
-            SYK_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
-            SYK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
-            k1<<<(unsigned)g1, NT_T1, L1.total, s>>>(arr, o, F, L1, nullptr, nullptr, list1, cnt1);
-            k2<<<(unsigned)g2, NT_T2, L2.total, s>>>(arr, o, F, L2, list1, cnt1, list2, cnt2);
+            k1 = s7 ? k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 7, 13, 13>
+                    : s13 ? k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 13, 13, 7> : k_cs_fast<true, GMAX_T1, NT_T1, MINB1>;
+            k2 = k_cs_fast<true, GMAX_T2, NT_T2, MINB2>;
         } else {
-            auto k1 = k_cs_fast<false, GMAX_T1, NT_T1, MINB1>;
-            auto k2 = k_cs_fast<false, GMAX_T2, NT_T2, MINB2>;
-            SYK_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
-            SYK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
-            k1<<<(unsigned)g1, NT_T1, L1.total, s>>>(arr, o, F, L1, nullptr, nullptr, list1, cnt1);
-            k2<<<(unsigned)g2, NT_T2, L2.total, s>>>(arr, o, F, L2, list1, cnt1, list2, cnt2);
+            k1 = k_cs_fast<false, GMAX_T1, NT_T1, MINB1>;
+            k2 = k_cs_fast<false, GMAX_T2, NT_T2, MINB2>;
         }
+        SYK_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
+        SYK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
+        k1<<<(unsigned)g1, NT_T1, L1.total, s>>>(arr, o, F, L1, nullptr, nullptr, list1, cnt1);
+        k2<<<(unsigned)g2, NT_T2, L2.total, s>>>(arr, o, F, L2, list1, cnt1, list2, cnt2);
         SYK_CUDA(cudaGetLastError());
         G.seg_list = list2;
         G.seg_count = cnt2;

@@ -63,20 +63,20 @@ struct FastSmem {  // offsets in bytes into dynamic shared memory
     int raw, comp, ssum, cflag, elist, total;
 };
 
-inline FastSmem fast_layout(const FastGeom &G, int GMAX) {
+__host__ __device__ __forceinline__ int fast_align16(int bytes) { return (bytes + 15) & ~15; }  // regions are 16-byte aligned
+__host__ __device__ __forceinline__ FastSmem fast_layout(int VP, int WP, int CR, int CF, int GMAX) {
     FastSmem L;
-    const int plane = G.VP * G.WP;
-    const int oplane = TV * G.WP;
-    int o = 0;
-    auto take = [&](int bytes) { int at = o; o += (bytes + 15) & ~15; return at; };  // every region 16-byte aligned
-    L.raw = take(plane * 4);
-    L.comp = take(G.CR * plane);             // ring of compact-index planes, 1 byte per voxel
-    L.ssum = take(GMAX * oplane * 8);        // uint2 {even slots, odd slots} in 8-bit fields
-    L.cflag = take(G.CF * TV * TW);
-    L.elist = take(TV * TW * 2);
-    L.total = o;
+    const int plane = VP * WP;
+    const int oplane = TV * WP;
+    L.raw = 0;
+    L.comp = L.raw + fast_align16(plane * 4);
+    L.ssum = L.comp + fast_align16(CR * plane);            // ring of compact-index planes, 1 byte per voxel
+    L.cflag = L.ssum + fast_align16(GMAX * oplane * 8);    // uint2 {even slots, odd slots} in 8-bit fields
+    L.elist = L.cflag + fast_align16(CF * TV * TW);
+    L.total = L.elist + fast_align16(TV * TW * 2);
     return L;
 }
+inline FastSmem fast_layout(const FastGeom &G, int GMAX) { return fast_layout(G.VP, G.WP, G.CR, G.CF, GMAX); }
 
 constexpr unsigned SL_PENDING = 0xFFFFFFFFu;  // key inserted, slot being allocated
 constexpr unsigned SL_DEAD = 0xFFFFFFFEu;     // id left the su-plane window: its slot was recycled
@@ -89,7 +89,9 @@ struct HashT {
     int lastp[HASH];               // last plane in which the key was seen
     unsigned ids[KMAX];            // id held by a slot
     int owner[KMAX];               // hash index owning the slot
-    unsigned short tb[KMAX];       // ((255 - rank by id) << 8) | slot: tie-break key of the arg-max (smallest id wins)
+    // ((255 - rank by id) << 8) | slot: tie-break key of the arg-max (smallest id wins).  The 8 entries of a group are
+    // stored in the order of the 16-bit count fields {0,4 | 2,6 | 1,5 | 3,7} so that one 16-byte load pairs them up.
+    __align__(16) unsigned short tb[KMAX];
     unsigned lut[GMAX][KMAX + 8];  // indicator word of compact index j in group g
     unsigned long long freemask;   // bit s set: slot s is free (lowest free slot is handed out first)
     int ovf, newflag, n_edge;
@@ -176,10 +178,12 @@ __device__ __forceinline__ void vsum8(const unsigned char *col, int WP, int sv, 
     }
 }
 
-// seg_list == nullptr: all G.nsegs segments; otherwise the *seg_count segments named in seg_list (tier 2)
-template <bool VEC4, int GMAX, int NT, int MINB>
+// seg_list == nullptr: all G.nsegs segments; otherwise the *seg_count segments named in seg_list (tier 2).
+// SU/SV/SW != 0: stencil known at compile time (must equal G.sten) -- plane pitches, ring depths and the shared-memory
+// layout fold into immediates and the window loops unroll.
+template <bool VEC4, int GMAX, int NT, int MINB, int SU = 0, int SV = 0, int SW = 0>
 __global__ void __launch_bounds__(NT, MINB)
-k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, FastGeom G, FastSmem L,
+k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, FastGeom G, FastSmem Lrt,
           const unsigned *__restrict__ seg_list, const unsigned *__restrict__ seg_count,
           unsigned *__restrict__ hard_list, unsigned *__restrict__ hard_count) {
     using Hash = HashT<GMAX>;
@@ -187,6 +191,13 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
     constexpr unsigned long long ALL_SLOTS = Hash::ALL_SLOTS;
     constexpr int MAXQ = (MAX_NQUAD + NT - 1) / NT;             // relabel quads (4 voxels along w) per thread
     constexpr int MAXIT = (GMAX * (TV / 8) * MAX_WP + NT - 1) / NT;  // v-pass items (8 outputs each) per thread
+    constexpr bool FIX = SU > 0;
+    const int su = FIX ? SU : G.sten[0], sv = FIX ? SV : G.sten[1], sw = FIX ? SW : G.sten[2];
+    const int ou = FIX ? SU / 2 : G.off[0], ov = FIX ? SV / 2 : G.off[1], ow = FIX ? SW / 2 : G.off[2];
+    const int VP = FIX ? TV + SV - 1 : G.VP, WP = FIX ? ((TW + SW - 1 + 3) & ~3) : G.WP;
+    const int CR = FIX ? SU + 1 : G.CR, CF = FIX ? SU / 2 + 1 : G.CF;
+    const bool pair_ok = FIX ? (2 * SU * SV <= 255) : (G.pair_ok != 0);
+    const FastSmem L = FIX ? fast_layout(VP, WP, CR, CF, GMAX) : Lrt;
     extern __shared__ __align__(16) unsigned char sm[];
     unsigned *raw = reinterpret_cast<unsigned *>(sm + L.raw);
     unsigned char *comp = sm + L.comp;
@@ -196,9 +207,6 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
     __shared__ Hash H;
 
     const int tid = threadIdx.x;
-    const int su = G.sten[0], sv = G.sten[1], sw = G.sten[2];
-    const int ou = G.off[0], ov = G.off[1], ow = G.off[2];
-    const int VP = G.VP, WP = G.WP, CR = G.CR;
     const int plane = VP * WP, oplane = TV * WP;
     const int nquad = plane >> 2, qpr = WP >> 2;  // quads per plane / per row
 
@@ -315,7 +323,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
         auto compact_outputs = [&](int p, int rf) {  // rf == p % CF
             const int uo = p - su + 1;
             if (dq < 0 || dIn == 0u || uo < 0 || u0 + uo >= G.on[0]) return;
-            const unsigned char *cf = cflag + (rf + 1 == G.CF ? 0 : rf + 1) * (TV * TW);  // plane uo + ou == p - ou; CF == ou + 1
+            const unsigned char *cf = cflag + (rf + 1 == CF ? 0 : rf + 1) * (TV * TW);  // plane uo + ou == p - ou; CF == ou + 1
             const unsigned E = reinterpret_cast<const unsigned *>(cf)[dq] & dIn;  // 0x80 per in-bounds boundary voxel
             unsigned long long *o4 = out + (u0 + uo) * G.ost[0] + d_rowoff;
             if (E == 0u && dIn == 0x80808080u && G.out_vec) {
@@ -346,7 +354,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
         __syncthreads();
         bool aborted = false;
         int rp = 0, rf = 0;  // p % CR, p % CF (ring positions, kept without divisions)
-        for (int p = 0; p < NP; ++p, rp = (rp + 1 == CR ? 0 : rp + 1), rf = (rf + 1 == G.CF ? 0 : rf + 1)) {
+        for (int p = 0; p < NP; ++p, rp = (rp + 1 == CR ? 0 : rp + 1), rf = (rf + 1 == CF ? 0 : rf + 1)) {
             const long long gu = u0 + p;
             const int rp1 = rp ? rp - 1 : CR - 1, rp2 = rp1 ? rp1 - 1 : CR - 1, rpn = rp + 1 == CR ? 0 : rp + 1;
             // A. prefetch plane p+1 into registers; relabel pass 1 (find / insert the key of every voxel of plane p)
@@ -379,7 +387,8 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 const unsigned me = H.ids[tid];
                 int r = 0;
                 for (unsigned long long m = used; m; m &= m - 1ull) r += H.ids[__ffsll((long long)m) - 1] < me;
-                H.tb[tid] = (unsigned short)(((255 - r) << 8) | tid);
+                const int n = tid & 7;
+                H.tb[(tid & ~7) | ((n & 1) << 2) | (n & 2) | (n >> 2)] = (unsigned short)(((255 - r) << 8) | tid);
             }
             const int NG = used ? ((64 - __clzll((long long)used) + 7) >> 3) : 0;
             unsigned char *cp = comp + rp * plane;
@@ -421,7 +430,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 unsigned D = ((C ^ ld4(c0 + rowo, col)) & mUlo) | ((C ^ ld4(c2 + rowo, col)) & mUhi);
                 D |= ((C ^ ld4(c1 + rowo - WP, col)) & mVlo) | ((C ^ ld4(c1 + rowo + WP, col)) & mVhi);
                 D |= ((C ^ ld4(c1 + rowo, col - 1)) & mL) | ((C ^ ld4(c1 + rowo, col + 1)) & mR);
-                reinterpret_cast<unsigned *>(cflag + (rf ? rf - 1 : G.CF - 1) * (TV * TW))[tid] = C | (nz_bytes(D) & nz_bytes(C));
+                reinterpret_cast<unsigned *>(cflag + (rf ? rf - 1 : CF - 1) * (TV * TW))[tid] = C | (nz_bytes(D) & nz_bytes(C));
             }
             // C2. v-sums (4-bit fields) of the entering plane p and of the leaving plane p - su; their difference
             //     advances the running sum over the last su planes (8-bit fields)
@@ -456,19 +465,20 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             // D. boundary voxels of plane uo = p - su + 1: final sum along w and arg-max
             const int uo = p - su + 1;
             if (uo >= 0 && u0 + uo < G.on[0]) {
-                const unsigned char *cf = cflag + (rf + 1 == G.CF ? 0 : rf + 1) * (TV * TW);
+                const unsigned char *cf = cflag + (rf + 1 == CF ? 0 : rf + 1) * (TV * TW);
                 unsigned long long *orow = out + (u0 + uo) * G.ost[0];
                 const int ne = H.n_edge;
                 for (int e = tid; e < ne; e += NT) {
                     const int i = elist[e];
                     const int b = i / TW, c = i - b * TW;
                     const int jc = cf[i] & 0x7F;
+                    const int gc = (jc - 1) >> 3, nc = (jc - 1) & 7;
                     unsigned best = 0u;
                     for (int g = 0; g < NG; ++g) {
                         const uint2 *sp = ssum + g * oplane + b * WP + c;
                         unsigned c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
                         int r = 0;
-                        if (G.pair_ok) {  // add two ring sums in 8-bit fields first (2*su*sv <= 255), then widen
+                        if (pair_ok) {  // add two ring sums in 8-bit fields first (2*su*sv <= 255), then widen
                             for (; r + 1 < sw; r += 2) {
                                 const uint2 a = sp[r], d = sp[r + 1];
                                 const unsigned l = a.x + d.x, h = a.y + d.y;
@@ -486,19 +496,24 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                             c3 += (a.y >> 8) & 0x00FF00FFu;  // slots 3, 7
                         }
                         if ((c0 | c1 | c2 | c3) == 0u) continue;
-                        const unsigned cnt[8] = {c0 & 0xFFFFu, c2 & 0xFFFFu, c1 & 0xFFFFu, c3 & 0xFFFFu,
-                                                 c0 >> 16,     c2 >> 16,     c1 >> 16,     c3 >> 16};
-#pragma unroll
-                        for (int n = 0; n < 8; ++n) {
-                            const int s = g * 8 + n;
-                            if (s + 1 != jc && cnt[n] != 0u) {  // free slots have zero counts
-                                const unsigned key = (cnt[n] << 16) | H.tb[s];
-                                best = key > best ? key : best;
-                            }
+                        if (g == gc) {  // the centre id does not compete: clear its 16-bit field
+                            const unsigned keep = (nc & 4) ? 0x0000FFFFu : 0xFFFF0000u;
+                            const int r4 = nc & 3;
+                            if (r4 == 0) c0 &= keep;
+                            else if (r4 == 1) c2 &= keep;
+                            else if (r4 == 2) c1 &= keep;
+                            else c3 &= keep;
                         }
+                        // keys (count << 16) | tie-break; slots that are free or absent have count 0 -> key < 65536
+                        const uint4 t = reinterpret_cast<const uint4 *>(H.tb)[g];
+                        const unsigned k0 = max(__byte_perm(t.x, c0, 0x5410), __byte_perm(t.x, c0, 0x7632));
+                        const unsigned k1 = max(__byte_perm(t.y, c1, 0x5410), __byte_perm(t.y, c1, 0x7632));
+                        const unsigned k2 = max(__byte_perm(t.z, c2, 0x5410), __byte_perm(t.z, c2, 0x7632));
+                        const unsigned k3 = max(__byte_perm(t.w, c3, 0x5410), __byte_perm(t.w, c3, 0x7632));
+                        best = max(best, max(max(k0, k1), max(k2, k3)));
                     }
                     unsigned long long res = 0ull;
-                    if (best) {
+                    if (best >> 16) {
                         const unsigned center = H.ids[jc - 1], key = H.ids[best & 0xFFu];
                         res = center > key ? (((unsigned long long)key << 32) + center) : (((unsigned long long)center << 32) + key);
                     }
