@@ -37,7 +37,7 @@ constexpr int MAX_WP = 48;        // host guarantees WP <= MAX_WP
 #define SYK_NT1 192
 #endif
 #ifndef SYK_MINB1
-#define SYK_MINB1 6
+#define SYK_MINB1 5
 #endif
 constexpr int GMAX_T1 = 3, NT_T1 = SYK_NT1;
 constexpr int GMAX_T2 = 8, NT_T2 = 320;
@@ -372,10 +372,28 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 hidx[k][0] = hidx[k][1] = hidx[k][2] = hidx[k][3] = -1;
                 if (q < nquad) {
                     const uint4 a = reinterpret_cast<const uint4 *>(raw)[q];
-                    if (a.x != 0u) hidx[k][0] = hash_find_insert(H, a.x, p);
-                    if (a.y != 0u) hidx[k][1] = (a.y == a.x) ? hidx[k][0] : hash_find_insert(H, a.y, p);
-                    if (a.z != 0u) hidx[k][2] = (a.z == a.y) ? hidx[k][1] : hash_find_insert(H, a.z, p);
-                    if (a.w != 0u) hidx[k][3] = (a.w == a.z) ? hidx[k][2] : hash_find_insert(H, a.w, p);
+                    int h0 = -1, h1 = -1, h2 = -1, h3 = -1;
+                    if (a.x != 0u) h0 = hash_find_insert(H, a.x, p);
+                    if (a.y == a.x) h1 = h0;
+                    if (a.z == a.x) h2 = h0;
+                    if (a.w == a.x) h3 = h0;
+                    // the other distinct labels of the quad (rare: a boundary crosses it) share one call site
+                    unsigned need = 0u;
+                    if (a.y != 0u && a.y != a.x) need |= 2u;
+                    if (a.z != 0u && a.z != a.x && a.z != a.y) need |= 4u;
+                    if (a.w != 0u && a.w != a.x && a.w != a.y && a.w != a.z) need |= 8u;
+                    while (need) {
+                        const unsigned lab = (need & 2u) ? a.y : (need & 4u) ? a.z : a.w;
+                        const int h = hash_find_insert(H, lab, p);
+                        if (a.y == lab) h1 = h;
+                        if (a.z == lab) h2 = h;
+                        if (a.w == lab) h3 = h;
+                        need &= need - 1u;
+                    }
+                    hidx[k][0] = h0;
+                    hidx[k][1] = h1;
+                    hidx[k][2] = h2;
+                    hidx[k][3] = h3;
                 }
             }
             __syncthreads();
