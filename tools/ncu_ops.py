@@ -33,12 +33,15 @@ for f in os.listdir(tmp):
             continue
         if fn and re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
             seq.append(cur)
+which = int(os.environ.get("NCU_RESULT", "0"))  # index of the result inside the report (the page lists them back to back)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-hi = next(i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r)
+heads = [i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r]
+hi = heads[which]
+end = heads[which + 1] - 1 if which + 1 < len(heads) else len(rows)
 hdr = rows[hi]
 ia, isrc, ismp = hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("# Samples")
-data = [r for r in rows[hi + 1:] if len(r) > ia and r[ia].isdigit()]
+data = [r for r in rows[hi + 1:end] if len(r) > ia and r[ia].isdigit()]
 cands = [k for k in lines_by_fn if ksub in k and len(lines_by_fn[k]) == len(data)]
 if not cands:
     sys.exit("no function with matching SASS length (profile taken with another build?)")

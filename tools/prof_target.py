@@ -30,7 +30,11 @@ elif what == "map":
     sts = [dev.IdTable(1 << 18) for _ in range(3)]
     pts = [dev.PairTable(1 << 18) for _ in range(3)]
     for _ in range(reps):
+        ct.clear()
+        for t in sts + pts:
+            t.clear()
         dev.map_subcell_extract_props(ct, sts, pts, cell, subs)
+    print('digest', ct.count()[0], [t.count()[0] for t in sts], [int(p.export()[:, 2].sum()) for p in pts])
 elif what == "cs":
     seg = dev.synth_labels((S + 12, S + 12, S + 6), pitch=pitch, seed=1, dtype=torch.int32, order=order)
     out = dev.detect_cs(seg)
