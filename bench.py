@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--e2e-chunks", type=int, default=2, help="chunks per step of the host-buffer (e2e) measurement")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-workers", type=int, default=4, help="host threads issuing the host-buffer calls")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -355,53 +356,80 @@ def e2e_host(args, chunks):
         ho = torch.empty(oshape, dtype=torch.int64, pin_memory=True)
         keep.append((hc, hs, hh, ho))
         host.append((hc.numpy().view(np.uint64), hs.numpy().view(np.uint64), hh.numpy().view(np.uint32), ho.numpy().view(np.uint64)))
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    lock = threading.Lock()
     h2d = d2h = 0
 
-    def one_pass(fused=False):
+    def cs_task(halo, cbuf, fused):
         nonlocal h2d, d2h
-        h2d = d2h = 0
-        for cell, subs, halo, cbuf in host:
-            if fused:  # extension: contact volume + its properties in one call (no second PCIe trip of the contacts)
-                contacts, props = detect_cs(halo, STENCIL, out=cbuf, return_props=True)
-                h2d += halo.nbytes
-                d2h += contacts.nbytes + 64 * len(props[2])
-            else:      # the reference worker's call sequence, cs_extraction_steps.py:391,439
-                contacts = detect_cs(halo, STENCIL, out=cbuf)
-                h2d += halo.nbytes
-                d2h += contacts.nbytes
-                r = _host.find_object_properties_records(contacts)
-                h2d += contacts.nbytes
-                d2h += r.nbytes
-            cr, sr, pr = _host.map_subcell_records(cell, subs)
+        if fused:  # extension: contact volume + its properties in one call (no second PCIe trip of the contacts)
+            contacts, rec = detect_cs(halo, STENCIL, out=cbuf, return_props="records")
+            up, down = halo.nbytes, contacts.nbytes + rec.nbytes
+        else:      # the reference worker's call sequence, cs_extraction_steps.py:391,439
+            contacts = detect_cs(halo, STENCIL, out=cbuf)
+            r = _host.find_object_properties_records(contacts)
+            up, down = halo.nbytes + contacts.nbytes, contacts.nbytes + r.nbytes
+        with lock:
+            h2d += up
+            d2h += down
+
+    def map_task(cell, subs):
+        nonlocal h2d, d2h
+        cr, sr, pr = _host.map_subcell_records(cell, subs)
+        with lock:
             h2d += cell.nbytes + subs.nbytes
             d2h += cr.nbytes + sum(x.nbytes for x in sr) + sum(x.nbytes for x in pr)
-    one_pass()
-    torch.cuda.synchronize()
+
+    def one_pass(fused, pool):
+        nonlocal h2d, d2h
+        h2d = d2h = 0
+        if pool is None:
+            for cell, subs, halo, cbuf in host:
+                cs_task(halo, cbuf, fused)
+                map_task(cell, subs)
+        else:  # one call per worker thread at a time; every thread owns a stream inside libsyk, so uploads, kernels and
+               # downloads of different calls overlap (PCIe is full duplex)
+            futs = []
+            for cell, subs, halo, cbuf in host:
+                futs.append(pool.submit(map_task, cell, subs))
+                futs.append(pool.submit(cs_task, halo, cbuf, fused))
+            for f in futs:
+                f.result()
+
     reps = max(1, min(args.steps, 3))
-    ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        one_pass()
-        torch.cuda.synchronize()
-        ts.append(time.perf_counter() - t0)
-    dt = float(np.median(ts))
     vox = sum(int(c[0].size) for c in host)
-    h2d0, d2h0 = h2d, d2h
-    one_pass(True)
-    torch.cuda.synchronize()
-    tf = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        one_pass(True)
+
+    def measure(fused, pool):
+        one_pass(fused, pool)
         torch.cuda.synchronize()
-        tf.append(time.perf_counter() - t0)
-    dtf = float(np.median(tf))
-    fused = {"value": vox / dtf / 1e9, "unit": "GVoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-             "api": "syk_detect_cs_props_host (extension) + syk_map_subcell_extract_props_host"}
-    h2d, d2h = h2d0, d2h0
-    return {"value": vox / dt / 1e9, "fused_variant": fused, "unit": "GVoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "chunks_per_step": n, "pass_seconds": [round(t, 4) for t in ts], "api": "syk_detect_cs_host + syk_find_object_properties_host + "
-                                        "syk_map_subcell_extract_props_host (pinned host buffers, one synchronous call per stage and chunk)"}
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            one_pass(fused, pool)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        return {"value": vox / float(np.median(ts)) / 1e9, "unit": "GVoxels/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "pass_seconds": [round(t, 4) for t in ts]}
+
+    seq_api = ("syk_detect_cs_host + syk_find_object_properties_host + syk_map_subcell_extract_props_host (pinned host buffers, "
+               "one synchronous call per stage and chunk)")
+    fused_api = "syk_detect_cs_props_host (extension) + syk_map_subcell_extract_props_host"
+    serial = measure(False, None)
+    serial_fused = measure(True, None)
+    W = max(1, args.e2e_workers)
+    with ThreadPoolExecutor(max_workers=W) as pool:
+        par = measure(False, pool)
+        par_fused = measure(True, pool)
+    serial["api"] = seq_api
+    serial_fused["api"] = fused_api
+    par_fused["api"] = fused_api + f", {W} worker threads"
+    out = dict(par)
+    out.update({"chunks_per_step": n, "workers": W,
+                "api": seq_api + f"; the calls are issued from {W} worker threads (the reference fans the same calls out over worker "
+                                 "processes), each thread's copies and kernels run on its own stream",
+                "single_thread": serial, "fused_variant": par_fused, "fused_single_thread": serial_fused})
+    return out
 
 
 if __name__ == "__main__":

@@ -13,6 +13,9 @@
 void syk_set_error(const char *fmt, ...);
 int syk_require_device();
 void syk_pool_keep_warm();  // raise the release threshold of the default stream-ordered pool (once)
+// Stream of the calling host thread for the *_host entry points (non-blocking, created on first use): calls made
+// from different threads overlap their PCIe copies and kernels instead of serialising on the default stream.
+cudaStream_t syk_host_stream();
 
 #define SYK_CUDA(call)                                                                             \
     do {                                                                                           \
@@ -62,9 +65,10 @@ static_assert(sizeof(SykPairSlot) == 32, "pair slot must be 32 bytes");
 struct syk_table {
     SykSlot *slots;
     uint64_t capacity;  // power of two
-    int *flags;         // device: [0] overflow
-    unsigned long long *counter;  // device scratch counter (export)
+    int *flags;         // device: [0] overflow (first 16 bytes of the 64-byte control block)
+    unsigned long long *counter;  // device scratch counter (export), control block + 32
     int device;
+    cudaStream_t stream;  // allocation stream (the table is freed on it)
 };
 struct syk_pairs {
     SykPairSlot *slots;
@@ -72,7 +76,11 @@ struct syk_pairs {
     int *flags;
     unsigned long long *counter;
     int device;
+    cudaStream_t stream;
 };
+// stream-ordered construction (the public creators use the default stream)
+int syk_table_create_on(syk_table **out, uint64_t capacity, cudaStream_t s);
+int syk_pairs_create_on(syk_pairs **out, uint64_t capacity, cudaStream_t s);
 
 // device-side views passed by value to kernels
 struct TableView {

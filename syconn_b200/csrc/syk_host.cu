@@ -61,16 +61,27 @@ __global__ void k_synth(void *out, int elem_bytes, long long nx, long long ny, l
 
 // Device scratch of the host entry points comes from the stream-ordered pool (kept warm between calls: a call per
 // chunk must not pay cudaMalloc/cudaFree round trips for gigabyte buffers).
-static cudaError_t dev_alloc(void **p, size_t bytes) {
-    syk_pool_keep_warm();
-    return cudaMallocAsync(p, bytes ? bytes : 16, (cudaStream_t)0);
-}
+// Everything a host call enqueues goes to the calling thread's own stream (syk_host_stream): concurrent calls from
+// several worker threads overlap their uploads, kernels and downloads.
 struct DevBuf {
     void *p = nullptr;
+    cudaStream_t s = nullptr;
     ~DevBuf() {
-        if (p) cudaFreeAsync(p, (cudaStream_t)0);
+        if (p) cudaFreeAsync(p, s);
     }
 };
+static cudaError_t dev_alloc(DevBuf &b, size_t bytes, cudaStream_t s) {
+    syk_pool_keep_warm();
+    b.s = s;
+    return cudaMallocAsync(&b.p, bytes ? bytes : 16, s);
+}
+#define SYK_H2D(dst, src, bytes, s) SYK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s))
+// device -> host, complete on return
+#define SYK_D2H(dst, src, bytes, s)                                            \
+    do {                                                                       \
+        SYK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); \
+        SYK_CUDA(cudaStreamSynchronize(s));                                    \
+    } while (0)
 
 // a dense block viewed through `strides`: nbytes = elem_bytes * prod(shape); base offset must be 0
 static int check_dense(const int64_t *shape, const int64_t *strides, int nd) {
@@ -102,10 +113,10 @@ static uint64_t pick_capacity(uint64_t hint, uint64_t nvox) {
     return c;
 }
 
-static int export_to_host(syk_table_t *t, const syk_chunk_geom_t *geom, syk_record_t **out, uint64_t *n_out) {
+static int export_to_host(syk_table_t *t, const syk_chunk_geom_t *geom, syk_record_t **out, uint64_t *n_out, cudaStream_t hs) {
     uint64_t n = 0;
     int ovf = 0;
-    int rc = syk_table_count(t, nullptr, &n, &ovf);
+    int rc = syk_table_count(t, hs, &n, &ovf);
     if (rc) return rc;
     if (ovf) {
         syk_set_error("id table overflow");
@@ -115,12 +126,12 @@ static int export_to_host(syk_table_t *t, const syk_chunk_geom_t *geom, syk_reco
     *out = nullptr;
     if (n == 0) return SYK_OK;
     DevBuf recs;
-    SYK_CUDA(dev_alloc(&recs.p, n * sizeof(syk_record_t)));
-    rc = syk_table_export(t, geom, 1, (syk_record_t *)recs.p, n, &n, nullptr);
+    SYK_CUDA(dev_alloc(recs, n * sizeof(syk_record_t), hs));
+    rc = syk_table_export(t, geom, 1, (syk_record_t *)recs.p, n, &n, hs);
     if (rc) return rc;
     *out = (syk_record_t *)malloc(n * sizeof(syk_record_t));
     if (!*out) return SYK_ENOMEM;
-    SYK_CUDA(cudaMemcpy(*out, recs.p, n * sizeof(syk_record_t), cudaMemcpyDeviceToHost));
+    SYK_D2H(*out, recs.p, n * sizeof(syk_record_t), hs);
     return SYK_OK;
 }
 
@@ -159,9 +170,10 @@ SYK_API int syk_find_object_properties_host(const void *labels_host, int elem_by
     if (nvox == 0) return SYK_OK;
     rc = check_dense(shape, strides, 3);
     if (rc) return rc;
+    cudaStream_t hs = syk_host_stream();
     DevBuf lab;
-    SYK_CUDA(dev_alloc(&lab.p, nvox * elem_bytes));
-    SYK_CUDA(cudaMemcpy(lab.p, labels_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
+    SYK_CUDA(dev_alloc(lab, nvox * elem_bytes, hs));
+    SYK_H2D(lab.p, labels_host, nvox * elem_bytes, hs);
     const int64_t origin[3] = {0, 0, 0};
     syk_chunk_geom_t geom;
     for (int a = 0; a < 3; ++a) {
@@ -171,10 +183,10 @@ SYK_API int syk_find_object_properties_host(const void *labels_host, int elem_by
     uint64_t cap = pick_capacity(capacity_hint, nvox);
     for (;;) {
         syk_table_t *t = nullptr;
-        rc = syk_table_create(&t, cap);
+        rc = syk_table_create_on(&t, cap, hs);
         if (rc) return rc;
-        rc = syk_find_object_properties(t, lab.p, elem_bytes, shape, strides, origin, 0, nullptr);
-        if (!rc) rc = export_to_host(t, &geom, records_out, n_out);
+        rc = syk_find_object_properties(t, lab.p, elem_bytes, shape, strides, origin, 0, hs);
+        if (!rc) rc = export_to_host(t, &geom, records_out, n_out, hs);
         syk_table_destroy(t);
         if (rc != SYK_EOVERFLOW || cap >= nvox * 2) return rc;
         cap *= 4;
@@ -207,13 +219,14 @@ SYK_API int syk_map_subcell_extract_props_host(const void *cell_host, const int6
         rc = check_dense(sshape, sub_strides, 4);
         if (rc) return rc;
     }
+    cudaStream_t hs = syk_host_stream();
     DevBuf cell, sub;
-    SYK_CUDA(dev_alloc(&cell.p, nvox * elem_bytes));
-    SYK_CUDA(cudaMemcpy(cell.p, cell_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
+    SYK_CUDA(dev_alloc(cell, nvox * elem_bytes, hs));
+    SYK_H2D(cell.p, cell_host, nvox * elem_bytes, hs);
     const void *subp[4] = {nullptr, nullptr, nullptr, nullptr};
     if (n_sub) {
-        SYK_CUDA(dev_alloc(&sub.p, nvox * elem_bytes * n_sub));
-        SYK_CUDA(cudaMemcpy(sub.p, subcell_host, nvox * elem_bytes * n_sub, cudaMemcpyHostToDevice));
+        SYK_CUDA(dev_alloc(sub, nvox * elem_bytes * n_sub, hs));
+        SYK_H2D(sub.p, subcell_host, nvox * elem_bytes * n_sub, hs);
         for (int c = 0; c < n_sub; ++c) subp[c] = (const char *)sub.p + (size_t)c * sub_strides[0] * elem_bytes;
     }
     const int64_t origin[3] = {0, 0, 0};
@@ -227,28 +240,28 @@ SYK_API int syk_map_subcell_extract_props_host(const void *cell_host, const int6
         syk_table_t *ct = nullptr, *st[4] = {nullptr, nullptr, nullptr, nullptr};
         syk_pairs_t *pt[4] = {nullptr, nullptr, nullptr, nullptr};
         rc = SYK_OK;
-        if (props_too) rc = syk_table_create(&ct, cap);
+        if (props_too) rc = syk_table_create_on(&ct, cap, hs);
         for (int c = 0; c < n_sub && !rc; ++c) {
-            if (props_too) rc = syk_table_create(&st[c], cap);
-            if (!rc) rc = syk_pairs_create(&pt[c], cap);
+            if (props_too) rc = syk_table_create_on(&st[c], cap, hs);
+            if (!rc) rc = syk_pairs_create_on(&pt[c], cap, hs);
         }
         if (!rc)
             rc = syk_map_subcell_extract_props(props_too ? ct : nullptr, props_too ? st : nullptr, pt, cell.p, cell_strides, subp,
-                                               sub_strides + 1, n_sub, elem_bytes, shape, origin, 0, nullptr);
-        if (!rc && props_too) rc = export_to_host(ct, &geom, cell_records_out, n_cell_out);
+                                               sub_strides + 1, n_sub, elem_bytes, shape, origin, 0, hs);
+        if (!rc && props_too) rc = export_to_host(ct, &geom, cell_records_out, n_cell_out, hs);
         for (int c = 0; c < n_sub && !rc; ++c) {
-            if (props_too) rc = export_to_host(st[c], &geom, &sub_records_out[c], &n_sub_out[c]);
+            if (props_too) rc = export_to_host(st[c], &geom, &sub_records_out[c], &n_sub_out[c], hs);
             if (rc) break;
             uint64_t np = 0;
             DevBuf pb;
             const uint64_t maxp = pt[c]->capacity;
-            SYK_CUDA(dev_alloc(&pb.p, maxp * sizeof(syk_pair_t)));
-            rc = syk_pairs_export(pt[c], (syk_pair_t *)pb.p, maxp, &np, nullptr);
+            SYK_CUDA(dev_alloc(pb, maxp * sizeof(syk_pair_t), hs));
+            rc = syk_pairs_export(pt[c], (syk_pair_t *)pb.p, maxp, &np, hs);
             if (rc) break;
             n_pairs_out[c] = np;
             if (np) {
                 pairs_out[c] = (syk_pair_t *)malloc(np * sizeof(syk_pair_t));
-                SYK_CUDA(cudaMemcpy(pairs_out[c], pb.p, np * sizeof(syk_pair_t), cudaMemcpyDeviceToHost));
+                SYK_D2H(pairs_out[c], pb.p, np * sizeof(syk_pair_t), hs);
             }
         }
         syk_table_destroy(ct);
@@ -293,23 +306,26 @@ static int cs_host_impl(const void *edges_host, int edge_bytes, const int64_t *e
     const uint64_t nvox = (uint64_t)shape[0] * shape[1] * shape[2];
     rc = check_dense(shape, strides, 3);
     if (rc) return rc;
+    cudaStream_t hs = syk_host_stream();
     DevBuf arr, edg, out;
-    SYK_CUDA(dev_alloc(&arr.p, nvox * elem_bytes));
-    SYK_CUDA(cudaMemcpy(arr.p, arr_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
+    SYK_CUDA(dev_alloc(arr, nvox * elem_bytes, hs));
+    SYK_H2D(arr.p, arr_host, nvox * elem_bytes, hs);
     if (edges_host) {
         rc = check_dense(shape, edge_strides, 3);
         if (rc) return rc;
-        SYK_CUDA(dev_alloc(&edg.p, nvox * edge_bytes));
-        SYK_CUDA(cudaMemcpy(edg.p, edges_host, nvox * edge_bytes, cudaMemcpyHostToDevice));
+        SYK_CUDA(dev_alloc(edg, nvox * edge_bytes, hs));
+        SYK_H2D(edg.p, edges_host, nvox * edge_bytes, hs);
     }
-    SYK_CUDA(dev_alloc(&out.p, nout * 8));
+    SYK_CUDA(dev_alloc(out, nout * 8, hs));
     const int64_t ost[3] = {oshape[1] * oshape[2], oshape[2], 1};
     if (edges_host)
         rc = syk_process_block_nonzero(edg.p, edge_bytes, edge_strides, arr.p, elem_bytes, strides, shape, stencil, (uint64_t *)out.p,
-                                       ost, nullptr);
+                                       ost, hs);
     else
-        rc = syk_detect_cs(arr.p, elem_bytes, shape, strides, stencil, (uint64_t *)out.p, ost, nullptr);
+        rc = syk_detect_cs(arr.p, elem_bytes, shape, strides, stencil, (uint64_t *)out.p, ost, hs);
     if (rc) return rc;
+    // the contact volume goes home while its properties are computed (second stream of the thread would be needed for a
+    // true overlap inside one call; across worker threads the copies overlap anyway)
     if (records_out) {  // properties of the contact volume while it is still on the device (cs_extraction_steps.py:439)
         const int64_t origin[3] = {0, 0, 0};
         syk_chunk_geom_t geom;
@@ -320,17 +336,17 @@ static int cs_host_impl(const void *edges_host, int edge_bytes, const int64_t *e
         uint64_t cap = pick_capacity(0, nout);
         for (;;) {
             syk_table_t *t = nullptr;
-            rc = syk_table_create(&t, cap);
+            rc = syk_table_create_on(&t, cap, hs);
             if (rc) return rc;
-            rc = syk_find_object_properties(t, out.p, 8, oshape, ost, origin, 0, nullptr);
-            if (!rc) rc = export_to_host(t, &geom, records_out, n_out);
+            rc = syk_find_object_properties(t, out.p, 8, oshape, ost, origin, 0, hs);
+            if (!rc) rc = export_to_host(t, &geom, records_out, n_out, hs);
             syk_table_destroy(t);
             if (rc != SYK_EOVERFLOW || cap >= nout * 2) break;
             cap *= 4;
         }
         if (rc) return rc;
     }
-    SYK_CUDA(cudaMemcpy(out_host, out.p, nout * 8, cudaMemcpyDeviceToHost));
+    SYK_D2H(out_host, out.p, nout * 8, hs);
     return SYK_OK;
 }
 
@@ -371,16 +387,17 @@ SYK_API int syk_extract_cs_syntype_host(const void *cs_host, int elem_bytes, con
     if ((rc = check_dense(shape, cs_strides, 3)) || (rc = check_dense(shape, syn_strides, 3)) ||
         (rc = check_dense(shape, asym_strides, 3)) || (rc = check_dense(shape, sym_strides, 3)))
         return rc;
+    cudaStream_t hs = syk_host_stream();
     DevBuf cs, syn, asym, sym, vox, cnt;
-    SYK_CUDA(dev_alloc(&cs.p, nvox * elem_bytes));
-    SYK_CUDA(dev_alloc(&syn.p, nvox));
-    SYK_CUDA(dev_alloc(&asym.p, nvox));
-    SYK_CUDA(dev_alloc(&sym.p, nvox));
-    SYK_CUDA(dev_alloc(&cnt.p, 16));
-    SYK_CUDA(cudaMemcpy(cs.p, cs_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
-    SYK_CUDA(cudaMemcpy(syn.p, syn_host, nvox, cudaMemcpyHostToDevice));
-    SYK_CUDA(cudaMemcpy(asym.p, asym_host, nvox, cudaMemcpyHostToDevice));
-    SYK_CUDA(cudaMemcpy(sym.p, sym_host, nvox, cudaMemcpyHostToDevice));
+    SYK_CUDA(dev_alloc(cs, nvox * elem_bytes, hs));
+    SYK_CUDA(dev_alloc(syn, nvox, hs));
+    SYK_CUDA(dev_alloc(asym, nvox, hs));
+    SYK_CUDA(dev_alloc(sym, nvox, hs));
+    SYK_CUDA(dev_alloc(cnt, 16, hs));
+    SYK_H2D(cs.p, cs_host, nvox * elem_bytes, hs);
+    SYK_H2D(syn.p, syn_host, nvox, hs);
+    SYK_H2D(asym.p, asym_host, nvox, hs);
+    SYK_H2D(sym.p, sym_host, nvox, hs);
     const int64_t origin[3] = {0, 0, 0};
     syk_chunk_geom_t geom;
     for (int a = 0; a < 3; ++a) {
@@ -391,25 +408,25 @@ SYK_API int syk_extract_cs_syntype_host(const void *cs_host, int elem_bytes, con
     uint64_t max_vox = nvox / 16 + 4096;
     for (;;) {
         syk_table_t *t = nullptr;
-        rc = syk_table_create(&t, cap);
+        rc = syk_table_create_on(&t, cap, hs);
         if (rc) return rc;
         if (vox.p) {
-            cudaFreeAsync(vox.p, (cudaStream_t)0);
+            cudaFreeAsync(vox.p, hs);
             vox.p = nullptr;
         }
-        SYK_CUDA(dev_alloc(&vox.p, max_vox * sizeof(syk_synvox_t)));
-        SYK_CUDA(cudaMemsetAsync(cnt.p, 0, 16, (cudaStream_t)0));
+        SYK_CUDA(dev_alloc(vox, max_vox * sizeof(syk_synvox_t), hs));
+        SYK_CUDA(cudaMemsetAsync(cnt.p, 0, 16, hs));
         rc = syk_extract_cs_syntype(t, cs.p, elem_bytes, shape, cs_strides, (const uint8_t *)syn.p, syn_strides, (const uint8_t *)asym.p,
                                     asym_strides, (const uint8_t *)sym.p, sym_strides, origin, 0, (syk_synvox_t *)vox.p, max_vox,
-                                    (uint64_t *)cnt.p, nullptr);
+                                    (uint64_t *)cnt.p, hs);
         unsigned long long nv = 0;
-        if (!rc) SYK_CUDA(cudaMemcpy(&nv, cnt.p, sizeof(nv), cudaMemcpyDeviceToHost));
+        if (!rc) SYK_D2H(&nv, cnt.p, sizeof(nv), hs);
         if (!rc && nv > max_vox) {  // voxel buffer too small: retry with the exact size
             syk_table_destroy(t);
             max_vox = nv;
             continue;
         }
-        if (!rc) rc = export_to_host(t, &geom, cs_records_out, n_cs_out);
+        if (!rc) rc = export_to_host(t, &geom, cs_records_out, n_cs_out, hs);
         syk_table_destroy(t);
         if (rc == SYK_EOVERFLOW && cap < nvox * 2) {
             cap *= 4;
@@ -420,7 +437,7 @@ SYK_API int syk_extract_cs_syntype_host(const void *cs_host, int elem_bytes, con
         if (nv) {
             *vox_out = (syk_synvox_t *)malloc(nv * sizeof(syk_synvox_t));
             if (!*vox_out) return SYK_ENOMEM;
-            SYK_CUDA(cudaMemcpy(*vox_out, vox.p, nv * sizeof(syk_synvox_t), cudaMemcpyDeviceToHost));
+            SYK_D2H(*vox_out, vox.p, nv * sizeof(syk_synvox_t), hs);
         }
         return SYK_OK;
     }
@@ -435,12 +452,13 @@ SYK_API int syk_detect_seg_boundaries_host(const void *arr_host, int elem_bytes,
     if (nvox == 0) return SYK_OK;
     rc = check_dense(shape, strides, 3);
     if (rc) return rc;
+    cudaStream_t hs = syk_host_stream();
     DevBuf arr, out;
-    SYK_CUDA(dev_alloc(&arr.p, nvox * elem_bytes));
-    SYK_CUDA(cudaMemcpy(arr.p, arr_host, nvox * elem_bytes, cudaMemcpyHostToDevice));
-    SYK_CUDA(dev_alloc(&out.p, nvox));
-    rc = syk_detect_seg_boundaries(arr.p, elem_bytes, shape, strides, (uint8_t *)out.p, nullptr);
+    SYK_CUDA(dev_alloc(arr, nvox * elem_bytes, hs));
+    SYK_H2D(arr.p, arr_host, nvox * elem_bytes, hs);
+    SYK_CUDA(dev_alloc(out, nvox, hs));
+    rc = syk_detect_seg_boundaries(arr.p, elem_bytes, shape, strides, (uint8_t *)out.p, hs);
     if (rc) return rc;
-    SYK_CUDA(cudaMemcpy(out_host, out.p, nvox, cudaMemcpyDeviceToHost));
+    SYK_D2H(out_host, out.p, nvox, hs);
     return SYK_OK;
 }

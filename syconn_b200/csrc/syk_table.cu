@@ -44,6 +44,17 @@ void syk_pool_keep_warm() {
     cudaGetLastError();
 }
 
+cudaStream_t syk_host_stream() {
+    static thread_local cudaStream_t streams[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return (cudaStream_t)0;
+    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        return (cudaStream_t)0;
+    }
+    return streams[dev];
+}
+
 SYK_API int syk_version(void) { return SYK_VERSION; }
 SYK_API const char *syk_last_error(void) { return g_err; }
 SYK_API int syk_device_count(void) {
@@ -69,35 +80,39 @@ static uint64_t round_pow2(uint64_t c) {
 }
 
 // ---- id tables ------------------------------------------------------------------------------------------------
-SYK_API int syk_table_create(syk_table_t **out, uint64_t capacity) {
+int syk_table_create_on(syk_table **out, uint64_t capacity, cudaStream_t s) {
     SYK_CHECK_ARG(out != nullptr, "out is NULL");
     int rc = syk_require_device();
     if (rc) return rc;
     syk_table *t = (syk_table *)calloc(1, sizeof(syk_table));
     if (!t) return SYK_ENOMEM;
     t->capacity = round_pow2(capacity);
+    t->stream = s;
     SYK_CUDA(cudaGetDevice(&t->device));
     syk_pool_keep_warm();
-    cudaError_t e = cudaMallocAsync((void **)&t->slots, t->capacity * sizeof(SykSlot), (cudaStream_t)0);
+    void *ctl = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&t->slots, t->capacity * sizeof(SykSlot), s);
+    if (e == cudaSuccess) e = cudaMallocAsync(&ctl, 64, s);
     if (e != cudaSuccess) {
         syk_set_error("cudaMalloc of %llu table slots failed: %s", (unsigned long long)t->capacity, cudaGetErrorString(e));
+        if (t->slots) cudaFreeAsync(t->slots, s);
         free(t);
+        cudaGetLastError();
         return SYK_ENOMEM;
     }
-    SYK_CUDA(cudaMalloc(&t->flags, 4 * sizeof(int)));
-    SYK_CUDA(cudaMalloc(&t->counter, 4 * sizeof(unsigned long long)));
-    SYK_CUDA(cudaMemsetAsync(t->slots, 0, t->capacity * sizeof(SykSlot), (cudaStream_t)0));
-    SYK_CUDA(cudaMemset(t->flags, 0, 4 * sizeof(int)));
-    SYK_CUDA(cudaMemset(t->counter, 0, 4 * sizeof(unsigned long long)));
+    t->flags = (int *)ctl;
+    t->counter = (unsigned long long *)((char *)ctl + 32);
+    SYK_CUDA(cudaMemsetAsync(t->slots, 0, t->capacity * sizeof(SykSlot), s));
+    SYK_CUDA(cudaMemsetAsync(ctl, 0, 64, s));
     *out = t;
     return SYK_OK;
 }
+SYK_API int syk_table_create(syk_table_t **out, uint64_t capacity) { return syk_table_create_on(out, capacity, (cudaStream_t)0); }
 
 SYK_API int syk_table_destroy(syk_table_t *t) {
     if (!t) return SYK_OK;
-    cudaFreeAsync(t->slots, (cudaStream_t)0);
-    cudaFree(t->flags);
-    cudaFree(t->counter);
+    cudaFreeAsync(t->slots, t->stream);
+    cudaFreeAsync(t->flags, t->stream);
     free(t);
     return SYK_OK;
 }
@@ -398,33 +413,38 @@ SYK_API int syk_pairs_bucket(const syk_pair_t *pairs_dev, uint64_t n, uint32_t n
 }
 
 // ---- pair tables ------------------------------------------------------------------------------------------------
-SYK_API int syk_pairs_create(syk_pairs_t **out, uint64_t capacity) {
+int syk_pairs_create_on(syk_pairs **out, uint64_t capacity, cudaStream_t s) {
     SYK_CHECK_ARG(out != nullptr, "out is NULL");
     int rc = syk_require_device();
     if (rc) return rc;
     syk_pairs *t = (syk_pairs *)calloc(1, sizeof(syk_pairs));
     if (!t) return SYK_ENOMEM;
     t->capacity = round_pow2(capacity);
+    t->stream = s;
     SYK_CUDA(cudaGetDevice(&t->device));
     syk_pool_keep_warm();
-    cudaError_t e = cudaMallocAsync((void **)&t->slots, t->capacity * sizeof(SykPairSlot), (cudaStream_t)0);
+    void *ctl = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&t->slots, t->capacity * sizeof(SykPairSlot), s);
+    if (e == cudaSuccess) e = cudaMallocAsync(&ctl, 64, s);
     if (e != cudaSuccess) {
         syk_set_error("cudaMalloc of %llu pair slots failed: %s", (unsigned long long)t->capacity, cudaGetErrorString(e));
+        if (t->slots) cudaFreeAsync(t->slots, s);
         free(t);
+        cudaGetLastError();
         return SYK_ENOMEM;
     }
-    SYK_CUDA(cudaMalloc(&t->flags, 4 * sizeof(int)));
-    SYK_CUDA(cudaMalloc(&t->counter, 4 * sizeof(unsigned long long)));
-    SYK_CUDA(cudaMemsetAsync(t->slots, 0, t->capacity * sizeof(SykPairSlot), (cudaStream_t)0));
-    SYK_CUDA(cudaMemset(t->flags, 0, 4 * sizeof(int)));
+    t->flags = (int *)ctl;
+    t->counter = (unsigned long long *)((char *)ctl + 32);
+    SYK_CUDA(cudaMemsetAsync(t->slots, 0, t->capacity * sizeof(SykPairSlot), s));
+    SYK_CUDA(cudaMemsetAsync(ctl, 0, 64, s));
     *out = t;
     return SYK_OK;
 }
+SYK_API int syk_pairs_create(syk_pairs_t **out, uint64_t capacity) { return syk_pairs_create_on(out, capacity, (cudaStream_t)0); }
 SYK_API int syk_pairs_destroy(syk_pairs_t *t) {
     if (!t) return SYK_OK;
-    cudaFreeAsync(t->slots, (cudaStream_t)0);
-    cudaFree(t->flags);
-    cudaFree(t->counter);
+    cudaFreeAsync(t->slots, t->stream);
+    cudaFreeAsync(t->flags, t->stream);
     free(t);
     return SYK_OK;
 }

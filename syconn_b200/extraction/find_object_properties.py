@@ -31,7 +31,8 @@ def detect_cs(arr, stencil=None, out=None, return_props=False):
     ``.astype(np.uint32)`` (cs_extraction_steps.py:385-387).  ``stencil`` overrides the config default; ``out`` may be a
     preallocated C-contiguous uint64 array of the output shape (e.g. pinned memory).  ``return_props=True`` also returns
     ``find_object_properties(contacts)`` (the next call of the reference worker, cs_extraction_steps.py:439), computed
-    while the contact volume is still on the GPU: ``(contacts, (rep_coords, bounding_box, sizes))``."""
+    while the contact volume is still on the GPU: ``(contacts, (rep_coords, bounding_box, sizes))``; ``return_props="records"``
+    returns the raw ``syk_record_t`` array instead of the three dicts."""
     arr = np.asarray(arr)
     if arr.dtype not in (np.uint32, np.uint64):
         raise ValueError(f"Buffer dtype mismatch, expected 'uint32_t' but got '{arr.dtype}'")
@@ -52,7 +53,8 @@ def detect_cs(arr, stencil=None, out=None, return_props=False):
         rec, n = C.c_void_p(), C.c_uint64()
         _lib.check(_lib.load().syk_detect_cs_props_host(arr.ctypes.data, arr.itemsize, _lib.i64(arr.shape), _lib.i64(estrides(arr)),
                                                         _lib.i32(st), out.ctypes.data, C.byref(rec), C.byref(n)))
-        return out, records_to_dicts(_lib.take_array(rec.value, n.value, _lib.RECORD_DTYPE))
+        rec = _lib.take_array(rec.value, n.value, _lib.RECORD_DTYPE)
+        return out, (rec if return_props == "records" else records_to_dicts(rec))
     _lib.check(_lib.load().syk_detect_cs_host(arr.ctypes.data, arr.itemsize, _lib.i64(arr.shape), _lib.i64(estrides(arr)),
                                               _lib.i32(st), out.ctypes.data))
     return out

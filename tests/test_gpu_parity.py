@@ -137,7 +137,8 @@ def test_map_vs_oracle_random(mods, seed, shape, nsub):
 @pytest.mark.parametrize("seed,shape,st", [(0, (40, 44, 39), (13, 13, 7)), (1, (30, 30, 30), (7, 7, 3)),
                                            (2, (21, 37, 50), (5, 5, 3)), (3, (70, 20, 19), (3, 3, 3)),
                                            (4, (24, 24, 24), (17, 17, 9)), (5, (16, 20, 33), (1, 3, 1)),
-                                           (6, (48, 40, 36), (15, 15, 9)), (7, (40, 36, 44), (9, 15, 15))])
+                                           (6, (48, 40, 36), (15, 15, 9)), (7, (40, 36, 44), (9, 15, 15)),
+                                           (8, (44, 40, 40), (13, 13, 7))])  # 16-byte rows in both orders: specialised kernels
 def test_detect_cs_vs_oracle_random(mods, seed, shape, st):
     rng = np.random.default_rng(seed)
     oracle, synth = mods["oracle"], mods["synth"]
@@ -161,6 +162,27 @@ def test_detect_cs_with_props_extension(mods):
     want = mods["oracle"].detect_cs(seg, (7, 7, 3))
     assert np.array_equal(cs, want)
     assert_props_equal(props, mods["oracle"].find_object_properties(want), "cs props")
+
+
+def test_host_calls_from_worker_threads(mods):
+    """The host entry points are issued from several threads at once (each thread owns a stream inside libsyk):
+    results must equal the serial ones."""
+    from concurrent.futures import ThreadPoolExecutor
+    fop, synth = mods["fop"], mods["synth"]
+    segs = [synth((72, 64, 56), origin=(100 * i, 7, 3), pitch=(14, 12, 8), warp_amp=3, seed=20 + i, dtype=np.uint32) for i in range(6)]
+    labs = [synth((64, 48, 40), origin=(5, 90 * i, 1), pitch=(9, 9, 6), seed=30 + i) for i in range(6)]
+    want_cs = [fop.detect_cs(s, (7, 7, 3)) for s in segs]
+    want_pr = [fop.find_object_properties(l) for l in labs]
+
+    def job(i):
+        return fop.detect_cs(segs[i], (7, 7, 3)), fop.find_object_properties(labs[i])
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        for _ in range(3):
+            got = list(pool.map(job, range(6)))
+            for i, (cs, pr) in enumerate(got):
+                assert np.array_equal(cs, want_cs[i])
+                assert_props_equal(pr, want_pr[i], f"props thread job {i}")
+    assert np.array_equal(want_cs[0], mods["oracle"].detect_cs(segs[0], (7, 7, 3)))
 
 
 def test_detect_cs_random_labels_overflow_path(mods):
