@@ -433,6 +433,10 @@ def e2e_host(args, chunks):
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (e.g. NCCL's version banner) are sent to stderr
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     a = parse()
     if a.impl == "reference":
         run_reference(a)
