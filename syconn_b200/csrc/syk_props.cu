@@ -256,17 +256,25 @@ __device__ __forceinline__ void acc_batch(const T *buf, unsigned bnd, unsigned n
         const int first = __ffs(peers) - 1;
         const int last = 31 - __clz(peers);
         Group r;
+        unsigned smin = (unsigned)s;
         if ((peers & partial_mask) == 0u) {  // every lane of the group holds one run spanning the whole batch
             r.cnt = (unsigned)R * (unsigned)__popc(peers);
             r.mnv = lv0;
             r.mxv = lv0 + R - 1;
-            r.rep = rowrep - (unsigned)(lane - first) * Tc.cw;
-        } else {  // ragged group: reduce over the peers
+        } else {  // ragged group: reduce over the peers (the group's lanes all take this branch)
+            static_assert(R <= 16, "run start / end are OR-reduced as two 16-bit one-hot fields");
             r.cnt = __reduce_add_sync(peers, (unsigned)(e - s));
-            r.mnv = lv0 + __reduce_min_sync(peers, (unsigned)s);
-            r.mxv = lv0 + __reduce_max_sync(peers, (unsigned)e) - 1u;
-            r.rep = __reduce_min_sync(peers, rowrep + (unsigned)s * Tc.cv);
+            const unsigned se = __reduce_or_sync(peers, (1u << s) | (0x8000u << e));  // bit s | bit 16 + (e - 1)
+            smin = (unsigned)__ffs(se & 0xFFFFu) - 1u;
+            r.mnv = lv0 + smin;
+            r.mxv = lv0 + (unsigned)(31 - __clz(se)) - 16u;
         }
+        // first voxel of the group in logical scan order (all lanes converged again): rep_local is a mixed-radix number,
+        // so the minimum over the group is lexicographic -- lane first when the lane axis is the slower logical axis,
+        // row first otherwise
+        const unsigned at_min = __ballot_sync(FULL, (unsigned)s == smin);
+        const int src = (Tc.cv > Tc.cw) ? __ffs(peers & at_min) - 1 : first;
+        r.rep = __shfl_sync(FULL, rowrep + (unsigned)s * Tc.cv, src);
         if (lane == first && key != 0ull) {
             r.mnu = r.mxu = lu;
             r.mnw = (unsigned)first;
@@ -351,26 +359,31 @@ struct MapArgs {
 
 // One kernel for both entry points: NCH = 1 + n_sub staged channels (n_sub == 0 => find_object_properties).
 //   R   rows per batch;  TU x TV rows per tile (TV multiple of R)
-template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS, int NBUF, bool TMA>
+//   MODE 0: labels only (find_object_properties); 1: organelle-first scan of one channel; 2: fused, run-time channel count.
+//   With MODE 0/1 the per-warp shared-memory layout is a compile-time constant (measured: -19% for MODE 0; the organelle scan
+//   is launched with MODE 2, the specialised instantiation was 7% slower).
+template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS, int NBUF, bool TMA, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : 3) k_scan(const T *__restrict__ cell, ScanGeom G, TableView cell_t, MapArgs A,
                                                      const __grid_constant__ TmapSet tm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long mbar[WARPS][2];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int nch = 1 + A.n_sub;
-    const int nstage = A.org_mode ? 1 : nch;  // channels staged by TMA / cp.async (org mode fills channel 1 on demand)
+    const int n_sub = MODE == 0 ? 0 : (MODE == 1 ? 1 : A.n_sub);
+    const bool org_mode = MODE == 1 ? true : (MODE == 0 ? false : A.org_mode != 0);
+    const int nch = 1 + n_sub;
+    const int nstage = org_mode ? 1 : nch;  // channels staged by TMA / cp.async (org mode fills channel 1 on demand)
     // per-warp layout: stage[NBUF][nch][R*32] T | WarpTab<WS> cell | n_sub x WarpTab<WSS> | n_sub x WarpPairTab<PS>
     const size_t stage_bytes = (size_t)NBUF * nch * R * 32 * sizeof(T);
-    const size_t per_warp = (stage_bytes + sizeof(WarpTab<WS>) + (size_t)A.n_sub * (sizeof(WarpTab<WSS>) + sizeof(WarpPairTab<PS>)) + 127) &
+    const size_t per_warp = (stage_bytes + sizeof(WarpTab<WS>) + (size_t)n_sub * (sizeof(WarpTab<WSS>) + sizeof(WarpPairTab<PS>)) + 127) &
                             ~(size_t)127;
     unsigned char *mine = smem_raw + per_warp * wib;
     T *stage = reinterpret_cast<T *>(mine);
     WarpTab<WS> *ctab = reinterpret_cast<WarpTab<WS> *>(mine + stage_bytes);
     WarpTab<WSS> *stab = reinterpret_cast<WarpTab<WSS> *>(ctab + 1);
-    WarpPairTab<PS> *ptab = reinterpret_cast<WarpPairTab<PS> *>(stab + A.n_sub);
+    WarpPairTab<PS> *ptab = reinterpret_cast<WarpPairTab<PS> *>(stab + n_sub);
     for (int i = lane; i < WS; i += 32) ctab->keys[i] = 0ull;
-    for (int c = 0; c < A.n_sub; ++c) {
+    for (int c = 0; c < n_sub; ++c) {
         for (int i = lane; i < WSS; i += 32) stab[c].keys[i] = 0ull;
         for (int i = lane; i < PS; i += 32) {
             ptab[c].sub[i] = 0ull;
@@ -467,7 +480,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : 3) k
                 const unsigned bnd = run_starts<T, R>(cb, lane, nzs);
                 acc_batch<T, R, WS>(cb, bnd, nzs, *ctab, cell_t, G, Tc, lu, lv0, lane);
             }
-            if (A.org_mode) {
+            if (org_mode) {
                 // staged channel 0 = organelle (props done above as the "cell" channel); overlap with the real cell
                 // volume, fetched only where the organelle is non-zero
                 if (!A.do_cell_props) run_starts<T, R>(cb, lane, nzs);
@@ -485,7 +498,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : 3) k
                     acc_pairs<T, R, PS>(cb, cbuf, ptab[0], A.pair_t[0], lane);
                 }
             } else {
-                for (int c = 0; c < A.n_sub; ++c) {
+                for (int c = 0; c < n_sub; ++c) {
                     const T *sbuf = cb + (size_t)(1 + c) * R * 32;
                     unsigned snz;
                     const unsigned bnd = run_starts<T, R>(sbuf, lane, snz);
@@ -505,7 +518,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : 3) k
             }
         }
         if (A.do_cell_props) wtab_flush<WS>(*ctab, cell_t, G, Tc, lane);
-        for (int c = 0; c < A.n_sub; ++c) {
+        for (int c = 0; c < n_sub; ++c) {
             if (A.do_sub_props) wtab_flush<WSS>(stab[c], A.sub_t[c], G, Tc, lane);
             ptab_flush<PS>(ptab[c], A.pair_t[c], lane);  // per tile: a full private table would degrade every probe
         }
@@ -598,13 +611,13 @@ static bool make_tmap(CUtensorMap *m, const void *base, int elem_bytes, const lo
     return r == CUDA_SUCCESS;
 }
 
-template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS, int NBUF, bool TMA>
+template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS, int NBUF, bool TMA, int MODE>
 static int launch_cfg(const void *cell, const ScanGeom &G, const TableView &cell_t, const MapArgs &A, const TmapSet &tm, cudaStream_t s) {
     const int nch = 1 + A.n_sub;
     const size_t per_warp = ((size_t)NBUF * nch * R * 32 * sizeof(T) + sizeof(WarpTab<WS>) +
                              (size_t)A.n_sub * (sizeof(WarpTab<WSS>) + sizeof(WarpPairTab<PS>)) + 127) & ~(size_t)127;
     const size_t smem = per_warp * WARPS;
-    auto kern = k_scan<T, R, TU, TV, WARPS, WS, WSS, PS, NBUF, TMA>;
+    auto kern = k_scan<T, R, TU, TV, WARPS, WS, WSS, PS, NBUF, TMA, MODE>;
     SYK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -620,7 +633,7 @@ static int launch_cfg(const void *cell, const ScanGeom &G, const TableView &cell
     return SYK_OK;
 }
 
-template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS>
+template <typename T, int MODE, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS>
 static int launch_scan(const void *cell, const ScanGeom &G, const TableView &cell_t, const MapArgs &A, cudaStream_t s) {
     TmapSet tm;
     memset(&tm, 0, sizeof(tm));
@@ -631,8 +644,8 @@ static int launch_scan(const void *cell, const ScanGeom &G, const TableView &cel
 #ifndef SYK_TMA_NBUF
 #define SYK_TMA_NBUF 1
 #endif
-    if (tma) return launch_cfg<T, R, TU, TV, WARPS, WS, WSS, PS, SYK_TMA_NBUF, true>(cell, G, cell_t, A, tm, s);
-    return launch_cfg<T, R, TU, TV, WARPS, WS, WSS, PS, 2, false>(cell, G, cell_t, A, tm, s);
+    if (tma) return launch_cfg<T, R, TU, TV, WARPS, WS, WSS, PS, SYK_TMA_NBUF, true, MODE>(cell, G, cell_t, A, tm, s);
+    return launch_cfg<T, R, TU, TV, WARPS, WS, WSS, PS, 2, false, MODE>(cell, G, cell_t, A, tm, s);
 }
 
 }  // namespace
@@ -666,8 +679,8 @@ SYK_API int syk_find_object_properties(syk_table_t *t, const void *labels_dev, i
     MapArgs A;
     memset(&A, 0, sizeof(A));
     A.do_cell_props = 1;
-    if (elem_bytes == 8) return launch_scan<unsigned long long, PROPS_CFG>(labels_dev, G, view_of(t), A, (cudaStream_t)stream);
-    return launch_scan<unsigned int, PROPS_CFG>(labels_dev, G, view_of(t), A, (cudaStream_t)stream);
+    if (elem_bytes == 8) return launch_scan<unsigned long long, 0, PROPS_CFG>(labels_dev, G, view_of(t), A, (cudaStream_t)stream);
+    return launch_scan<unsigned int, 0, PROPS_CFG>(labels_dev, G, view_of(t), A, (cudaStream_t)stream);
 }
 
 SYK_API int syk_map_subcell_extract_props(syk_table_t *cell_t, syk_table_t *const *sub_t, syk_pairs_t *const *pair_t,
@@ -706,8 +719,8 @@ SYK_API int syk_map_subcell_extract_props(syk_table_t *cell_t, syk_table_t *cons
             A.sub[0] = cell_dev;
             A.pair_t[0] = view_of(pair_t[c]);
             const TableView tv = view_of(sub_t ? sub_t[c] : nullptr);
-            rc = elem_bytes == 8 ? launch_scan<unsigned long long, ORG_CFG>(subcell_dev[c], G, tv, A, (cudaStream_t)stream)
-                                 : launch_scan<unsigned int, ORG_CFG>(subcell_dev[c], G, tv, A, (cudaStream_t)stream);
+            rc = elem_bytes == 8 ? launch_scan<unsigned long long, 2, ORG_CFG>(subcell_dev[c], G, tv, A, (cudaStream_t)stream)
+                                 : launch_scan<unsigned int, 2, ORG_CFG>(subcell_dev[c], G, tv, A, (cudaStream_t)stream);
             if (rc) return rc;
         }
         return SYK_OK;
@@ -725,6 +738,6 @@ SYK_API int syk_map_subcell_extract_props(syk_table_t *cell_t, syk_table_t *cons
         A.pair_t[c] = view_of(pair_t[c]);
         if (sub_t) A.sub_t[c] = view_of(sub_t[c]);
     }
-    if (elem_bytes == 8) return launch_scan<unsigned long long, MAP_CFG>(cell_dev, G, view_of(cell_t), A, (cudaStream_t)stream);
-    return launch_scan<unsigned int, MAP_CFG>(cell_dev, G, view_of(cell_t), A, (cudaStream_t)stream);
+    if (elem_bytes == 8) return launch_scan<unsigned long long, 2, MAP_CFG>(cell_dev, G, view_of(cell_t), A, (cudaStream_t)stream);
+    return launch_scan<unsigned int, 2, MAP_CFG>(cell_dev, G, view_of(cell_t), A, (cudaStream_t)stream);
 }
