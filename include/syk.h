@@ -162,6 +162,21 @@ int syk_extract_cs_syntype(syk_table_t *cs_t, const void *cs_dev, int elem_bytes
                            const int64_t sym_strides[3], const int64_t origin[3], uint32_t chunk_seq, syk_synvox_t *vox_dev,
                            uint64_t max_vox, uint64_t *counter_dev, void *stream);
 
+/* detect_contact_partners(seg_arr, edge_arr, offset) -- syconn/extraction/find_object_properties.py:371-421, the
+ * numba twin of process_block_nonzero behind detect_cs_64bit (:347-368).  Same window histogram; ties go to the id met
+ * first in the x, y, z scan of the window (numba typed.Dict keeps insertion order); out = (centre << 32) | partner of
+ * uint32 labels, 0 = no partner.  edges_dev == NULL: boundary mask (detect_seg_boundaries) computed on the fly. */
+int syk_detect_contact_partners(const void *edges_dev, int edge_bytes, const int64_t edge_strides[3], const void *arr_dev,
+                                const int64_t arr_strides[3], const int64_t shape[3], const int32_t stencil[3],
+                                uint64_t *out_dev, const int64_t out_strides[3], void *stream);
+/* (centre << 32) | partner  ->  out[i][0..1] = [min, max] of the ids (ids_dev[label - 1], NULL = labels are the ids):
+ * the XYZC layout of detect_cs_64bit (find_object_properties.py:418-420) */
+int syk_cs64_unpack(const uint64_t *packed_dev, uint64_t n, const uint64_t *ids_dev, uint64_t *out_dev, void *stream);
+/* dense uint32 labels for a block of 64-bit ids (support of the 64-bit variants): labels_out[i] in 1..n_ids (0 for id
+ * 0), ids_out[label - 1] = id.  `t` must be empty.  SYK_EOVERFLOW when the table or ids_out is too small. */
+int syk_dense_relabel(syk_table_t *t, const void *vol_dev, int elem_bytes, uint64_t n, uint32_t *labels_out_dev,
+                      uint64_t *ids_out_dev, uint64_t max_ids, uint64_t *n_ids_out_host, void *stream);
+
 /* ---- synthetic label volumes (bench/test inputs; bit-identical to syconn_b200/synth.py) ------------------ */
 /* kind 0: cell supervoxels (ids < 2^32, ~3% background); kind 1..: organelle channel (sparse 64-bit ids) */
 int syk_synth_labels(void *out_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
@@ -194,6 +209,16 @@ int syk_extract_cs_syntype_host(const void *cs_host, int elem_bytes, const int64
                                 syk_record_t **cs_records_out, uint64_t *n_cs_out, syk_synvox_t **vox_out, uint64_t *n_vox_out);
 int syk_detect_seg_boundaries_host(const void *arr_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
                                    uint8_t *out_host);
+/* detect_cs_64bit(arr) / detect_contact_partners(seg, edges, symmetric offset) -- find_object_properties.py:347-421.
+ * out_host: C-contiguous uint64 [shape - stencil + 1][2] = sorted partner ids (0, 0 where there is no contact).
+ * edges_host == NULL: detect_seg_boundaries(arr) is used (detect_cs_64bit). */
+int syk_detect_contact_partners_host(const void *edges_host, int edge_bytes, const int64_t edge_strides[3], const void *arr_host,
+                                     int elem_bytes, const int64_t strides[3], const int64_t shape[3], const int32_t stencil[3],
+                                     uint64_t *out_host);
+/* find_object_properties_cs_64bit(cs_seg) -- find_object_properties.py:197-269: properties per partner PAIR of an XYZC
+ * contact volume (C = 2).  records_out[i].id is internal; partners_out[2 i .. 2 i + 1] are the pair's ids. */
+int syk_find_object_properties_cs_64bit_host(const uint64_t *cs_host, const int64_t shape[3], const int64_t strides[4],
+                                             syk_record_t **records_out, uint64_t **partners_out, uint64_t *n_out);
 void syk_free(void *p);
 
 #ifdef __cplusplus

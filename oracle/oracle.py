@@ -220,6 +220,60 @@ def detect_cs(arr, stencil=CS_FILTERSIZE):
     return process_block_nonzero(edges, arr, stencil)
 
 
+def detect_contact_partners(seg_arr, edge_arr, offset):
+    """syconn/extraction/find_object_properties.py:371-421 (numba), restated with NumPy per flagged voxel: histogram of
+    the window without 0 and the centre id; the winner is the id with the largest count, ties going to the id met first
+    in the x, y, z scan of the window (the reference iterates a numba typed.Dict, which keeps insertion order, and
+    only replaces the candidate on a strictly larger count, :408-413).  Small volumes only (pure Python loop)."""
+    seg = np.asarray(seg_arr)
+    edge = np.asarray(edge_arr)
+    off = np.asarray(offset)
+    nx, ny, nz = seg.shape[:3]
+    out = np.zeros((nx + off[0, 0] - off[0, 1], ny + off[1, 0] - off[1, 1], nz + off[2, 0] - off[2, 1], 2), np.uint64)
+    for xx in range(-off[0, 0], nx - off[0, 1]):
+        for yy in range(-off[1, 0], ny - off[1, 1]):
+            for zz in range(-off[2, 0], nz - off[2, 1]):
+                if edge[xx, yy, zz] == 0:
+                    continue
+                c = seg[xx, yy, zz]
+                w = seg[xx + off[0, 0]:xx + off[0, 1] + 1, yy + off[1, 0]:yy + off[1, 1] + 1,
+                        zz + off[2, 0]:zz + off[2, 1] + 1].reshape(-1)
+                w = w[(w != 0) & (w != c)]
+                if w.size == 0:
+                    continue
+                ids, first, cnt = np.unique(w, return_index=True, return_counts=True)
+                cand = np.flatnonzero(cnt == cnt.max())
+                m = ids[cand[np.argmin(first[cand])]]
+                out[xx + off[0, 0], yy + off[1, 0], zz + off[2, 0]] = (m, c) if c > m else (c, m)
+    return out
+
+
+def detect_cs_64bit(arr, stencil=CS_FILTERSIZE):
+    """syconn/extraction/find_object_properties.py:347-368."""
+    o = np.asarray(stencil) // 2
+    return detect_contact_partners(arr, detect_seg_boundaries(arr), np.array([(-o[0], o[0]), (-o[1], o[1]), (-o[2], o[2])]))
+
+
+def find_object_properties_cs_64bit(cs_seg):
+    """syconn/extraction/find_object_properties.py:197-269: nested dicts d[id0][id1] of rep coord (first voxel in x, y, z
+    order), bounding box [[min], [max + 1]] and size for every pair with id0 != 0."""
+    cs = np.asarray(cs_seg)
+    rep, bb, sz = {}, {}, {}
+    xs, ys, zs = np.nonzero(cs[..., 0])
+    for x, y, z in zip(xs.tolist(), ys.tolist(), zs.tolist()):  # np.nonzero is in C (x, y, z) order
+        k0, k1 = int(cs[x, y, z, 0]), int(cs[x, y, z, 1])
+        if k1 not in sz.setdefault(k0, {}):
+            sz[k0][k1] = 1
+            rep.setdefault(k0, {})[k1] = np.array([x, y, z], np.int64)
+            bb.setdefault(k0, {})[k1] = np.array([(x, y, z), (x + 1, y + 1, z + 1)], np.int64)
+        else:
+            sz[k0][k1] += 1
+            b = bb[k0][k1]
+            b[0] = np.minimum(b[0], (x, y, z))
+            b[1] = np.maximum(b[1], (x + 1, y + 1, z + 1))
+    return rep, bb, sz
+
+
 def extract_cs_syntype(cs_seg, syn_mask, asym_mask, sym_mask, offset):
     """syconn/extraction/block_processing_C.pyx:78-158 ("next" row f1) ->
     ([rc, bb, size], [rc_syn, bb_syn, size_syn], cs_asym, cs_sym, voxels_syn)."""

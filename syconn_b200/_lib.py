@@ -31,6 +31,8 @@ EXPORTS = [
     "syk_process_block_nonzero", "syk_detect_cs", "syk_extract_cs_syntype", "syk_synth_labels",
     "syk_find_object_properties_host", "syk_map_subcell_extract_props_host", "syk_detect_cs_host", "syk_detect_cs_props_host",
     "syk_process_block_nonzero_host", "syk_extract_cs_syntype_host", "syk_detect_seg_boundaries_host", "syk_free",
+    "syk_detect_contact_partners", "syk_cs64_unpack", "syk_dense_relabel",
+    "syk_detect_contact_partners_host", "syk_find_object_properties_cs_64bit_host",
 ]
 
 
@@ -93,6 +95,11 @@ def load():
     L.syk_detect_cs_props_host.argtypes = [vp, ci, i64p, i64p, i32p, vp, C.POINTER(vp), u64p]
     L.syk_process_block_nonzero_host.argtypes = [vp, ci, i64p, vp, ci, i64p, i64p, i32p, vp]
     L.syk_detect_seg_boundaries_host.argtypes = [vp, ci, i64p, i64p, vp]
+    L.syk_detect_contact_partners.argtypes = [vp, ci, i64p, vp, i64p, i64p, i32p, vp, i64p, vp]
+    L.syk_cs64_unpack.argtypes = [vp, u64, vp, vp, vp]
+    L.syk_dense_relabel.argtypes = [vp, vp, ci, u64, vp, vp, u64, u64p, vp]
+    L.syk_detect_contact_partners_host.argtypes = [vp, ci, i64p, vp, ci, i64p, i64p, i32p, vp]
+    L.syk_find_object_properties_cs_64bit_host.argtypes = [vp, i64p, i64p, C.POINTER(vp), C.POINTER(vp), u64p]
     L.syk_free.argtypes = [vp]
     L.syk_free.restype = None
     for name in EXPORTS:

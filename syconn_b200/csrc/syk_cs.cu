@@ -43,6 +43,11 @@ struct CsGeom {
     const unsigned *seg_count;
     long long segs[3];  // segment grid of the fast path
     int seg_tiles[3];   // tiles per segment along u, v, w
+    // first-seen mode (detect_contact_partners, find_object_properties.py:371-421): ties of the arg-max go to the id met
+    // first when the window is scanned in LOGICAL x, y, z order, and the output is (centre << 32) | partner, unordered
+    int first_seen;
+    int la[3];          // logical axis of internal axis u, v, w
+    int lsten[3];       // stencil along the logical axes
 };
 
 __device__ __forceinline__ unsigned ld_id(const void *base, int elem_bytes, long long idx) {
@@ -60,10 +65,12 @@ __global__ void __launch_bounds__(CS_THREADS) k_detect_cs(const void *__restrict
     unsigned *tile = reinterpret_cast<unsigned *>(smem_raw);                       // hd[0]*hd[1]*hd[2]
     const int tile_n = G.hd[0] * G.hd[1] * G.hd[2];
     unsigned short *offs = reinterpret_cast<unsigned short *>(tile + tile_n);       // total (padded to x2)
-    unsigned short *elist = offs + ((G.total + 1) & ~1);                            // OT
+    unsigned short *lrank = offs + ((G.total + 1) & ~1);                            // total (padded), first-seen mode only
+    unsigned short *elist = lrank + (G.first_seen ? ((G.total + 1) & ~1) : 0);      // OT
     unsigned short *olist = elist + OT;                                             // OT (overflow voxels)
     unsigned *hkeys = reinterpret_cast<unsigned *>(olist + OT);                     // hslots
     unsigned *hcnt = hkeys + G.hslots;                                              // hslots
+    unsigned *hfirst = hcnt + G.hslots;                                             // hslots, first-seen mode only
     __shared__ int n_edge, n_over;
     __shared__ unsigned long long best_sh;
 
@@ -75,10 +82,18 @@ __global__ void __launch_bounds__(CS_THREADS) k_detect_cs(const void *__restrict
         const int j = r % G.sten[1];
         const int ii = r / G.sten[1];
         offs[i] = (unsigned short)((ii * G.hd[1] + j) * G.hd[2] + k);
+        if (G.first_seen) {  // rank of the window voxel in the reference's x, y, z loop nest
+            int l[3];
+            l[G.la[0]] = ii;
+            l[G.la[1]] = j;
+            l[G.la[2]] = k;
+            lrank[i] = (unsigned short)((l[0] * G.lsten[1] + l[1]) * G.lsten[2] + l[2]);
+        }
     }
     for (int i = tid; i < G.hslots; i += CS_THREADS) {
         hkeys[i] = 0u;
         hcnt[i] = 0u;
+        if (G.first_seen) hfirst[i] = 0xFFFFFFFFu;
     }
 
     const int tps = G.seg_tiles[0] * G.seg_tiles[1] * G.seg_tiles[2];
@@ -171,7 +186,7 @@ __global__ void __launch_bounds__(CS_THREADS) k_detect_cs(const void *__restrict
             // window origin inside the smem tile
             const int wbase = ((lu + G.hlo[0] - G.off[0]) * G.hd[1] + (lv + G.hlo[1] - G.off[1])) * G.hd[2] + (lw + G.hlo[2] - G.off[2]);
             const unsigned center = tile[((lu + G.hlo[0]) * G.hd[1] + (lv + G.hlo[1])) * G.hd[2] + (lw + G.hlo[2])];
-            unsigned my_key = 0u, my_cnt = 0u;
+            unsigned my_key = 0u, my_cnt = 0u, my_first = 0xFFFFu;
             int nheld = 0;
             bool overflow = false;
             for (int base = 0; base < G.total && !overflow; base += 32) {
@@ -183,19 +198,26 @@ __global__ void __launch_bounds__(CS_THREADS) k_detect_cs(const void *__restrict
                 const unsigned peers = __match_any_sync(FULL, id);
                 const bool leader = (id != 0u) && (lane == __ffs(peers) - 1);
                 const unsigned n = (unsigned)__popc(peers);
+                unsigned rk = 0xFFFFu;  // first-seen mode: smallest logical rank of this id in the block of 32
+                if (G.first_seen) rk = __reduce_min_sync(peers, idx < G.total ? (unsigned)lrank[idx] : 0xFFFFu);
                 unsigned todo = __ballot_sync(FULL, leader);
                 while (todo) {
                     const int src = __ffs(todo) - 1;
                     todo &= todo - 1u;
                     const unsigned kv = __shfl_sync(FULL, id, src);
                     const unsigned kn = __shfl_sync(FULL, n, src);
+                    const unsigned kr = __shfl_sync(FULL, rk, src);
                     const unsigned hit = __ballot_sync(FULL, lane < nheld && my_key == kv);
                     if (hit) {
-                        if (lane == __ffs(hit) - 1) my_cnt += kn;
+                        if (lane == __ffs(hit) - 1) {
+                            my_cnt += kn;
+                            my_first = min(my_first, kr);
+                        }
                     } else if (nheld < 32) {
                         if (lane == nheld) {
                             my_key = kv;
                             my_cnt = kn;
+                            my_first = kr;
                         }
                         ++nheld;
                     } else {
@@ -208,17 +230,27 @@ __global__ void __launch_bounds__(CS_THREADS) k_detect_cs(const void *__restrict
                 if (lane == 0) olist[atomicAdd(&n_over, 1)] = (unsigned short)i;
                 continue;
             }
-            // arg-max: larger count wins, ties -> smaller id
-            unsigned long long best = (lane < nheld) ? (((unsigned long long)my_cnt << 32) | (unsigned long long)(~my_key)) : 0ull;
+            // arg-max: larger count wins, ties -> smaller id (first-seen mode: -> smaller logical rank; window <= 16384
+            // voxels, so count takes 15 bits and the rank 14)
+            unsigned long long best = 0ull;
+            if (lane < nheld)
+                best = G.first_seen ? (((unsigned long long)my_cnt << 46) | ((unsigned long long)(0x3FFFu - my_first) << 32) | my_key)
+                                    : (((unsigned long long)my_cnt << 32) | (unsigned long long)(~my_key));
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
                 const unsigned long long other = __shfl_xor_sync(FULL, best, o);
                 best = other > best ? other : best;
             }
             if (lane == 0) {
-                const unsigned bc = (unsigned)(best >> 32);
-                const unsigned bk = ~(unsigned)(best & 0xffffffffull);
-                out[(o0[0] + lu) * G.ost[0] + (o0[1] + lv) * G.ost[1] + (o0[2] + lw) * G.ost[2]] = pack_result(center, bk, bc);
+                unsigned long long res;
+                if (G.first_seen) {
+                    res = best ? (((unsigned long long)center << 32) | (best & 0xffffffffull)) : 0ull;
+                } else {
+                    const unsigned bc = (unsigned)(best >> 32);
+                    const unsigned bk = ~(unsigned)(best & 0xffffffffull);
+                    res = pack_result(center, bk, bc);
+                }
+                out[(o0[0] + lu) * G.ost[0] + (o0[1] + lv) * G.ost[1] + (o0[2] + lw) * G.ost[2]] = res;
             }
         }
         __syncthreads();
@@ -243,6 +275,7 @@ __global__ void __launch_bounds__(CS_THREADS) k_detect_cs(const void *__restrict
                     const unsigned prev = atomicCAS(&hkeys[h], 0u, id);
                     if (prev == 0u || prev == id) {
                         atomicAdd(&hcnt[h], 1u);
+                        if (G.first_seen) atomicMin(&hfirst[h], (unsigned)lrank[idx]);
                         break;
                     }
                     h = (h + 1u) & hm;
@@ -253,19 +286,28 @@ __global__ void __launch_bounds__(CS_THREADS) k_detect_cs(const void *__restrict
             for (int h = tid; h < G.hslots; h += CS_THREADS) {
                 const unsigned k = hkeys[h];
                 if (k != 0u) {
-                    const unsigned long long cand = ((unsigned long long)hcnt[h] << 32) | (unsigned long long)(~k);
+                    const unsigned long long cand =
+                        G.first_seen ? (((unsigned long long)hcnt[h] << 46) | ((unsigned long long)(0x3FFFu - hfirst[h]) << 32) | k)
+                                     : (((unsigned long long)hcnt[h] << 32) | (unsigned long long)(~k));
                     best = cand > best ? cand : best;
                     hkeys[h] = 0u;
                     hcnt[h] = 0u;
+                    if (G.first_seen) hfirst[h] = 0xFFFFFFFFu;
                 }
             }
             if (best) atomicMax(&best_sh, best);
             __syncthreads();
             if (tid == 0) {
                 const unsigned long long b = best_sh;
-                const unsigned bc = (unsigned)(b >> 32);
-                const unsigned bk = ~(unsigned)(b & 0xffffffffull);
-                out[(o0[0] + lu) * G.ost[0] + (o0[1] + lv) * G.ost[1] + (o0[2] + lw) * G.ost[2]] = pack_result(center, bk, bc);
+                unsigned long long res;
+                if (G.first_seen) {
+                    res = b ? (((unsigned long long)center << 32) | (b & 0xffffffffull)) : 0ull;
+                } else {
+                    const unsigned bc = (unsigned)(b >> 32);
+                    const unsigned bk = ~(unsigned)(b & 0xffffffffull);
+                    res = pack_result(center, bk, bc);
+                }
+                out[(o0[0] + lu) * G.ost[0] + (o0[1] + lv) * G.ost[1] + (o0[2] + lw) * G.ost[2]] = res;
             }
             __syncthreads();
         }
@@ -333,7 +375,10 @@ static void cs_plan(const int64_t shape[3], const int64_t strides[3], const int3
         G.on[a] = shape[l] - stencil[l] + 1;
         G.hlo[a] = G.off[a] > 1 ? G.off[a] : 1;
         G.total *= stencil[l];
+        G.la[a] = l;
+        G.lsten[a] = stencil[a];
     }
+    G.first_seen = 0;
     const int od[3] = {OU, OV, OW};
     for (int a = 0; a < 3; ++a) {
         G.hd[a] = od[a] + 2 * G.hlo[a];
@@ -386,7 +431,7 @@ static bool fast_plan(const CsGeom &C, csfast::FastGeom &F) {
 
 static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_strides, const void *arr, int elem_bytes,
                      const int64_t strides[3], const int64_t shape[3], const int32_t stencil[3], uint64_t *out,
-                     const int64_t out_strides[3], cudaStream_t s) {
+                     const int64_t out_strides[3], cudaStream_t s, int first_seen = 0) {
     int rc = syk_require_device();
     if (rc) return rc;
     SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
@@ -403,7 +448,9 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
     cs_plan(shape, strides, stencil, edge_strides, out_strides, elem_bytes, edge_bytes, G);
     const size_t tile_n = (size_t)G.hd[0] * G.hd[1] * G.hd[2];
     SYK_CHECK_ARG(tile_n < 65536, "stencil too large for the shared-memory tile");
-    const size_t smem = tile_n * 4 + (size_t)((G.total + 1) & ~1) * 2 + (size_t)OT * 2 * 2 + (size_t)G.hslots * 8;
+    G.first_seen = first_seen;
+    const size_t smem = tile_n * 4 + (size_t)((G.total + 1) & ~1) * 2 * (first_seen ? 2 : 1) + (size_t)OT * 2 * 2 +
+                        (size_t)G.hslots * (first_seen ? 12 : 8);
     SYK_CHECK_ARG(smem <= 220 * 1024, "stencil too large for shared memory");
     SYK_CUDA(cudaFuncSetAttribute(k_detect_cs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
@@ -415,7 +462,7 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
     long long grid = (long long)sms * bps;
     if (grid > G.ntiles) grid = G.ntiles;
     csfast::FastGeom F;
-    if (edges == nullptr && !getenv("SYK_CS_GENERIC") && fast_plan(G, F)) {
+    if (edges == nullptr && !first_seen && !getenv("SYK_CS_GENERIC") && fast_plan(G, F)) {
         using namespace csfast;
         // tier 1 (<= 24 ids near the plane, many CTAs/SM) -> tier 2 (<= 64 ids) on the listed segments -> generic kernel
         unsigned *hard = nullptr;  // [count1, count2, list1[nsegs], list2[nsegs]]
@@ -591,4 +638,49 @@ SYK_API int syk_process_block_nonzero(const void *edges_dev, int edge_bytes, con
 SYK_API int syk_detect_cs(const void *arr_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
                           const int32_t stencil[3], uint64_t *out_dev, const int64_t out_strides[3], void *stream) {
     return cs_launch(nullptr, 0, nullptr, arr_dev, elem_bytes, strides, shape, stencil, out_dev, out_strides, (cudaStream_t)stream);
+}
+
+// detect_contact_partners (find_object_properties.py:371-421), the numba 64-bit twin of process_block_nonzero: same
+// window histogram, but ties go to the id met first in the x, y, z window scan and the result is the unordered
+// pair (centre << 32) | partner of uint32 labels (0 = no partner).  edges_dev == NULL: boundary mask computed on the fly.
+SYK_API int syk_detect_contact_partners(const void *edges_dev, int edge_bytes, const int64_t edge_strides[3], const void *arr_dev,
+                                        const int64_t arr_strides[3], const int64_t shape[3], const int32_t stencil[3],
+                                        uint64_t *out_dev, const int64_t out_strides[3], void *stream) {
+    if (edges_dev) SYK_CHECK_ARG(edge_bytes == 1 || edge_bytes == 4, "edge_bytes must be 1 or 4");
+    return cs_launch(edges_dev, edge_bytes, edge_strides, arr_dev, 4, arr_strides, shape, stencil, out_dev, out_strides,
+                     (cudaStream_t)stream, 1);
+}
+
+// (centre << 32) | partner of dense labels -> [min, max] of the original ids (ids_dev[label - 1]; NULL = identity)
+__global__ void k_cs64_unpack(const unsigned long long *__restrict__ packed, unsigned long long n,
+                              const unsigned long long *__restrict__ ids, unsigned long long *__restrict__ out) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long p = packed[i];
+        unsigned long long a = 0ull, b = 0ull;
+        if (p != 0ull) {
+            const unsigned lc = (unsigned)(p >> 32), lp = (unsigned)p;
+            a = lc ? (ids ? ids[lc - 1u] : lc) : 0ull;
+            b = lp ? (ids ? ids[lp - 1u] : lp) : 0ull;
+            if (a > b) {
+                const unsigned long long t = a;
+                a = b;
+                b = t;
+            }
+        }
+        out[2 * i] = a;
+        out[2 * i + 1] = b;
+    }
+}
+SYK_API int syk_cs64_unpack(const uint64_t *packed_dev, uint64_t n, const uint64_t *ids_dev, uint64_t *out_dev, void *stream) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    if (n == 0) return SYK_OK;
+    SYK_CHECK_ARG(packed_dev && out_dev, "NULL buffer");
+    unsigned long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_cs64_unpack<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned long long *)packed_dev, n,
+                                                                     (const unsigned long long *)ids_dev, (unsigned long long *)out_dev);
+    SYK_CUDA(cudaGetLastError());
+    return SYK_OK;
 }

@@ -135,6 +135,41 @@ static int export_to_host(syk_table_t *t, const syk_chunk_geom_t *geom, syk_reco
     return SYK_OK;
 }
 
+// (label0 << 32) | label1 per voxel of a dense [X, Y, Z, 2] label block (0 where label0 == 0), written in C order
+__global__ void k_pack_pairs(const unsigned *__restrict__ labels, long long nx, long long ny, long long nz, long long sx, long long sy,
+                             long long sz, long long sc, unsigned long long *__restrict__ out) {
+    const long long total = nx * ny * nz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long z = i % nz;
+        const long long r = i / nz;
+        const long long y = r % ny;
+        const long long x = r / ny;
+        const long long a = x * sx + y * sy + z * sz;
+        const unsigned l0 = labels[a], l1 = labels[a + sc];
+        out[i] = l0 ? (((unsigned long long)l0 << 32) | (unsigned long long)l1) : 0ull;
+    }
+}
+
+// dense uint32 labels of a device block of n ids (retry with a larger table on overflow); ids.p[label - 1] = id
+static int relabel_block(const void *vol_dev, int elem_bytes, uint64_t n, DevBuf &labels, DevBuf &ids, uint64_t *n_ids, cudaStream_t hs) {
+    SYK_CUDA(dev_alloc(labels, n * sizeof(uint32_t), hs));
+    uint64_t cap = n / 32 < (1u << 16) ? (1u << 16) : n / 32;
+    for (;;) {
+        syk_table_t *t = nullptr;
+        int rc = syk_table_create_on(&t, cap, hs);
+        if (rc) return rc;
+        if (ids.p) {
+            cudaFreeAsync(ids.p, hs);
+            ids.p = nullptr;
+        }
+        SYK_CUDA(dev_alloc(ids, t->capacity * sizeof(uint64_t), hs));
+        rc = syk_dense_relabel(t, vol_dev, elem_bytes, n, (uint32_t *)labels.p, (uint64_t *)ids.p, t->capacity, n_ids, hs);
+        syk_table_destroy(t);
+        if (rc != SYK_EOVERFLOW || cap >= n * 2) return rc;
+        cap *= 4;
+    }
+}
+
 }  // namespace
 
 SYK_API int syk_synth_labels(void *out_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
@@ -460,5 +495,123 @@ SYK_API int syk_detect_seg_boundaries_host(const void *arr_host, int elem_bytes,
     rc = syk_detect_seg_boundaries(arr.p, elem_bytes, shape, strides, (uint8_t *)out.p, hs);
     if (rc) return rc;
     SYK_D2H(out_host, out.p, nvox, hs);
+    return SYK_OK;
+}
+
+SYK_API int syk_detect_contact_partners_host(const void *edges_host, int edge_bytes, const int64_t edge_strides[3], const void *arr_host,
+                                             int elem_bytes, const int64_t strides[3], const int64_t shape[3], const int32_t stencil[3],
+                                             uint64_t *out_host) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    SYK_CHECK_ARG(arr_host && out_host && shape && strides && stencil, "NULL argument");
+    for (int a = 0; a < 3; ++a)
+        SYK_CHECK_ARG(stencil[a] >= 1 && (stencil[a] % 2) == 1, "stencil must be odd along every axis");
+    int64_t oshape[3];
+    uint64_t nout = 1;
+    for (int a = 0; a < 3; ++a) {
+        oshape[a] = shape[a] - stencil[a] + 1;
+        if (oshape[a] <= 0) return SYK_OK;
+        nout *= (uint64_t)oshape[a];
+    }
+    const uint64_t nvox = (uint64_t)shape[0] * shape[1] * shape[2];
+    if ((rc = check_dense(shape, strides, 3))) return rc;
+    cudaStream_t hs = syk_host_stream();
+    DevBuf arr, labels, ids, edg, packed, out;
+    SYK_CUDA(dev_alloc(arr, nvox * elem_bytes, hs));
+    SYK_H2D(arr.p, arr_host, nvox * elem_bytes, hs);
+    const void *lab = arr.p;
+    if (elem_bytes == 8) {  // 64-bit ids -> dense uint32 labels (a bijection keeps boundaries, counts and scan order)
+        uint64_t n_ids = 0;
+        if ((rc = relabel_block(arr.p, 8, nvox, labels, ids, &n_ids, hs))) return rc;
+        lab = labels.p;
+    }
+    if (edges_host) {
+        SYK_CHECK_ARG(edge_bytes == 1 || edge_bytes == 4, "edge_bytes must be 1 or 4");
+        if ((rc = check_dense(shape, edge_strides, 3))) return rc;
+        SYK_CUDA(dev_alloc(edg, nvox * edge_bytes, hs));
+        SYK_H2D(edg.p, edges_host, nvox * edge_bytes, hs);
+    }
+    SYK_CUDA(dev_alloc(packed, nout * 8, hs));
+    SYK_CUDA(dev_alloc(out, nout * 16, hs));
+    const int64_t ost[3] = {oshape[1] * oshape[2], oshape[2], 1};
+    rc = syk_detect_contact_partners(edg.p, edge_bytes, edge_strides, lab, strides, shape, stencil, (uint64_t *)packed.p, ost, hs);
+    if (!rc) rc = syk_cs64_unpack((const uint64_t *)packed.p, nout, (const uint64_t *)ids.p, (uint64_t *)out.p, hs);
+    if (rc) return rc;
+    SYK_D2H(out_host, out.p, nout * 16, hs);
+    return SYK_OK;
+}
+
+SYK_API int syk_find_object_properties_cs_64bit_host(const uint64_t *cs_host, const int64_t shape[3], const int64_t strides[4],
+                                                     syk_record_t **records_out, uint64_t **partners_out, uint64_t *n_out) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(cs_host && shape && strides && records_out && partners_out && n_out, "NULL argument");
+    *records_out = nullptr;
+    *partners_out = nullptr;
+    *n_out = 0;
+    const uint64_t nvox = (uint64_t)shape[0] * shape[1] * shape[2];
+    if (nvox == 0) return SYK_OK;
+    const int64_t shape4[4] = {shape[0], shape[1], shape[2], 2};
+    if ((rc = check_dense(shape4, strides, 4))) return rc;
+    cudaStream_t hs = syk_host_stream();
+    DevBuf cs, labels, ids, packed;
+    SYK_CUDA(dev_alloc(cs, nvox * 16, hs));
+    SYK_H2D(cs.p, cs_host, nvox * 16, hs);
+    uint64_t n_ids = 0;
+    if ((rc = relabel_block(cs.p, 8, nvox * 2, labels, ids, &n_ids, hs))) return rc;
+    SYK_CUDA(dev_alloc(packed, nvox * 8, hs));
+    long long blocks = (long long)((nvox + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_pack_pairs<<<(unsigned)blocks, 256, 0, hs>>>((const unsigned *)labels.p, shape[0], shape[1], shape[2], strides[0], strides[1],
+                                                   strides[2], strides[3], (unsigned long long *)packed.p);
+    SYK_CUDA(cudaGetLastError());
+    const int64_t origin[3] = {0, 0, 0};
+    const int64_t pst[3] = {shape[1] * shape[2], shape[2], 1};
+    syk_chunk_geom_t geom;
+    for (int a = 0; a < 3; ++a) {
+        geom.origin[a] = 0;
+        geom.shape[a] = shape[a];
+    }
+    uint64_t cap = pick_capacity(0, nvox);
+    for (;;) {
+        syk_table_t *t = nullptr;
+        if ((rc = syk_table_create_on(&t, cap, hs))) return rc;
+        rc = syk_find_object_properties(t, packed.p, 8, shape, pst, origin, 0, hs);
+        if (!rc) rc = export_to_host(t, &geom, records_out, n_out, hs);
+        syk_table_destroy(t);
+        if (rc != SYK_EOVERFLOW || cap >= nvox * 2) break;
+        cap *= 4;
+    }
+    if (rc || *n_out == 0) return rc;
+    uint64_t *idh = (uint64_t *)malloc((n_ids ? n_ids : 1) * sizeof(uint64_t));
+    uint64_t *pr = (uint64_t *)malloc(*n_out * 2 * sizeof(uint64_t));
+    if (!idh || !pr) {
+        free(idh);
+        free(pr);
+        free(*records_out);
+        *records_out = nullptr;
+        *n_out = 0;
+        return SYK_ENOMEM;
+    }
+    cudaError_t e = cudaMemcpyAsync(idh, ids.p, n_ids * sizeof(uint64_t), cudaMemcpyDeviceToHost, hs);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(hs);
+    if (e != cudaSuccess) {
+        syk_set_error("copy of the id list failed: %s", cudaGetErrorString(e));
+        free(idh);
+        free(pr);
+        free(*records_out);
+        *records_out = nullptr;
+        *n_out = 0;
+        return SYK_ECUDA;
+    }
+    for (uint64_t i = 0; i < *n_out; ++i) {  // packed dense labels -> the two partner ids of the record
+        const uint64_t k = (*records_out)[i].id;
+        const uint32_t l0 = (uint32_t)(k >> 32), l1 = (uint32_t)k;
+        pr[2 * i] = l0 ? idh[l0 - 1] : 0;
+        pr[2 * i + 1] = l1 ? idh[l1 - 1] : 0;
+    }
+    free(idh);
+    *partners_out = pr;
     return SYK_OK;
 }

@@ -412,6 +412,66 @@ SYK_API int syk_pairs_bucket(const syk_pair_t *pairs_dev, uint64_t n, uint32_t n
     return bucket_impl<syk_pair_t>(pairs_dev, n, n_owners, out_dev, counts_dev, (cudaStream_t)stream);
 }
 
+// ---- dense relabelling of 64-bit ids (support of the 64-bit contact-site variants) -------------------------------------
+__global__ void k_dense_insert(const void *__restrict__ vol, int elem_bytes, unsigned long long n, TableView t) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = elem_bytes == 8 ? ((const unsigned long long *)vol)[i] : (unsigned long long)((const unsigned *)vol)[i];
+        if (k != 0ull) syk_table_slot(t, k);
+    }
+}
+__global__ void k_dense_number(SykSlot *slots, uint64_t cap, unsigned long long *counter, unsigned long long *ids, unsigned long long max_ids) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = slots[i].key;
+        if (k == 0ull) continue;
+        const unsigned long long idx = atomicAdd(counter, 1ull);
+        slots[i].count = idx + 1ull;  // dense label
+        if (idx < max_ids) ids[idx] = k;
+    }
+}
+__global__ void k_dense_apply(const void *__restrict__ vol, int elem_bytes, unsigned long long n, TableView t, unsigned *__restrict__ out) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = elem_bytes == 8 ? ((const unsigned long long *)vol)[i] : (unsigned long long)((const unsigned *)vol)[i];
+        unsigned lab = 0u;
+        if (k != 0ull) {
+            const SykSlot *s = syk_table_slot(t, k);
+            lab = s ? (unsigned)s->count : 0u;
+        }
+        out[i] = lab;
+    }
+}
+// labels_out[i] = dense label (1..n_ids, 0 for id 0) of vol[i]; ids_out[label - 1] = id.  `t` must be empty; it is left
+// holding id -> label in the count field.  SYK_EOVERFLOW: table or ids_out too small.
+SYK_API int syk_dense_relabel(syk_table_t *t, const void *vol_dev, int elem_bytes, uint64_t n, uint32_t *labels_out_dev,
+                              uint64_t *ids_out_dev, uint64_t max_ids, uint64_t *n_ids_out_host, void *stream) {
+    SYK_CHECK_ARG(t && vol_dev && labels_out_dev && ids_out_dev && n_ids_out_host, "NULL argument");
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    cudaStream_t s = (cudaStream_t)stream;
+    *n_ids_out_host = 0;
+    if (n == 0) return SYK_OK;
+    unsigned long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_dense_insert<<<(unsigned)blocks, 256, 0, s>>>(vol_dev, elem_bytes, n, view_of(t));
+    SYK_CUDA(cudaMemsetAsync(t->counter, 0, sizeof(unsigned long long), s));
+    unsigned long long cb = (t->capacity + 255) / 256;
+    if (cb > 148 * 16) cb = 148 * 16;
+    k_dense_number<<<(unsigned)cb, 256, 0, s>>>(t->slots, t->capacity, t->counter, (unsigned long long *)ids_out_dev, max_ids);
+    k_dense_apply<<<(unsigned)blocks, 256, 0, s>>>(vol_dev, elem_bytes, n, view_of(t), labels_out_dev);
+    SYK_CUDA(cudaGetLastError());
+    unsigned long long nid = 0;
+    int fl = 0;
+    SYK_CUDA(cudaMemcpyAsync(&nid, t->counter, sizeof(nid), cudaMemcpyDeviceToHost, s));
+    SYK_CUDA(cudaMemcpyAsync(&fl, t->flags, sizeof(fl), cudaMemcpyDeviceToHost, s));
+    SYK_CUDA(cudaStreamSynchronize(s));
+    *n_ids_out_host = nid;
+    if (fl || nid > max_ids || nid >= 0xFFFFFFFFull) {
+        syk_set_error("dense relabel: table / id buffer too small (%llu ids)", nid);
+        return SYK_EOVERFLOW;
+    }
+    return SYK_OK;
+}
+
 // ---- pair tables ------------------------------------------------------------------------------------------------
 int syk_pairs_create_on(syk_pairs **out, uint64_t capacity, cudaStream_t s) {
     SYK_CHECK_ARG(out != nullptr, "out is NULL");

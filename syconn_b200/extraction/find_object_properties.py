@@ -58,3 +58,106 @@ def detect_cs(arr, stencil=None, out=None, return_props=False):
     _lib.check(_lib.load().syk_detect_cs_host(arr.ctypes.data, arr.itemsize, _lib.i64(arr.shape), _lib.i64(estrides(arr)),
                                               _lib.i32(st), out.ctypes.data))
     return out
+
+
+def detect_contact_partners(seg_arr, edge_arr, offset):
+    """syconn/extraction/find_object_properties.py:371-421 (numba).  Most frequent foreign id inside the window
+    ``offset`` around every voxel flagged in ``edge_arr``; ties go to the id met first in the x, y, z scan of the window.
+    Returns the "valid" XYZC (C = 2) uint64 volume of sorted partner ids.  The GPU path supports the symmetric windows
+    the reference itself uses (``offset = [(-o, o)] * 3``, :363-366); anything else raises ``NotImplementedError``."""
+    seg_arr = np.asarray(seg_arr)
+    offset = np.asarray(offset)
+    if offset.shape != (3, 2) or np.any(offset[:, 0] != -offset[:, 1]) or np.any(offset[:, 1] < 0):
+        raise NotImplementedError("libsyk implements the symmetric windows of detect_cs_64bit (offset = [(-o, o)] * 3)")
+    if seg_arr.dtype not in (np.uint32, np.uint64):
+        seg_arr = seg_arr.astype(np.uint64)
+    st = [int(2 * o + 1) for o in offset[:, 1]]
+    oshape = tuple(max(0, seg_arr.shape[i] - st[i] + 1) for i in range(3))
+    out = np.zeros(oshape + (2,), np.uint64)
+    if out.size == 0:
+        return out
+    seg = dense_view(seg_arr)
+    if edge_arr is None:
+        ep, eb, es = None, 0, None
+    else:
+        edges = np.asarray(edge_arr)
+        assert edges.shape == seg_arr.shape
+        edges = dense_view(edges.view(np.uint8) if edges.dtype == np.bool_ else
+                           edges if edges.dtype in (np.uint8, np.uint32) else (edges != 0).view(np.uint8))
+        ep, eb, es = edges.ctypes.data, edges.itemsize, _lib.i64(estrides(edges))
+    _lib.check(_lib.load().syk_detect_contact_partners_host(ep, eb, es, seg.ctypes.data, seg.itemsize, _lib.i64(estrides(seg)),
+                                                            _lib.i64(seg.shape), _lib.i32(st), out.ctypes.data))
+    return out
+
+
+def detect_cs_64bit(arr):
+    """syconn/extraction/find_object_properties.py:347-368: ``detect_seg_boundaries`` + ``detect_contact_partners``
+    with the stencil of ``global_params.config['cell_objects']['cs_filtersize']``; 4-D XYZC result (C = 2)."""
+    stencil = np.array(global_params.config['cell_objects']['cs_filtersize'])
+    assert np.sum(stencil % 2) == 3
+    o = stencil // 2
+    return detect_contact_partners(arr, None, np.array([(-o[0], o[0]), (-o[1], o[1]), (-o[2], o[2])]))
+
+
+def find_object_properties_cs_64bit(cs_seg):
+    """syconn/extraction/find_object_properties.py:197-269: representative coordinate, bounding box and size of every
+    partner pair of an XYZC (C = 2) contact volume, as nested dicts ``d[id0][id1]`` (int64 arrays / int)."""
+    import ctypes as C
+    cs_seg = np.asarray(cs_seg)
+    assert cs_seg.ndim == 4 and cs_seg.shape[3] == 2
+    if cs_seg.dtype != np.uint64:
+        cs_seg = cs_seg.astype(np.uint64)
+    rep_coords, bounding_box, sizes = {}, {}, {}
+    if cs_seg.size == 0:
+        return rep_coords, bounding_box, sizes
+    cs = dense_view(cs_seg)
+    rec, par, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    _lib.check(_lib.load().syk_find_object_properties_cs_64bit_host(cs.ctypes.data, _lib.i64(cs.shape[:3]), _lib.i64(estrides(cs)),
+                                                                    C.byref(rec), C.byref(par), C.byref(n)))
+    recs = _lib.take_array(rec.value, n.value, _lib.RECORD_DTYPE)
+    pairs = _lib.take_array(par.value, 2 * n.value, np.dtype("<u8")).reshape(-1, 2)
+    bbs = np.stack([recs["bb_min"], recs["bb_max"]], axis=1).astype(np.int64) if len(recs) else np.zeros((0, 2, 3), np.int64)
+    reps = recs["rep"].astype(np.int64)
+    for i in range(len(recs)):
+        k0, k1 = int(pairs[i, 0]), int(pairs[i, 1])
+        rep_coords.setdefault(k0, {})[k1] = reps[i]
+        bounding_box.setdefault(k0, {})[k1] = bbs[i]
+        sizes.setdefault(k0, {})[k1] = int(recs["count"][i])
+    return rep_coords, bounding_box, sizes
+
+
+def extract_cs_syntype_64bit(cs_seg, syn_mask, asym_mask, sym_mask):
+    """syconn/extraction/find_object_properties.py:23-195 -- dead code in the reference (no caller; its numba typing
+    fails at the first call).  Not provided; use ``block_processing_C.extract_cs_syntype``."""
+    raise NotImplementedError("extract_cs_syntype_64bit has no caller in the reference and does not compile there; "
+                              "use block_processing_C.extract_cs_syntype")
+
+
+def convert_nvox2ratio_syntype(syn_cnts, sym_cnts, asym_cnts):
+    """syconn/extraction/find_object_properties.py:272-299: per contact id, sym / asym voxel counts divided by the
+    synaptic voxel count (0 when the id has no such voxels).  Returns ``(asym_ratio, sym_ratio)``."""
+    sym_ratio = {k: (sym_cnts[k] / n if k in sym_cnts else 0) for k, n in syn_cnts.items()}
+    asym_ratio = {k: (asym_cnts[k] / n if k in asym_cnts else 0) for k, n in syn_cnts.items()}
+    return asym_ratio, sym_ratio
+
+
+def merge_type_dicts(type_dicts):
+    """syconn/extraction/find_object_properties.py:302-320: sum the per-id counts into ``type_dicts[0]`` (in place)."""
+    tot = type_dicts[0]
+    for d in type_dicts[1:]:
+        for k, cnt in d.items():
+            tot[k] = tot[k] + cnt if k in tot else cnt
+
+
+def merge_voxel_dicts(voxel_dicts, key_to_str=False):
+    """syconn/extraction/find_object_properties.py:323-344: concatenate the per-id voxel lists into
+    ``voxel_dicts[0]`` (in place); arrays become lists, keys optionally strings."""
+    tot = voxel_dicts[0]
+    for d in voxel_dicts[1:]:
+        for k, vxs in d.items():
+            if key_to_str:
+                k = str(k)
+            if k in tot:
+                tot[k].extend(vxs)
+            else:
+                tot[k] = vxs.tolist() if isinstance(vxs, np.ndarray) else vxs

@@ -16,3 +16,9 @@ def pytest_configure(config):
 def golden():
     import numpy as np
     return dict(np.load(os.path.join(ROOT, "tests", "golden", "hotpath_golden.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden64():
+    import numpy as np
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "cs64_golden.npz")))

@@ -146,6 +146,43 @@ def main():
 
     np.savez_compressed(os.path.join(OUT, "hotpath_golden.npz"), **out)
     print("wrote", len(out), "arrays,", os.path.getsize(os.path.join(OUT, "hotpath_golden.npz")), "bytes")
+    main64(fop, gp, rng)
+
+
+def pair_props_arrays(dicts):
+    rc, bb, sz = dicts
+    keys = sorted((int(k0), int(k1)) for k0, d in sz.items() for k1 in d.keys())
+    return (np.array(keys, np.uint64).reshape(-1, 2), np.array([int(sz[a][b]) for a, b in keys], np.int64),
+            np.array([np.asarray(bb[a][b]) for a, b in keys], np.int64).reshape(-1, 2, 3),
+            np.array([np.asarray(rc[a][b]) for a, b in keys], np.int64).reshape(-1, 3))
+
+
+def main64(fop, gp, rng):
+    """64-bit variants (numba): detect_cs_64bit / find_object_properties_cs_64bit -> cs64_golden.npz"""
+    out = {}
+    seg = synth_labels((26, 24, 22), pitch=(9, 8, 5), warp_amp=3, seed=5)
+    seg[seg != 0] += np.uint64(3) << np.uint64(40)            # ids beyond 32 bits
+    out["seg_in"] = seg
+    for st in ((13, 13, 7), (7, 7, 3), (5, 5, 3)):
+        gp.config["cell_objects"]["cs_filtersize"] = list(st)
+        out["seg_out_%d_%d_%d" % st] = np.asarray(fop.detect_cs_64bit(seg))
+    tie = rng.integers(0, 6, size=(13, 14, 12)).astype(np.uint64)  # every window full of ties
+    tie[tie != 0] += np.uint64(1) << np.uint64(33)
+    out["tie_in"] = tie
+    for st in ((5, 5, 3), (3, 3, 3)):
+        gp.config["cell_objects"]["cs_filtersize"] = list(st)
+        out["tie_out_%d_%d_%d" % st] = np.asarray(fop.detect_cs_64bit(tie))
+    gp.config["cell_objects"]["cs_filtersize"] = [13, 13, 7]
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):               # the numba function prints debug lines
+        pr = fop.find_object_properties_cs_64bit(out["seg_out_7_7_3"])
+        pt = fop.find_object_properties_cs_64bit(out["tie_out_5_5_3"])
+    for tag, r in (("seg", pr), ("tie", pt)):
+        for k, a in zip(("keys", "sizes", "bbox", "rep"), pair_props_arrays(r)):
+            out[f"props_{tag}_" + k] = a
+    np.savez_compressed(os.path.join(OUT, "cs64_golden.npz"), **out)
+    print("wrote", len(out), "arrays,", os.path.getsize(os.path.join(OUT, "cs64_golden.npz")), "bytes")
 
 
 if __name__ == "__main__":

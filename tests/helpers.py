@@ -49,3 +49,27 @@ def check_syntype_against_golden(res, g):
     assert np.array_equal(ids, g["syn_vox_ids"])
     assert np.array_equal(np.array([len(vox[int(k)]) for k in ids], np.int64), g["syn_vox_len"])
     assert np.array_equal(np.array([c for k in ids for c in vox[int(k)]], np.int64).reshape(-1, 3), g["syn_vox_xyz"])  # scan order
+
+
+def pair_props_to_arrays(dicts):
+    """nested dicts d[id0][id1] of find_object_properties_cs_64bit -> (keys [N, 2], sizes, bbox, rep), sorted by key."""
+    rc, bb, sz = dicts
+    keys = sorted((int(a), int(b)) for a, d in sz.items() for b in d)
+    assert keys == sorted((int(a), int(b)) for a, d in rc.items() for b in d) == sorted((int(a), int(b)) for a, d in bb.items() for b in d)
+    return (np.array(keys, np.uint64).reshape(-1, 2), np.array([int(sz[a][b]) for a, b in keys], np.int64),
+            np.array([np.asarray(bb[a][b]) for a, b in keys], np.int64).reshape(-1, 2, 3),
+            np.array([np.asarray(rc[a][b]) for a, b in keys], np.int64).reshape(-1, 3))
+
+
+def check_cs64_against_golden(detect_cs_64bit, find_props_64bit, g):
+    """detect_cs_64bit / find_object_properties_cs_64bit (numba, find_object_properties.py:197-269,347-421) against the
+    vectors the reference produced (tests/golden/make_golden.py main64).  ``detect_cs_64bit(arr, stencil)``."""
+    for st in ((13, 13, 7), (7, 7, 3), (5, 5, 3)):
+        out = detect_cs_64bit(g["seg_in"], st)
+        assert out.dtype == np.uint64 and np.array_equal(out, g["seg_out_%d_%d_%d" % st]), st
+    for st in ((5, 5, 3), (3, 3, 3)):
+        assert np.array_equal(detect_cs_64bit(g["tie_in"], st), g["tie_out_%d_%d_%d" % st]), st
+    for tag, vol in (("seg", g["seg_out_7_7_3"]), ("tie", g["tie_out_5_5_3"])):
+        got = pair_props_to_arrays(find_props_64bit(vol))
+        for name, a in zip(("keys", "sizes", "bbox", "rep"), got):
+            assert np.array_equal(a, g[f"props_{tag}_{name}"]), f"{tag}: {name} differ"

@@ -278,3 +278,46 @@ def test_extract_cs_syntype(mods, golden):
     empty = bpc.extract_cs_syntype(np.zeros((4, 4, 4), np.uint64), np.ones((4, 4, 4), np.uint8), np.ones((4, 4, 4), np.uint8),
                                    np.ones((4, 4, 4), np.uint8), [0, 0, 0])
     assert empty == ([{}, {}, {}], [{}, {}, {}], {}, {}, {})
+
+
+def test_cs64_variants(mods, golden64):
+    """detect_cs_64bit / detect_contact_partners / find_object_properties_cs_64bit (the numba twins,
+    find_object_properties.py:197-269,347-421): golden vectors of the reference, then seeded volumes against the oracle."""
+    from helpers import check_cs64_against_golden, pair_props_to_arrays
+    from syconn_b200 import global_params
+    fop, oracle = mods["fop"], mods["oracle"]
+    keep = list(global_params.config['cell_objects']['cs_filtersize'])
+
+    def dcs(arr, st):
+        global_params.config['cell_objects']['cs_filtersize'] = list(st)
+        try:
+            return fop.detect_cs_64bit(arr)
+        finally:
+            global_params.config['cell_objects']['cs_filtersize'] = keep
+    check_cs64_against_golden(dcs, fop.find_object_properties_cs_64bit, golden64)
+    rng = np.random.default_rng(3)
+    for seed, shape, st in ((0, (30, 28, 26), (13, 13, 7)), (1, (21, 33, 18), (5, 7, 3)), (2, (16, 16, 40), (3, 3, 3))):
+        seg = mods["synth"](shape, pitch=(7, 8, 5), warp_amp=3, seed=seed)
+        seg[rng.random(shape) < 0.04] = rng.integers(1, 2 ** 50)
+        want = oracle.detect_cs_64bit(seg, st)
+        for lay in (seg, np.asfortranarray(seg)):
+            assert np.array_equal(dcs(lay, st), want), (seed, st)
+        # explicit edge mask (bool / uint32) and uint32 labels
+        o = np.array(st) // 2
+        off = np.array([(-o[0], o[0]), (-o[1], o[1]), (-o[2], o[2])])
+        edges = rng.random(shape) < 0.2
+        want_e = oracle.detect_contact_partners(seg, edges, off)
+        assert np.array_equal(fop.detect_contact_partners(seg, edges, off), want_e)
+        assert np.array_equal(fop.detect_contact_partners(seg, edges.astype(np.uint32), off), want_e)
+        seg32 = (seg & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        assert np.array_equal(fop.detect_contact_partners(seg32, edges, off), oracle.detect_contact_partners(seg32, edges, off))
+        got, wantp = fop.find_object_properties_cs_64bit(want), oracle.find_object_properties_cs_64bit(want)
+        for a, b in zip(pair_props_to_arrays(got), pair_props_to_arrays(wantp)):
+            assert np.array_equal(a, b)
+    # near-random labels: more than 32 distinct ids per window (block-cooperative fallback keeps the first-seen rank)
+    noise = rng.integers(1, 2 ** 40, size=(14, 13, 12)).astype(np.uint64)
+    noise[rng.random(noise.shape) < 0.4] = 5
+    assert np.array_equal(dcs(noise, (5, 5, 3)), oracle.detect_cs_64bit(noise, (5, 5, 3)))
+    assert fop.find_object_properties_cs_64bit(np.zeros((3, 3, 3, 2), np.uint64)) == ({}, {}, {})
+    with pytest.raises(NotImplementedError):
+        fop.detect_contact_partners(noise, None, np.array([(-1, 2), (-1, 1), (-1, 1)]))

@@ -162,3 +162,14 @@ def test_oracle_vs_golden_syntype(golden):
     from helpers import check_syntype_against_golden
     g = golden
     check_syntype_against_golden(oracle.extract_cs_syntype(g["syn_cs"], g["syn_mask"], g["syn_asym"], g["syn_sym"], g["syn_off"]), g)
+
+
+def test_oracle_vs_golden_cs64(golden64):
+    """the numba 64-bit variants (first-seen tie-break, XYZC output, per-pair properties)"""
+    from helpers import check_cs64_against_golden
+    check_cs64_against_golden(oracle.detect_cs_64bit, oracle.find_object_properties_cs_64bit, golden64)
+    # reference tests/test_segmentation_analysis.py:132-135 (test_detect_cs_64bit): same analytic volumes as test_detect_cs
+    for d in ([0, 6, 0], [6, 0, 0], [0, 0, 6]):
+        sample, lo, hi = gen_sample_seg(np.array(d), STENCIL, 5)
+        out = oracle.detect_cs_64bit(sample.astype(np.uint64), tuple(STENCIL))
+        assert np.array_equal(out[..., 0], lo) and np.array_equal(out[..., 1], hi)
