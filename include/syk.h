@@ -177,6 +177,16 @@ int syk_cs64_unpack(const uint64_t *packed_dev, uint64_t n, const uint64_t *ids_
 int syk_dense_relabel(syk_table_t *t, const void *vol_dev, int elem_bytes, uint64_t n, uint32_t *labels_out_dev,
                       uint64_t *ids_out_dev, uint64_t max_ids, uint64_t *n_ids_out_host, void *stream);
 
+/* Per-contact closing + dilation ("next" row f2): the per-id loop of the contact-site worker,
+ * syconn/extraction/cs_extraction_steps.py:439-461.  For every id of ids_host[0..n_ids), in list order: the id's mask
+ * inside its bounding box padded by n_closings (clipped to the volume) is closed (scipy.ndimage.binary_closing,
+ * iterations = n_closings) and dilated (binary_dilation, iterations = n_dilations), 6-neighbourhood, border value 0;
+ * voxels of the result that are still background take the id (the first id in list order wins, as in the sequential
+ * loop).  cs_dev is modified in place.  bbox_host[i] = {min[3], max_exclusive[3]} in voxels of the volume passed, as
+ * find_object_properties returns it (it must contain every voxel of the id).  Synchronises `stream`. */
+int syk_close_contacts(void *cs_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3], const uint64_t *ids_host,
+                       const int32_t *bbox_host, uint64_t n_ids, int n_closings, int n_dilations, void *stream);
+
 /* ---- synthetic label volumes (bench/test inputs; bit-identical to syconn_b200/synth.py) ------------------ */
 /* kind 0: cell supervoxels (ids < 2^32, ~3% background); kind 1..: organelle channel (sparse 64-bit ids) */
 int syk_synth_labels(void *out_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
@@ -219,6 +229,9 @@ int syk_detect_contact_partners_host(const void *edges_host, int edge_bytes, con
  * contact volume (C = 2).  records_out[i].id is internal; partners_out[2 i .. 2 i + 1] are the pair's ids. */
 int syk_find_object_properties_cs_64bit_host(const uint64_t *cs_host, const int64_t shape[3], const int64_t strides[4],
                                              syk_record_t **records_out, uint64_t **partners_out, uint64_t *n_out);
+/* host-buffer form of syk_close_contacts: cs_host (dense block) is updated in place */
+int syk_close_contacts_host(void *cs_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3], const uint64_t *ids_host,
+                            const int32_t *bbox_host, uint64_t n_ids, int n_closings, int n_dilations);
 void syk_free(void *p);
 
 #ifdef __cplusplus

@@ -17,6 +17,7 @@ The functions mirror the reference API (same return structures):
   * process_block_nonzero       -- syconn/extraction/block_processing_C.pyx:53-75 (+ kernel :21-49)
   * detect_cs                   -- syconn/extraction/find_object_properties.py:458-472
   * merge_prop_dicts / merge_map_dicts -- syconn/proc/sd_proc.py:1248-1273, :1300-1322
+  * close_contact_sites         -- syconn/extraction/cs_extraction_steps.py:439-461 (+ scipy.ndimage restated)
 """
 import ctypes as C
 import os
@@ -309,6 +310,64 @@ def extract_cs_syntype(cs_seg, syn_mask, asym_mask, sym_mask, offset):
 
 
 # ------------------------------------------------------------------------------------------ merges (a6)
+def _binary_step(mask, erode):
+    """One iteration of scipy.ndimage.binary_dilation / binary_erosion with the default structure
+    (generate_binary_structure(3, 1): the 6-neighbourhood cross) and border_value = 0: a voxel of the result is the
+    OR (dilation) / AND (erosion) of itself and its six face neighbours, neighbours outside the array counting as 0."""
+    out = mask.copy()
+    for ax in range(3):
+        for sh in (1, -1):
+            nb = np.zeros_like(mask)
+            src = [slice(None)] * 3
+            dst = [slice(None)] * 3
+            if sh == 1:
+                src[ax], dst[ax] = slice(0, -1), slice(1, None)
+            else:
+                src[ax], dst[ax] = slice(1, None), slice(0, -1)
+            nb[tuple(dst)] = mask[tuple(src)]
+            out = (out & nb) if erode else (out | nb)
+    return out
+
+
+def binary_closing_dilation(mask, n_closings, n_dilations):
+    """scipy.ndimage.binary_closing(mask, iterations=n_closings) followed by binary_dilation(iterations=n_dilations),
+    restated (scipy is the third-party home of this arithmetic; the reference pins scipy < 1.9, environment.yml:41):
+    closing = n dilations then n erosions, each with border_value 0."""
+    m = np.asarray(mask) != 0
+    for _ in range(n_closings):
+        m = _binary_step(m, False)
+    for _ in range(n_closings):
+        m = _binary_step(m, True)
+    for _ in range(n_dilations):
+        m = _binary_step(m, False)
+    return m
+
+
+def close_contact_sites(contacts, bb_dc, n_closings, cs_dilation, use_scipy=False):
+    """syconn/extraction/cs_extraction_steps.py:439-461 ("next" row f2): per contact id, in the iteration order of
+    ``bb_dc``, the id's mask inside its bounding box padded by ``n_closings`` (clipped to the volume) is closed and
+    dilated; the result is written where the volume still holds background (or the id itself).  In place, like the
+    reference.  ``use_scipy``: call scipy.ndimage literally as the reference does (pins the restatement above)."""
+    for ix in bb_dc.keys():
+        obj_start, obj_end = np.array(bb_dc[ix])
+        obj_start -= n_closings
+        obj_start[obj_start < 0] = 0
+        obj_end += n_closings
+        sl = tuple(slice(obj_start[ii], obj_end[ii], None) for ii in range(3))
+        sub_vol = contacts[sl]
+        binary_mask = (sub_vol == ix).astype(np.int8, copy=False)
+        if use_scipy:
+            import scipy.ndimage
+            res = scipy.ndimage.binary_closing(binary_mask, iterations=n_closings) if n_closings > 0 else binary_mask
+            if cs_dilation > 0:
+                res = scipy.ndimage.binary_dilation(res, iterations=cs_dilation)
+        else:
+            res = binary_closing_dilation(binary_mask, n_closings, cs_dilation)
+        proc_mask = ((binary_mask == 1) | (sub_vol == 0)) & (res == 1)
+        contacts[sl][proc_mask] = np.uint64(ix)  # == res[proc_mask] * ix (:461); np.uint64 keeps ids >= 2^63 exact
+    return contacts
+
+
 def merge_prop_dicts(prop_dicts, offset=None):
     """syconn/proc/sd_proc.py:1248-1273: rc overwritten by later chunks, bboxes appended, sizes summed."""
     tot_rc, tot_bb, tot_size = prop_dicts[0]

@@ -33,6 +33,7 @@ EXPORTS = [
     "syk_process_block_nonzero_host", "syk_extract_cs_syntype_host", "syk_detect_seg_boundaries_host", "syk_free",
     "syk_detect_contact_partners", "syk_cs64_unpack", "syk_dense_relabel",
     "syk_detect_contact_partners_host", "syk_find_object_properties_cs_64bit_host",
+    "syk_close_contacts", "syk_close_contacts_host",
 ]
 
 
@@ -100,6 +101,8 @@ def load():
     L.syk_dense_relabel.argtypes = [vp, vp, ci, u64, vp, vp, u64, u64p, vp]
     L.syk_detect_contact_partners_host.argtypes = [vp, ci, i64p, vp, ci, i64p, i64p, i32p, vp]
     L.syk_find_object_properties_cs_64bit_host.argtypes = [vp, i64p, i64p, C.POINTER(vp), C.POINTER(vp), u64p]
+    L.syk_close_contacts.argtypes = [vp, ci, i64p, i64p, vp, vp, u64, ci, ci, vp]
+    L.syk_close_contacts_host.argtypes = [vp, ci, i64p, i64p, vp, vp, u64, ci, ci]
     L.syk_free.argtypes = [vp]
     L.syk_free.restype = None
     for name in EXPORTS:

@@ -615,3 +615,22 @@ SYK_API int syk_find_object_properties_cs_64bit_host(const uint64_t *cs_host, co
     *partners_out = pr;
     return SYK_OK;
 }
+
+SYK_API int syk_close_contacts_host(void *cs_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                                    const uint64_t *ids_host, const int32_t *bbox_host, uint64_t n_ids, int n_closings,
+                                    int n_dilations) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    SYK_CHECK_ARG(cs_host && shape && strides, "NULL argument");
+    const uint64_t nvox = (uint64_t)shape[0] * shape[1] * shape[2];
+    if (nvox == 0 || n_ids == 0) return SYK_OK;
+    if ((rc = check_dense(shape, strides, 3))) return rc;
+    cudaStream_t hs = syk_host_stream();
+    DevBuf cs;
+    SYK_CUDA(dev_alloc(cs, nvox * elem_bytes, hs));
+    SYK_H2D(cs.p, cs_host, nvox * elem_bytes, hs);
+    if ((rc = syk_close_contacts(cs.p, elem_bytes, shape, strides, ids_host, bbox_host, n_ids, n_closings, n_dilations, hs))) return rc;
+    SYK_D2H(cs_host, cs.p, nvox * elem_bytes, hs);
+    return SYK_OK;
+}

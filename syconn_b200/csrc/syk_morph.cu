@@ -1,0 +1,412 @@
+// syk_morph.cu -- per-contact binary closing + dilation ("next" row f2 of SURVEY.md section 8).
+//
+// Replaces the per-id Python loop of the contact-site worker (syconn/extraction/cs_extraction_steps.py:439-461):
+//   for every contact id, in the order of the id list: the id's mask inside its bounding box padded by n_closings
+//   (clipped to the volume) goes through scipy.ndimage.binary_closing(iterations = n_closings) and
+//   binary_dilation(iterations = cs_dilation), both with the 6-neighbourhood cross and border_value 0; the result is
+//   written to the voxels of the box that are still background.
+// The closed mask of an id only depends on the id's own voxels (no step ever writes or removes another id's label), so
+// all ids are processed in parallel; the sequential "first id in list order wins a background voxel" rule is restored
+// with an atomicMin of the id's list position into a per-voxel rank volume, resolved by one final pass.
+//
+// Masks are bit-packed along the memory-contiguous axis (32 voxels per word); one morphological step of a word is
+// OR / AND of the word, its two funnel-shifted row neighbours and the four words above/below/before/behind it.
+//   * boxes of up to SMALL_WORDS words (the typical contact): ONE CTA keeps both ping-pong bit buffers in shared memory
+//     and does mask build, all 2 n + m steps and the write-back in a single launch;
+//   * larger boxes: bit buffers in HBM, one launch per step over all words of all large boxes.
+// All arithmetic is integer/bitwise; results are bit-identical to the reference loop run in the same id order.
+#include <stdlib.h>
+
+#include <vector>
+
+#include "syk_common.cuh"
+
+namespace {
+
+constexpr int MT = 256;              // threads per CTA
+constexpr int SMALL_WORDS = 6144;    // 2 buffers x 24 KB of shared memory, 256 threads
+constexpr int TINY_WORDS = 1024;     // 2 buffers x 4 KB, 128 threads: the typical contact
+constexpr unsigned NO_RANK = 0xFFFFFFFFu;
+
+struct MorphBox {  // 64 bytes
+    unsigned long long id;
+    unsigned long long word0;  // first word of the box in the HBM bit buffers (large boxes)
+    int lo[3];                 // padded, clipped box origin (internal axes u, v, w)
+    int ext[3];                // padded, clipped box extents
+    int ilo[3];                // the id's own bounding box relative to lo ...
+    int ihi[3];                // ... (exclusive): the mask is empty outside of it
+};
+static_assert(sizeof(MorphBox) == 64, "MorphBox layout");
+
+struct MorphCta {
+    unsigned box;   // index into the box array
+    unsigned base;  // first word (inside the box) of this CTA
+};
+
+struct MorphGeom {
+    long long st[3];  // contact volume strides (elements) along the internal axes
+    int n[3];         // contact volume extents along the internal axes
+    int elem_bytes;
+};
+
+__device__ __forceinline__ unsigned long long ld_label(const void *vol, int elem_bytes, long long a) {
+    return elem_bytes == 8 ? ((const unsigned long long *)vol)[a] : (unsigned long long)((const unsigned *)vol)[a];
+}
+
+// one dilation (ERODE = false) or erosion (ERODE = true) step of word (u, v, k); voxels outside the box count as 0
+template <bool ERODE>
+__device__ __forceinline__ unsigned morph_word(const unsigned *src, int u, int v, int k, int eu, int ev, int wpr, unsigned valid) {
+    const int row = ev * wpr;
+    const unsigned *p = src + ((long long)u * ev + v) * wpr + k;
+    const unsigned c = p[0];
+    const unsigned l = k > 0 ? p[-1] : 0u, r = k + 1 < wpr ? p[1] : 0u;
+    const unsigned wl = __funnelshift_l(l, c, 1);  // bit i = voxel i - 1
+    const unsigned wr = __funnelshift_r(c, r, 1);  // bit i = voxel i + 1 (bits past the box end are kept 0 in storage)
+    const unsigned vm = v > 0 ? p[-wpr] : 0u, vp = v + 1 < ev ? p[wpr] : 0u;
+    const unsigned um = u > 0 ? p[-row] : 0u, up = u + 1 < eu ? p[row] : 0u;
+    if (ERODE) return c & wl & wr & vm & vp & um & up;
+    return (c | wl | wr | vm | vp | um | up) & valid;
+}
+
+__device__ __forceinline__ unsigned valid_bits(int k, int ew) {
+    const int left = ew - k * 32;
+    return left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
+}
+
+// mask word (u, v, k) of the box: bit i = (contacts[lo + (u, v, 32 k + i)] == id).  Warp-cooperative: lane i tests voxel i.
+__device__ __forceinline__ unsigned build_word(const void *vol, const MorphGeom &G, const MorphBox &B, int u, int v, int k, int lane) {
+    if (u < B.ilo[0] || u >= B.ihi[0] || v < B.ilo[1] || v >= B.ihi[1] || k * 32 >= B.ihi[2] || k * 32 + 32 <= B.ilo[2]) return 0u;
+    const int w = k * 32 + lane;
+    bool hit = false;
+    if (w >= B.ilo[2] && w < B.ihi[2])
+        hit = ld_label(vol, G.elem_bytes, (long long)(B.lo[0] + u) * G.st[0] + (long long)(B.lo[1] + v) * G.st[1] +
+                                              (long long)(B.lo[2] + w) * G.st[2]) == B.id;
+    return __ballot_sync(0xFFFFFFFFu, hit);
+}
+
+// result word (u, v, k): every set voxel takes part in the "first id in list order" vote (fire-and-forget RED.MIN; the
+// final pass only looks at the votes of voxels that are still background)
+__device__ __forceinline__ void apply_word(const MorphGeom &G, const MorphBox &B, unsigned rank, unsigned bits, int u, int v, int k,
+                                           int lane, unsigned *rankvol) {
+    if (!((bits >> lane) & 1u)) return;
+    const long long gu = B.lo[0] + u, gv = B.lo[1] + v, gw = B.lo[2] + k * 32 + lane;
+    atomicMin(&rankvol[(gu * G.n[1] + gv) * G.n[2] + gw], rank);
+}
+
+// ---- small boxes: everything in one launch, bit buffers in shared memory ---------------------------------------------------
+// WORDS = capacity of one bit buffer, NT = threads per CTA.  Two size classes are instantiated so that the typical contact
+// (a few hundred words) runs with many CTAs per SM.
+template <int WORDS, int NT>
+__global__ void __launch_bounds__(NT) k_morph_small(const void *__restrict__ vol, MorphGeom G, const MorphBox *__restrict__ boxes,
+                                                    const unsigned *__restrict__ list, unsigned nlist, int n_close, int n_dil,
+                                                    unsigned *__restrict__ rankvol) {
+    __shared__ unsigned buf[2][WORDS];
+    constexpr int PRE = 4;  // rounds of the step loop whose word coordinates are kept in registers
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (unsigned bi = blockIdx.x; bi < nlist; bi += gridDim.x) {
+        const unsigned rank = list[bi];
+        const MorphBox B = boxes[rank];
+        const int eu = B.ext[0], ev = B.ext[1], ew = B.ext[2];
+        const int wpr = (ew + 31) >> 5;
+        const int words = eu * ev * wpr;
+        __syncthreads();  // the previous box is done with the buffers
+        for (int i = tid; i < words; i += NT) buf[0][i] = 0u;
+        __syncthreads();
+        // mask of the id: only the rows of its own bounding box can hold voxels; four words (loads) in flight per warp
+        {
+            const int k0 = B.ilo[2] >> 5, nk = ((B.ihi[2] + 31) >> 5) - k0;
+            const int iv = B.ihi[1] - B.ilo[1];
+            const int nin = (B.ihi[0] - B.ilo[0]) * iv * nk;
+            for (int i0 = warp * 4; i0 < nin; i0 += (NT / 32) * 4) {
+                bool hit[4];
+                int dst[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j;
+                    hit[j] = false;
+                    dst[j] = -1;
+                    if (i < nin) {
+                        const int k = k0 + i % nk, r = i / nk;
+                        const int v = B.ilo[1] + r % iv, u = B.ilo[0] + r / iv;
+                        const int w = k * 32 + lane;
+                        dst[j] = (u * ev + v) * wpr + k;
+                        if (w >= B.ilo[2] && w < B.ihi[2])
+                            hit[j] = ld_label(vol, G.elem_bytes, (long long)(B.lo[0] + u) * G.st[0] + (long long)(B.lo[1] + v) * G.st[1] +
+                                                                     (long long)(B.lo[2] + w) * G.st[2]) == B.id;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned b = __ballot_sync(0xFFFFFFFFu, hit[j]);
+                    if (lane == 0 && dst[j] >= 0) buf[0][dst[j]] = b;
+                }
+            }
+        }
+        int pos[PRE];  // (u << 19) | (v << 8) | k of the word handled in round q (host: ext_u < 8192, ext_v < 2048, wpr < 256)
+#pragma unroll
+        for (int q = 0; q < PRE; ++q) {
+            const int wi = tid + q * NT;
+            const int k = wi % wpr, r = wi / wpr;
+            pos[q] = ((r / ev) << 19) | ((r % ev) << 8) | k;
+        }
+        __syncthreads();
+        int cur = 0;
+        const int steps = 2 * n_close + n_dil;
+        for (int s = 0; s < steps; ++s) {
+            const bool erode = s >= n_close && s < 2 * n_close;
+            const unsigned *src = buf[cur];
+            unsigned *dstb = buf[cur ^ 1];
+#pragma unroll
+            for (int q = 0; q < PRE; ++q) {
+                const int wi = tid + q * NT;
+                if (wi < words) {
+                    const int u = (int)((unsigned)pos[q] >> 19), v = (pos[q] >> 8) & 0x7FF, k = pos[q] & 0xFF;
+                    dstb[wi] = erode ? morph_word<true>(src, u, v, k, eu, ev, wpr, 0u) : morph_word<false>(src, u, v, k, eu, ev, wpr, valid_bits(k, ew));
+                }
+            }
+            for (int wi = tid + PRE * NT; wi < words; wi += NT) {
+                const int k = wi % wpr, r = wi / wpr;
+                const int v = r % ev, u = r / ev;
+                dstb[wi] = erode ? morph_word<true>(src, u, v, k, eu, ev, wpr, 0u) : morph_word<false>(src, u, v, k, eu, ev, wpr, valid_bits(k, ew));
+            }
+            cur ^= 1;
+            __syncthreads();
+        }
+        for (int w0 = warp * 32; w0 < words; w0 += NT) {
+            const int nw = min(32, words - w0);
+            const unsigned mine = lane < nw ? buf[cur][w0 + lane] : 0u;
+            unsigned todo = __ballot_sync(0xFFFFFFFFu, mine != 0u);
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                const unsigned bits = __shfl_sync(0xFFFFFFFFu, mine, j);
+                const int wi = w0 + j;
+                const int k = wi % wpr, r = wi / wpr;
+                apply_word(G, B, rank, bits, r / ev, r % ev, k, lane, rankvol);
+            }
+        }
+    }
+}
+
+// ---- large boxes: bit buffers in HBM, one launch per step --------------------------------------------------------------------
+__global__ void __launch_bounds__(MT) k_morph_build(const void *__restrict__ vol, MorphGeom G, const MorphBox *__restrict__ boxes,
+                                                    const MorphCta *__restrict__ ctas, unsigned *__restrict__ dst) {
+    const MorphCta c = ctas[blockIdx.x];
+    const MorphBox B = boxes[c.box];
+    const int ev = B.ext[1], wpr = (B.ext[2] + 31) >> 5;
+    const long long words = (long long)B.ext[0] * ev * wpr;
+    const int lane = threadIdx.x & 31;
+    const long long w0 = (long long)c.base + (threadIdx.x >> 5) * 32;
+    if (w0 >= words) return;
+    const int nw = (int)min(32ll, words - w0);
+    unsigned mine = 0u;
+    for (int j = 0; j < nw; ++j) {
+        const long long wi = w0 + j;
+        const int k = (int)(wi % wpr);
+        const long long r = wi / wpr;
+        const unsigned b = build_word(vol, G, B, (int)(r / ev), (int)(r % ev), k, lane);
+        if (lane == j) mine = b;
+    }
+    if (lane < nw) dst[B.word0 + w0 + lane] = mine;
+}
+
+template <bool ERODE>
+__global__ void __launch_bounds__(MT) k_morph_step(const MorphBox *__restrict__ boxes, const MorphCta *__restrict__ ctas,
+                                                   const unsigned *__restrict__ src, unsigned *__restrict__ dst) {
+    const MorphCta c = ctas[blockIdx.x];
+    const MorphBox B = boxes[c.box];
+    const int eu = B.ext[0], ev = B.ext[1], wpr = (B.ext[2] + 31) >> 5;
+    const long long words = (long long)eu * ev * wpr;
+    const long long wi = (long long)c.base + threadIdx.x;
+    if (wi >= words) return;
+    const int k = (int)(wi % wpr);
+    const long long r = wi / wpr;
+    dst[B.word0 + wi] = morph_word<ERODE>(src + B.word0, (int)(r / ev), (int)(r % ev), k, eu, ev, wpr, valid_bits(k, B.ext[2]));
+}
+
+__global__ void __launch_bounds__(MT) k_morph_apply(MorphGeom G, const MorphBox *__restrict__ boxes,
+                                                    const MorphCta *__restrict__ ctas, const unsigned *__restrict__ src,
+                                                    unsigned *__restrict__ rankvol) {
+    const MorphCta c = ctas[blockIdx.x];
+    const MorphBox B = boxes[c.box];
+    const int ev = B.ext[1], wpr = (B.ext[2] + 31) >> 5;
+    const long long words = (long long)B.ext[0] * ev * wpr;
+    const int lane = threadIdx.x & 31;
+    const long long w0 = (long long)c.base + (threadIdx.x >> 5) * 32;
+    if (w0 >= words) return;
+    const int nw = (int)min(32ll, words - w0);
+    const unsigned mine = lane < nw ? src[B.word0 + w0 + lane] : 0u;
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, mine != 0u);
+    while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const unsigned bits = __shfl_sync(0xFFFFFFFFu, mine, j);
+        const long long wi = w0 + j;
+        const int k = (int)(wi % wpr);
+        const long long r = wi / wpr;
+        apply_word(G, B, c.box, bits, (int)(r / ev), (int)(r % ev), k, lane, rankvol);
+    }
+}
+
+// background voxels covered by a closed mask take the id of the first such id in list order
+__global__ void __launch_bounds__(MT) k_morph_final(void *__restrict__ vol, MorphGeom G, const unsigned *__restrict__ rankvol,
+                                                    const MorphBox *__restrict__ boxes) {
+    const long long total = (long long)G.n[0] * G.n[1] * G.n[2];
+    for (long long i = (long long)blockIdx.x * MT + threadIdx.x; i < total; i += (long long)gridDim.x * MT) {
+        const unsigned r = rankvol[i];
+        if (r == NO_RANK) continue;
+        const long long w = i % G.n[2], q = i / G.n[2];
+        const long long a = (q / G.n[1]) * G.st[0] + (q % G.n[1]) * G.st[1] + w * G.st[2];
+        if (ld_label(vol, G.elem_bytes, a) != 0ull) continue;  // only background is ever written (cs_extraction_steps.py:460)
+        const unsigned long long id = boxes[r].id;
+        if (G.elem_bytes == 8) ((unsigned long long *)vol)[a] = id;
+        else ((unsigned *)vol)[a] = (unsigned)id;
+    }
+}
+
+struct Scratch {  // stream-ordered device scratch, released when the call returns
+    void *p = nullptr;
+    cudaStream_t s = nullptr;
+    ~Scratch() {
+        if (p) cudaFreeAsync(p, s);
+    }
+    cudaError_t alloc(size_t bytes, cudaStream_t st) {
+        syk_pool_keep_warm();
+        s = st;
+        return cudaMallocAsync(&p, bytes ? bytes : 16, st);
+    }
+};
+
+}  // namespace
+
+SYK_API int syk_close_contacts(void *cs_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3], const uint64_t *ids_host,
+                               const int32_t *bbox_host, uint64_t n_ids, int n_closings, int n_dilations, void *stream) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    SYK_CHECK_ARG(shape && strides, "NULL argument");
+    SYK_CHECK_ARG(n_closings >= 0 && n_dilations >= 0 && n_closings <= 64 && n_dilations <= 64, "iterations must be in 0..64");
+    SYK_CHECK_ARG(n_ids < 0xFFFFFFFFull, "too many ids");
+    if (n_ids == 0 || (n_closings == 0 && n_dilations == 0)) return SYK_OK;
+    SYK_CHECK_ARG(cs_dev && ids_host && bbox_host, "NULL argument");
+    for (int a = 0; a < 3; ++a) SYK_CHECK_ARG(shape[a] > 0 && shape[a] < (1ll << 30), "bad shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    // internal axes: u = slowest, w = memory-contiguous (bit-packing / coalescing axis)
+    int ax[3] = {0, 1, 2};
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j)
+            if (llabs(strides[ax[j]]) > llabs(strides[ax[i]])) {
+                const int t = ax[i];
+                ax[i] = ax[j];
+                ax[j] = t;
+            }
+    MorphGeom G;
+    for (int a = 0; a < 3; ++a) {
+        G.st[a] = strides[ax[a]];
+        G.n[a] = (int)shape[ax[a]];
+    }
+    G.elem_bytes = elem_bytes;
+
+    // test hooks: SYK_MORPH_SMALL lowers the shared-memory threshold (words), SYK_MORPH_BATCH the HBM batch size (words)
+    long long small_words = SMALL_WORDS;
+    if (const char *e = getenv("SYK_MORPH_SMALL")) {
+        const long long v = atoll(e);
+        if (v >= 0 && v < small_words) small_words = v;
+    }
+    std::vector<MorphBox> boxes(n_ids);
+    std::vector<unsigned> small;
+    std::vector<unsigned> tiny;
+    std::vector<unsigned> large;
+    for (uint64_t i = 0; i < n_ids; ++i) {
+        MorphBox &B = boxes[i];
+        B.id = ids_host[i];
+        B.word0 = 0;
+        SYK_CHECK_ARG(B.id != 0, "id 0 in the id list");
+        long long words = 1;
+        for (int a = 0; a < 3; ++a) {
+            const long long mn = bbox_host[i * 6 + ax[a]], mx = bbox_host[i * 6 + 3 + ax[a]];
+            SYK_CHECK_ARG(mn >= 0 && mn < mx && mx <= G.n[a], "bounding box outside the volume");
+            const long long lo = mn - n_closings < 0 ? 0 : mn - n_closings;              // cs_extraction_steps.py:443-444
+            const long long hi = mx + n_closings > G.n[a] ? G.n[a] : mx + n_closings;    // :445, clipped by the slice
+            B.lo[a] = (int)lo;
+            B.ext[a] = (int)(hi - lo);
+            B.ilo[a] = (int)(mn - lo);
+            B.ihi[a] = (int)(mx - lo);
+            words *= a == 2 ? (hi - lo + 31) / 32 : hi - lo;
+        }
+        const bool fits = words <= small_words && B.ext[0] < 8192 && B.ext[1] < 2048 && (B.ext[2] + 31) / 32 < 256;
+        (!fits ? large : words <= TINY_WORDS ? tiny : small).push_back((unsigned)i);
+    }
+    const long long nvox = (long long)G.n[0] * G.n[1] * G.n[2];
+    Scratch d_boxes, d_rank, d_small;
+    SYK_CUDA(d_rank.alloc((size_t)nvox * 4, s));
+    SYK_CUDA(cudaMemsetAsync(d_rank.p, 0xFF, (size_t)nvox * 4, s));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+    // large boxes in batches of at most BATCH_WORDS words per bit buffer
+    const unsigned long long BATCH_WORDS = getenv("SYK_MORPH_BATCH") ? strtoull(getenv("SYK_MORPH_BATCH"), nullptr, 10) : (1ull << 26);
+    size_t li = 0;
+    std::vector<MorphCta> ctas;
+    while (li < large.size()) {
+        unsigned long long total = 0;
+        ctas.clear();
+        size_t lj = li;
+        for (; lj < large.size(); ++lj) {
+            MorphBox &B = boxes[large[lj]];
+            const unsigned long long words = (unsigned long long)B.ext[0] * B.ext[1] * ((B.ext[2] + 31) / 32);
+            if (lj > li && total + words > BATCH_WORDS) break;
+            B.word0 = total;
+            total += words;
+            for (unsigned long long b = 0; b < words; b += MT) ctas.push_back(MorphCta{large[lj], (unsigned)b});
+        }
+        li = lj;
+        Scratch bx, ct, bufA, bufB;  // word0 is per batch: upload the boxes with this batch's offsets
+        SYK_CUDA(bx.alloc(boxes.size() * sizeof(MorphBox), s));
+        SYK_CUDA(cudaMemcpyAsync(bx.p, boxes.data(), boxes.size() * sizeof(MorphBox), cudaMemcpyHostToDevice, s));
+        SYK_CUDA(ct.alloc(ctas.size() * sizeof(MorphCta), s));
+        SYK_CUDA(cudaMemcpyAsync(ct.p, ctas.data(), ctas.size() * sizeof(MorphCta), cudaMemcpyHostToDevice, s));
+        SYK_CUDA(bufA.alloc(total * 4, s));
+        SYK_CUDA(bufB.alloc(total * 4, s));
+        const unsigned grid = (unsigned)ctas.size();
+        unsigned *a = (unsigned *)bufA.p, *b = (unsigned *)bufB.p;
+        const MorphBox *dbx = (const MorphBox *)bx.p;
+        const MorphCta *dct = (const MorphCta *)ct.p;
+        k_morph_build<<<grid, MT, 0, s>>>(cs_dev, G, dbx, dct, a);
+        for (int it = 0; it < 2 * n_closings + n_dilations; ++it) {
+            if (it >= n_closings && it < 2 * n_closings) k_morph_step<true><<<grid, MT, 0, s>>>(dbx, dct, a, b);
+            else k_morph_step<false><<<grid, MT, 0, s>>>(dbx, dct, a, b);
+            unsigned *t = a;
+            a = b;
+            b = t;
+        }
+        k_morph_apply<<<grid, MT, 0, s>>>(G, dbx, dct, a, (unsigned *)d_rank.p);
+        SYK_CUDA(cudaGetLastError());
+        SYK_CUDA(cudaStreamSynchronize(s));  // the host vectors of this batch are reused by the next one
+    }
+    SYK_CUDA(d_boxes.alloc(boxes.size() * sizeof(MorphBox), s));
+    SYK_CUDA(cudaMemcpyAsync(d_boxes.p, boxes.data(), boxes.size() * sizeof(MorphBox), cudaMemcpyHostToDevice, s));
+    if (!small.empty() || !tiny.empty()) {  // one index list: [tiny..., small...]
+        const size_t nt = tiny.size(), ns = small.size();
+        tiny.insert(tiny.end(), small.begin(), small.end());
+        SYK_CUDA(d_small.alloc(tiny.size() * sizeof(unsigned), s));
+        SYK_CUDA(cudaMemcpyAsync(d_small.p, tiny.data(), tiny.size() * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+        const unsigned *lst = (const unsigned *)d_small.p;
+        if (nt) {
+            const unsigned long long grid = nt < (unsigned long long)sms * 64 ? nt : (unsigned long long)sms * 64;
+            k_morph_small<TINY_WORDS, 128><<<(unsigned)grid, 128, 0, s>>>(cs_dev, G, (const MorphBox *)d_boxes.p, lst, (unsigned)nt, n_closings,
+                                                                          n_dilations, (unsigned *)d_rank.p);
+        }
+        if (ns) {
+            const unsigned long long grid = ns < (unsigned long long)sms * 16 ? ns : (unsigned long long)sms * 16;
+            k_morph_small<SMALL_WORDS, MT><<<(unsigned)grid, MT, 0, s>>>(cs_dev, G, (const MorphBox *)d_boxes.p, lst + nt, (unsigned)ns,
+                                                                         n_closings, n_dilations, (unsigned *)d_rank.p);
+        }
+        SYK_CUDA(cudaGetLastError());
+    }
+    k_morph_final<<<sms * 8, MT, 0, s>>>(cs_dev, G, (const unsigned *)d_rank.p, (const MorphBox *)d_boxes.p);
+    SYK_CUDA(cudaGetLastError());
+    SYK_CUDA(cudaStreamSynchronize(s));  // `boxes` / `small` are pageable host memory owned by this call
+    return SYK_OK;
+}

@@ -200,6 +200,18 @@ def detect_seg_boundaries(arr, stream=None):
     return out
 
 
+def close_contacts(cs, ids, bbox, n_closings=6, cs_dilation=2, stream=None):
+    """syk_close_contacts on a CUDA contact volume (in place): ``ids`` uint64 [n] and ``bbox`` int32 [n, 2, 3]
+    (min, exclusive max) are HOST arrays in processing order (cs_extraction_steps.py:439-461)."""
+    import numpy as np
+    ids = np.ascontiguousarray(ids, np.uint64)
+    bbox = np.ascontiguousarray(bbox, np.int32).reshape(-1, 2, 3)
+    assert len(ids) == len(bbox)
+    check(_lib.load().syk_close_contacts(cs.data_ptr(), _elem_bytes(cs), i64(cs.shape), i64(_strides(cs)), ids.ctypes.data,
+                                         bbox.ctypes.data, len(ids), int(n_closings), int(cs_dilation), _stream_ptr(stream)))
+    return cs
+
+
 def synth_labels(shape, origin=(0, 0, 0), pitch=(32, 32, 16), warp_amp=4, seed=0, kind=0, density16=1,
                  dtype=torch.int64, order="C", out=None, stream=None):
     """Device twin of ``syconn_b200.synth.synth_labels`` (bit-identical)."""

@@ -321,3 +321,56 @@ def test_cs64_variants(mods, golden64):
     assert fop.find_object_properties_cs_64bit(np.zeros((3, 3, 3, 2), np.uint64)) == ({}, {}, {})
     with pytest.raises(NotImplementedError):
         fop.detect_contact_partners(noise, None, np.array([(-1, 2), (-1, 1), (-1, 1)]))
+
+
+def test_close_contact_sites(mods, monkeypatch):
+    """"next" row f2: the per-contact closing / dilation loop (cs_extraction_steps.py:439-461) against the oracle's
+    literal restatement, in the same id order; shared-memory path, HBM path and HBM batches."""
+    from syconn_b200.extraction.cs_extraction_steps import close_contact_sites
+    oracle, fop = mods["oracle"], mods["fop"]
+    seg = mods["synth"]((64, 60, 52), pitch=(14, 12, 8), warp_amp=3, seed=1, dtype=np.uint32)
+    cs = oracle.detect_cs(seg, (7, 7, 3))
+    bb = oracle.find_object_properties(cs)[1]
+    rng = np.random.default_rng(0)
+    keys = list(bb)
+    rng.shuffle(keys)
+    bb_shuffled = {k: bb[k] for k in keys}
+    for n_close, n_dil in ((3, 2), (6, 2), (0, 2), (2, 0), (1, 1)):
+        for order in (bb, bb_shuffled):
+            want = oracle.close_contact_sites(cs.copy(), order, n_close, n_dil)
+            got = close_contact_sites(cs.copy(), order, n_close, n_dil)
+            assert np.array_equal(got, want), (n_close, n_dil)
+    want = oracle.close_contact_sites(cs.copy(), bb, 3, 2)
+    assert (want != cs).sum() > 1000                                   # the closing does fill gaps in this volume
+    assert np.array_equal(oracle.close_contact_sites(cs.copy(), bb, 3, 2, use_scipy=True), want)
+    # memory layouts: x-fastest (production), a non-dense view
+    csF = np.asfortranarray(cs)
+    assert np.array_equal(close_contact_sites(csF, bb, 3, 2), want) and csF.flags.f_contiguous
+    wide = np.zeros((cs.shape[0], cs.shape[1], cs.shape[2] + 3), np.uint64)
+    wide[:, :, :-3] = cs
+    assert np.array_equal(close_contact_sites(wide[:, :, :-3], bb, 3, 2), want) and np.array_equal(wide[:, :, :-3], want)
+    # defaults from the config (n_closings = max(cs_filtersize // 2) = 6, cs_dilation = 2), boxes from the library itself
+    got = close_contact_sites(cs.copy())
+    assert np.array_equal(got, oracle.close_contact_sites(cs.copy(), {k: bb[k] for k in sorted(bb)}, 6, 2))
+    # HBM path (boxes above the shared-memory threshold) in several batches
+    monkeypatch.setenv("SYK_MORPH_SMALL", "64")
+    monkeypatch.setenv("SYK_MORPH_BATCH", "5000")
+    assert np.array_equal(close_contact_sites(cs.copy(), bb_shuffled, 3, 2), oracle.close_contact_sites(cs.copy(), bb_shuffled, 3, 2))
+    monkeypatch.setenv("SYK_MORPH_SMALL", "0")
+    assert np.array_equal(close_contact_sites(np.asfortranarray(cs), bb, 6, 2), oracle.close_contact_sites(cs.copy(), bb, 6, 2))
+    monkeypatch.delenv("SYK_MORPH_SMALL")
+    monkeypatch.delenv("SYK_MORPH_BATCH")
+    # one object spanning the whole volume with holes (box wider than one 32-voxel word, clipped on every side), uint32
+    big = (rng.random((40, 37, 100)) < 0.15).astype(np.uint32) * np.uint32(7)
+    big[5:9, 5:9, 40:60] = 9
+    bbb = oracle.find_object_properties(big)[1]
+    assert np.array_equal(close_contact_sites(big.copy(), bbb, 2, 1), oracle.close_contact_sites(big.copy(), bbb, 2, 1))
+    # ids >= 2^63 and the no-op cases
+    hi = cs.copy()
+    hi[hi != 0] |= np.uint64(1) << np.uint64(63)
+    bbh = oracle.find_object_properties(hi)[1]
+    assert np.array_equal(close_contact_sites(hi.copy(), bbh, 2, 1), oracle.close_contact_sites(hi.copy(), bbh, 2, 1))
+    assert np.array_equal(close_contact_sites(cs.copy(), bb, 0, 0), cs)
+    assert np.array_equal(close_contact_sites(cs.copy(), {}, 3, 2), cs)
+    z = np.zeros((4, 4, 4), np.uint64)
+    assert not close_contact_sites(z).any()

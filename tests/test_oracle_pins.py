@@ -173,3 +173,23 @@ def test_oracle_vs_golden_cs64(golden64):
         sample, lo, hi = gen_sample_seg(np.array(d), STENCIL, 5)
         out = oracle.detect_cs_64bit(sample.astype(np.uint64), tuple(STENCIL))
         assert np.array_equal(out[..., 0], lo) and np.array_equal(out[..., 1], hi)
+
+
+def test_oracle_closing_vs_scipy():
+    """f2: the restated binary closing / dilation equals scipy.ndimage (the reference's call, cs_extraction_steps.py:451-458)
+    on random masks, and the restated worker loop equals the literal one."""
+    ndi = pytest.importorskip("scipy.ndimage")
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        shp = tuple(int(v) for v in rng.integers(1, 14, size=3))
+        m = rng.random(shp) < rng.choice([0.05, 0.3, 0.7])
+        n, d = int(rng.integers(0, 7)), int(rng.integers(0, 3))
+        want = ndi.binary_closing(m, iterations=n) if n > 0 else m
+        if d > 0:
+            want = ndi.binary_dilation(want, iterations=d)
+        assert np.array_equal(oracle.binary_closing_dilation(m, n, d), want), (shp, n, d)
+    seg = synth_labels((40, 36, 30), pitch=(12, 10, 7), warp_amp=3, seed=2, dtype=np.uint32)
+    cs = oracle.detect_cs(seg, (5, 5, 3))
+    bb = oracle.find_object_properties(cs)[1]
+    a = oracle.close_contact_sites(cs.copy(), bb, 3, 2, use_scipy=True)
+    assert np.array_equal(a, oracle.close_contact_sites(cs.copy(), bb, 3, 2)) and (a != cs).any()
