@@ -25,7 +25,8 @@ namespace {
 
 constexpr int MT = 256;              // threads per CTA
 constexpr int SMALL_WORDS = 6144;    // 2 buffers x 24 KB of shared memory, 256 threads
-constexpr int TINY_WORDS = 1024;     // 2 buffers x 4 KB, 128 threads: the typical contact
+constexpr int MID_WORDS = 3072;      // 2 buffers x 12 KB, 256 threads
+constexpr int TINY_WORDS = 1024;     // 2 buffers x 4 KB, 128 threads: the typical contact (sizes include the zero halo)
 constexpr unsigned NO_RANK = 0xFFFFFFFFu;
 
 struct MorphBox {  // 64 bytes
@@ -94,23 +95,35 @@ __device__ __forceinline__ void apply_word(const MorphGeom &G, const MorphBox &B
 }
 
 // ---- small boxes: everything in one launch, bit buffers in shared memory ---------------------------------------------------
-// WORDS = capacity of one bit buffer, NT = threads per CTA.  Two size classes are instantiated so that the typical contact
-// (a few hundred words) runs with many CTAs per SM.
-template <int WORDS, int NT>
+// WORDS = capacity of one bit buffer, NT = threads per CTA, WPR1 = every row of the box is a single word (box at most 32
+// voxels wide along w).  The buffers carry a zero halo of one row / plane along v and u, so a step is five (WPR1) or
+// seven loads without any bounds test.  Size classes are instantiated so that the typical contact (a few hundred words)
+// runs with many CTAs per SM.
+template <int WORDS, int NT, bool WPR1>
 __global__ void __launch_bounds__(NT) k_morph_small(const void *__restrict__ vol, MorphGeom G, const MorphBox *__restrict__ boxes,
                                                     const unsigned *__restrict__ list, unsigned nlist, int n_close, int n_dil,
                                                     unsigned *__restrict__ rankvol) {
     __shared__ unsigned buf[2][WORDS];
-    constexpr int PRE = 4;  // rounds of the step loop whose word coordinates are kept in registers
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (unsigned bi = blockIdx.x; bi < nlist; bi += gridDim.x) {
         const unsigned rank = list[bi];
         const MorphBox B = boxes[rank];
         const int eu = B.ext[0], ev = B.ext[1], ew = B.ext[2];
-        const int wpr = (ew + 31) >> 5;
-        const int words = eu * ev * wpr;
+        const int wpr = WPR1 ? 1 : (ew + 31) >> 5;
+        const int rowp = wpr, planep = (ev + 2) * wpr;  // pitches of the haloed layout
+        const int words = eu * ev * wpr, padded = (eu + 2) * planep;
+        auto index_of = [&](int wi, int &u, int &v, int &k) {  // interior word wi -> coordinates and buffer index
+            k = WPR1 ? 0 : wi % wpr;
+            const int r = WPR1 ? wi : wi / wpr;
+            v = r % ev;
+            u = r / ev;
+            return (u + 1) * planep + (v + 1) * rowp + k;
+        };
         __syncthreads();  // the previous box is done with the buffers
-        for (int i = tid; i < words; i += NT) buf[0][i] = 0u;
+        for (int i = tid; i < padded; i += NT) {
+            buf[0][i] = 0u;
+            buf[1][i] = 0u;
+        }
         __syncthreads();
         // mask of the id: only the rows of its own bounding box can hold voxels; four words (loads) in flight per warp
         {
@@ -129,7 +142,7 @@ __global__ void __launch_bounds__(NT) k_morph_small(const void *__restrict__ vol
                         const int k = k0 + i % nk, r = i / nk;
                         const int v = B.ilo[1] + r % iv, u = B.ilo[0] + r / iv;
                         const int w = k * 32 + lane;
-                        dst[j] = (u * ev + v) * wpr + k;
+                        dst[j] = (u + 1) * planep + (v + 1) * rowp + k;
                         if (w >= B.ilo[2] && w < B.ihi[2])
                             hit[j] = ld_label(vol, G.elem_bytes, (long long)(B.lo[0] + u) * G.st[0] + (long long)(B.lo[1] + v) * G.st[1] +
                                                                      (long long)(B.lo[2] + w) * G.st[2]) == B.id;
@@ -142,47 +155,56 @@ __global__ void __launch_bounds__(NT) k_morph_small(const void *__restrict__ vol
                 }
             }
         }
-        int pos[PRE];  // (u << 19) | (v << 8) | k of the word handled in round q (host: ext_u < 8192, ext_v < 2048, wpr < 256)
-#pragma unroll
-        for (int q = 0; q < PRE; ++q) {
-            const int wi = tid + q * NT;
-            const int k = wi % wpr, r = wi / wpr;
-            pos[q] = ((r / ev) << 19) | ((r % ev) << 8) | k;
-        }
+        // step loop: a thread owns a column (v, k) and a contiguous range of planes u; marching along u keeps the words
+        // below / at the current plane in registers (three loads per word when the row is a single word)
+        const int ncol = ev * wpr;
+        const int ncolp = ncol < NT ? ncol : NT;       // columns handled concurrently
+        const int nph = NT / ncolp;                    // plane ranges per column
+        const int ulen = (eu + nph - 1) / nph;
+        const int c0 = tid % ncolp, ph = tid / ncolp;
+        const int u_beg = ph * ulen, u_end = ph < nph ? min(eu, u_beg + ulen) : 0;
         __syncthreads();
         int cur = 0;
         const int steps = 2 * n_close + n_dil;
+        const unsigned last_valid = valid_bits(wpr - 1, ew);
         for (int s = 0; s < steps; ++s) {
             const bool erode = s >= n_close && s < 2 * n_close;
             const unsigned *src = buf[cur];
             unsigned *dstb = buf[cur ^ 1];
-#pragma unroll
-            for (int q = 0; q < PRE; ++q) {
-                const int wi = tid + q * NT;
-                if (wi < words) {
-                    const int u = (int)((unsigned)pos[q] >> 19), v = (pos[q] >> 8) & 0x7FF, k = pos[q] & 0xFF;
-                    dstb[wi] = erode ? morph_word<true>(src, u, v, k, eu, ev, wpr, 0u) : morph_word<false>(src, u, v, k, eu, ev, wpr, valid_bits(k, ew));
+            for (int c = c0; c < ncol && u_beg < u_end; c += ncolp) {  // one round unless the box has more than NT columns
+                const int k = WPR1 ? 0 : c % wpr, v = WPR1 ? c : c / wpr;
+                int idx = (u_beg + 1) * planep + (v + 1) * rowp + k;
+                const unsigned vmask = (k + 1 == wpr) ? last_valid : 0xFFFFFFFFu;
+                unsigned um = src[idx - planep], cc = src[idx];
+                for (int u = u_beg; u < u_end; ++u, idx += planep) {
+                    const unsigned up = src[idx + planep], vm = src[idx - rowp], vp = src[idx + rowp];
+                    unsigned wl, wr;
+                    if (WPR1) {
+                        wl = cc << 1;
+                        wr = cc >> 1;
+                    } else {
+                        wl = __funnelshift_l(k > 0 ? src[idx - 1] : 0u, cc, 1);
+                        wr = __funnelshift_r(cc, k + 1 < wpr ? src[idx + 1] : 0u, 1);
+                    }
+                    dstb[idx] = erode ? (cc & wl & wr & vm & vp & um & up) : ((cc | wl | wr | vm | vp | um | up) & vmask);
+                    um = cc;
+                    cc = up;
                 }
-            }
-            for (int wi = tid + PRE * NT; wi < words; wi += NT) {
-                const int k = wi % wpr, r = wi / wpr;
-                const int v = r % ev, u = r / ev;
-                dstb[wi] = erode ? morph_word<true>(src, u, v, k, eu, ev, wpr, 0u) : morph_word<false>(src, u, v, k, eu, ev, wpr, valid_bits(k, ew));
             }
             cur ^= 1;
             __syncthreads();
         }
         for (int w0 = warp * 32; w0 < words; w0 += NT) {
-            const int nw = min(32, words - w0);
-            const unsigned mine = lane < nw ? buf[cur][w0 + lane] : 0u;
+            int mu = 0, mv = 0, mk = 0;
+            unsigned mine = 0u;
+            if (w0 + lane < words) mine = buf[cur][index_of(w0 + lane, mu, mv, mk)];
             unsigned todo = __ballot_sync(0xFFFFFFFFu, mine != 0u);
             while (todo) {
                 const int j = __ffs(todo) - 1;
                 todo &= todo - 1u;
                 const unsigned bits = __shfl_sync(0xFFFFFFFFu, mine, j);
-                const int wi = w0 + j;
-                const int k = wi % wpr, r = wi / wpr;
-                apply_word(G, B, rank, bits, r / ev, r % ev, k, lane, rankvol);
+                const int u = __shfl_sync(0xFFFFFFFFu, mu, j), v = __shfl_sync(0xFFFFFFFFu, mv, j), k = __shfl_sync(0xFFFFFFFFu, mk, j);
+                apply_word(G, B, rank, bits, u, v, k, lane, rankvol);
             }
         }
     }
@@ -314,15 +336,13 @@ SYK_API int syk_close_contacts(void *cs_dev, int elem_bytes, const int64_t shape
         if (v >= 0 && v < small_words) small_words = v;
     }
     std::vector<MorphBox> boxes(n_ids);
-    std::vector<unsigned> small;
-    std::vector<unsigned> tiny;
+    std::vector<unsigned> cls[6];  // shared-memory classes: {tiny, mid, small} x {one word per row, several}
     std::vector<unsigned> large;
     for (uint64_t i = 0; i < n_ids; ++i) {
         MorphBox &B = boxes[i];
         B.id = ids_host[i];
         B.word0 = 0;
         SYK_CHECK_ARG(B.id != 0, "id 0 in the id list");
-        long long words = 1;
         for (int a = 0; a < 3; ++a) {
             const long long mn = bbox_host[i * 6 + ax[a]], mx = bbox_host[i * 6 + 3 + ax[a]];
             SYK_CHECK_ARG(mn >= 0 && mn < mx && mx <= G.n[a], "bounding box outside the volume");
@@ -332,10 +352,11 @@ SYK_API int syk_close_contacts(void *cs_dev, int elem_bytes, const int64_t shape
             B.ext[a] = (int)(hi - lo);
             B.ilo[a] = (int)(mn - lo);
             B.ihi[a] = (int)(mx - lo);
-            words *= a == 2 ? (hi - lo + 31) / 32 : hi - lo;
         }
-        const bool fits = words <= small_words && B.ext[0] < 8192 && B.ext[1] < 2048 && (B.ext[2] + 31) / 32 < 256;
-        (!fits ? large : words <= TINY_WORDS ? tiny : small).push_back((unsigned)i);
+        const long long wpr = (B.ext[2] + 31) / 32;
+        const long long padded = (long long)(B.ext[0] + 2) * (B.ext[1] + 2) * wpr;  // with the zero halo along u and v
+        if (padded > small_words) large.push_back((unsigned)i);
+        else cls[(padded <= TINY_WORDS ? 0 : padded <= MID_WORDS ? 2 : 4) + (wpr == 1 ? 0 : 1)].push_back((unsigned)i);
     }
     const long long nvox = (long long)G.n[0] * G.n[1] * G.n[2];
     Scratch d_boxes, d_rank, d_small;
@@ -387,23 +408,35 @@ SYK_API int syk_close_contacts(void *cs_dev, int elem_bytes, const int64_t shape
     }
     SYK_CUDA(d_boxes.alloc(boxes.size() * sizeof(MorphBox), s));
     SYK_CUDA(cudaMemcpyAsync(d_boxes.p, boxes.data(), boxes.size() * sizeof(MorphBox), cudaMemcpyHostToDevice, s));
-    if (!small.empty() || !tiny.empty()) {  // one index list: [tiny..., small...]
-        const size_t nt = tiny.size(), ns = small.size();
-        tiny.insert(tiny.end(), small.begin(), small.end());
-        SYK_CUDA(d_small.alloc(tiny.size() * sizeof(unsigned), s));
-        SYK_CUDA(cudaMemcpyAsync(d_small.p, tiny.data(), tiny.size() * sizeof(unsigned), cudaMemcpyHostToDevice, s));
-        const unsigned *lst = (const unsigned *)d_small.p;
-        if (nt) {
-            const unsigned long long grid = nt < (unsigned long long)sms * 64 ? nt : (unsigned long long)sms * 64;
-            k_morph_small<TINY_WORDS, 128><<<(unsigned)grid, 128, 0, s>>>(cs_dev, G, (const MorphBox *)d_boxes.p, lst, (unsigned)nt, n_closings,
-                                                                          n_dilations, (unsigned *)d_rank.p);
+    {
+        std::vector<unsigned> all;
+        size_t first[7] = {0};
+        for (int c = 0; c < 6; ++c) {
+            all.insert(all.end(), cls[c].begin(), cls[c].end());
+            first[c + 1] = all.size();
         }
-        if (ns) {
-            const unsigned long long grid = ns < (unsigned long long)sms * 16 ? ns : (unsigned long long)sms * 16;
-            k_morph_small<SMALL_WORDS, MT><<<(unsigned)grid, MT, 0, s>>>(cs_dev, G, (const MorphBox *)d_boxes.p, lst + nt, (unsigned)ns,
-                                                                         n_closings, n_dilations, (unsigned *)d_rank.p);
+        if (!all.empty()) {
+            SYK_CUDA(d_small.alloc(all.size() * sizeof(unsigned), s));
+            SYK_CUDA(cudaMemcpyAsync(d_small.p, all.data(), all.size() * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+            const unsigned *lst = (const unsigned *)d_small.p;
+            const MorphBox *dbx = (const MorphBox *)d_boxes.p;
+            unsigned *rk = (unsigned *)d_rank.p;
+#define SYK_MORPH_LAUNCH(c, WORDS, NT, WPR1, PER_SM)                                                                              \
+    if (first[c + 1] > first[c]) {                                                                                               \
+        const unsigned long long n = first[c + 1] - first[c];                                                                    \
+        const unsigned long long grid = n < (unsigned long long)sms * PER_SM ? n : (unsigned long long)sms * PER_SM;             \
+        k_morph_small<WORDS, NT, WPR1><<<(unsigned)grid, NT, 0, s>>>(cs_dev, G, dbx, lst + first[c], (unsigned)n, n_closings,     \
+                                                                     n_dilations, rk);                                           \
+    }
+            SYK_MORPH_LAUNCH(0, TINY_WORDS, 128, true, 64)
+            SYK_MORPH_LAUNCH(1, TINY_WORDS, 128, false, 64)
+            SYK_MORPH_LAUNCH(2, MID_WORDS, 256, true, 32)
+            SYK_MORPH_LAUNCH(3, MID_WORDS, 256, false, 32)
+            SYK_MORPH_LAUNCH(4, SMALL_WORDS, MT, true, 16)
+            SYK_MORPH_LAUNCH(5, SMALL_WORDS, MT, false, 16)
+#undef SYK_MORPH_LAUNCH
+            SYK_CUDA(cudaGetLastError());
         }
-        SYK_CUDA(cudaGetLastError());
     }
     k_morph_final<<<sms * 8, MT, 0, s>>>(cs_dev, G, (const unsigned *)d_rank.p, (const MorphBox *)d_boxes.p);
     SYK_CUDA(cudaGetLastError());

@@ -200,6 +200,28 @@ def detect_seg_boundaries(arr, stream=None):
     return out
 
 
+def extract_cs_syntype(table, cs, syn, asym, sym, max_vox=None, origin=(0, 0, 0), chunk_seq=0, stream=None):
+    """syk_extract_cs_syntype on CUDA tensors (any strides, e.g. cropped views): contact-site props go to ``table``, the
+    synaptic voxel tuples are returned as an int64 tensor [n, 4] (``syk_synvox_t`` rows: id, lin, flags, pad).
+    Synchronises (the tuple count is read back; the call is repeated once when ``max_vox`` was too small -- ``table``
+    must then be cleared by the caller, so pass an empty table)."""
+    for m in (syn, asym, sym):
+        assert m.dtype == torch.uint8 and tuple(m.shape) == tuple(cs.shape)
+    L = _lib.load()
+    n_max = int(max_vox) if max_vox else cs.numel() // 16 + 4096
+    while True:
+        vox = torch.empty((n_max, 4), dtype=torch.int64, device=cs.device)
+        counter = torch.zeros(2, dtype=torch.int64, device=cs.device)
+        check(L.syk_extract_cs_syntype(table.h, cs.data_ptr(), _elem_bytes(cs), i64(cs.shape), i64(_strides(cs)), syn.data_ptr(),
+                                       i64(_strides(syn)), asym.data_ptr(), i64(_strides(asym)), sym.data_ptr(), i64(_strides(sym)),
+                                       i64(origin), int(chunk_seq), vox.data_ptr(), n_max, counter.data_ptr(), _stream_ptr(stream)))
+        n = int(counter[0].item())
+        if n <= n_max:
+            return vox[:n]
+        table.clear(stream)
+        n_max = n
+
+
 def close_contacts(cs, ids, bbox, n_closings=6, cs_dilation=2, stream=None):
     """syk_close_contacts on a CUDA contact volume (in place): ``ids`` uint64 [n] and ``bbox`` int32 [n, 2, 3]
     (min, exclusive max) are HOST arrays in processing order (cs_extraction_steps.py:439-461)."""

@@ -63,6 +63,39 @@ def pairs_to_dict(pairs):
     return out
 
 
+def syntype_to_dicts(cs_records, v, shape, offset):
+    """contact-site records + synaptic voxel tuples (``syk_synvox_t``) of one ``extract_cs_syntype`` call -> the reference's
+    return value ``[rc, bb, size], [rc_syn, bb_syn, size_syn], cs_asym, cs_sym, voxels_syn``
+    (block_processing_C.pyx:119-158): per id the synaptic voxels in scan order with ``offset`` added, their bounding box,
+    first voxel and count, and the number of them with ``asym_mask == 1`` / ``sym_mask == 1``."""
+    cs_props = records_to_dicts(cs_records)
+    rc_syn, bb_syn, size_syn, cs_asym, cs_sym, voxels = {}, {}, {}, {}, {}, {}
+    if len(v):
+        v = v[np.lexsort((v["lin"], v["id"]))]                   # per id, reference scan order
+        sy, sz = int(shape[1]), int(shape[2])
+        lin = v["lin"].astype(np.int64)
+        xyz = np.stack([lin // (sy * sz), (lin // sz) % sy, lin % sz], axis=1)
+        ids, start = np.unique(v["id"], return_index=True)
+        end = np.append(start[1:], len(v))
+        mn = np.minimum.reduceat(xyz, start, axis=0)
+        mx = np.maximum.reduceat(xyz, start, axis=0) + 1
+        n_asym = np.add.reduceat((v["flags"] & 1).astype(np.int64), start)
+        n_sym = np.add.reduceat(((v["flags"] >> 1) & 1).astype(np.int64), start)
+        off = np.array([int(offset[0]), int(offset[1]), int(offset[2])], np.int64)
+        shifted = (xyz + off).tolist()
+        for i, k in enumerate(ids.tolist()):
+            s, e = int(start[i]), int(end[i])
+            rc_syn[k] = xyz[s].tolist()
+            bb_syn[k] = [mn[i].tolist(), mx[i].tolist()]
+            size_syn[k] = e - s
+            voxels[k] = shifted[s:e]
+            if n_asym[i]:
+                cs_asym[k] = int(n_asym[i])
+            if n_sym[i]:
+                cs_sym[k] = int(n_sym[i])
+    return [cs_props[0], cs_props[1], cs_props[2]], [rc_syn, bb_syn, size_syn], cs_asym, cs_sym, voxels
+
+
 def find_object_properties_records(chunk, capacity_hint=0):
     chunk = dense_view(check_label_array(chunk, "chunk", 3))
     L = _lib.load()

@@ -41,7 +41,7 @@ def extract_cs_syntype(cs_seg, syn_mask, asym_mask, sym_mask, offset):
     list (scan order, ``offset`` added).  Returns
     ``[rc, bb, size], [rc_syn, bb_syn, size_syn], cs_asym, cs_sym, voxels_syn`` like the reference."""
     import ctypes as C
-    from ._host import check_label_array, records_to_dicts
+    from ._host import check_label_array, syntype_to_dicts
     cs_seg = check_label_array(cs_seg, "cs_seg", 3)
     masks = []
     for name, m in (("syn_mask", syn_mask), ("asym_mask", asym_mask), ("sym_mask", sym_mask)):
@@ -57,33 +57,8 @@ def extract_cs_syntype(cs_seg, syn_mask, asym_mask, sym_mask, offset):
         cs_seg.ctypes.data, cs_seg.itemsize, _lib.i64(cs_seg.shape), _lib.i64(estrides(cs_seg)),
         masks[0].ctypes.data, _lib.i64(estrides(masks[0])), masks[1].ctypes.data, _lib.i64(estrides(masks[1])),
         masks[2].ctypes.data, _lib.i64(estrides(masks[2])), C.byref(rec), C.byref(n_rec), C.byref(vox), C.byref(n_vox)))
-    cs_props = records_to_dicts(_lib.take_array(rec.value, n_rec.value, _lib.RECORD_DTYPE))
-    v = _lib.take_array(vox.value, n_vox.value, _lib.SYNVOX_DTYPE)
-    rc_syn, bb_syn, size_syn, cs_asym, cs_sym, voxels = {}, {}, {}, {}, {}, {}
-    if len(v):
-        v = v[np.lexsort((v["lin"], v["id"]))]                   # per id, reference scan order
-        sy, sz = cs_seg.shape[1], cs_seg.shape[2]
-        lin = v["lin"].astype(np.int64)
-        xyz = np.stack([lin // (sy * sz), (lin // sz) % sy, lin % sz], axis=1)
-        ids, start = np.unique(v["id"], return_index=True)
-        end = np.append(start[1:], len(v))
-        mn = np.minimum.reduceat(xyz, start, axis=0)
-        mx = np.maximum.reduceat(xyz, start, axis=0) + 1
-        n_asym = np.add.reduceat((v["flags"] & 1).astype(np.int64), start)
-        n_sym = np.add.reduceat(((v["flags"] >> 1) & 1).astype(np.int64), start)
-        off = np.array([int(offset[0]), int(offset[1]), int(offset[2])], np.int64)
-        shifted = (xyz + off).tolist()
-        for i, k in enumerate(ids.tolist()):
-            s, e = int(start[i]), int(end[i])
-            rc_syn[k] = xyz[s].tolist()
-            bb_syn[k] = [mn[i].tolist(), mx[i].tolist()]
-            size_syn[k] = e - s
-            voxels[k] = shifted[s:e]
-            if n_asym[i]:
-                cs_asym[k] = int(n_asym[i])
-            if n_sym[i]:
-                cs_sym[k] = int(n_sym[i])
-    return [cs_props[0], cs_props[1], cs_props[2]], [rc_syn, bb_syn, size_syn], cs_asym, cs_sym, voxels
+    return syntype_to_dicts(_lib.take_array(rec.value, n_rec.value, _lib.RECORD_DTYPE),
+                            _lib.take_array(vox.value, n_vox.value, _lib.SYNVOX_DTYPE), cs_seg.shape, offset)
 
 
 def kernel(chunk, center_id):

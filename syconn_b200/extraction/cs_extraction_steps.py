@@ -42,3 +42,85 @@ def close_contact_sites(contacts, bb_dc=None, n_closings=None, cs_dilation=None)
     if work is not contacts:        # non-dense view: the work copy goes back into the caller's array
         contacts[...] = work
     return contacts
+
+
+def _to_device(a, dtype_view=None):
+    """dense NumPy view -> CUDA tensor with the same strides (``zyx.swapaxes(0, 2)`` stays x-fastest on the device)."""
+    import torch
+    a = dense_view(np.asarray(a))
+    if dtype_view is not None:
+        a = a.view(dtype_view)
+    return torch.from_numpy(a).cuda()
+
+
+def contact_site_extraction_chunk(data, sj_d, asym_d, sym_d, offset, cs_filtersize=None, cs_dilation=None):
+    """Numeric body of one iteration of the chunk loop of ``_contact_site_extraction_thread``
+    (syconn/extraction/cs_extraction_steps.py:381-486), device resident between the stages:
+
+      ``detect_cs(data)`` (:391) -> ``find_object_properties(contacts)`` (:439) -> per-id closing / dilation
+      (:440-461) -> ``extract_cs_syntype`` on the volumes cropped by ``overlap`` (:465-470) -> contact-site and
+      synapse segmentations of the chunk (:472-479).
+
+    ``data``: uint32 cell supervoxels, block ``size + 2 * overlap + 2 * stencil_offset`` loaded at
+    ``offset - stencil_offset`` (:385-387); ``sj_d`` / ``asym_d`` / ``sym_d``: uint8 masks of the block ``size + 2 *
+    overlap`` at ``offset`` (:394-434); ``offset`` = ``chunk.coordinates - overlap`` (:382).  Ids are closed in ascending
+    id order.  Returns ``(curr_cs_p, curr_syn_p, asym_cnt, sym_cnt, curr_syn_vx, cs_seg, syn_seg)``: the five results of
+    ``extract_cs_syntype`` plus the cropped contact-site volume and its intersection with ``sj_d`` (XYZ, uint64) that the
+    worker writes to the ``cs`` / ``syn`` KnossosDatasets."""
+    import torch
+    from .. import device as dev
+    from ._host import syntype_to_dicts
+    st = np.array(global_params.config['cell_objects']['cs_filtersize'] if cs_filtersize is None else cs_filtersize)
+    assert np.sum(st % 2) == 3
+    if cs_dilation is None:
+        cs_dilation = int(global_params.config['cell_objects']['cs_dilation'])
+    overlap = int(max(st // 2))
+    data = np.asarray(data)
+    if data.dtype != np.uint32:
+        raise ValueError(f"Buffer dtype mismatch, expected 'uint32_t' but got '{data.dtype}' (data)")
+    oshape = tuple(int(data.shape[i] - st[i] + 1) for i in range(3))
+    masks = []
+    for name, m in (("sj_d", sj_d), ("asym_d", asym_d), ("sym_d", sym_d)):
+        m = np.asarray(m)
+        if m.dtype != np.uint8:
+            raise ValueError(f"Buffer dtype mismatch, expected 'uint8_t' but got '{m.dtype}' ({name})")
+        assert m.shape == oshape, f"{name} must have the shape of the contact volume {oshape}, got {m.shape}"
+        masks.append(_to_device(m))
+    assert min(oshape) > 2 * overlap, "block smaller than the overlap"
+    seg = _to_device(data, np.int32)
+    contacts = dev.detect_cs(seg, [int(s) for s in st])
+    del seg
+    tab = dev.IdTable(max(1 << 16, contacts.numel() // 64))
+    try:
+        while True:  # bounding boxes of the contact ids (retry with a larger table on overflow)
+            dev.find_object_properties(tab, contacts)
+            n, ovf = tab.count()
+            if not ovf:
+                break
+            tab.close()
+            tab = dev.IdTable(tab.capacity * 4)
+        rec = dev.records_numpy(tab.export(dev.geoms([[0, 0, 0]], [list(oshape)])))
+        rec = rec[np.argsort(rec["id"])]
+        if len(rec):
+            dev.close_contacts(contacts, rec["id"].copy(), np.stack([rec["bb_min"], rec["bb_max"]], axis=1).astype(np.int32),
+                               overlap, cs_dilation)
+        crop = (slice(overlap, -overlap),) * 3
+        cs_c = contacts[crop]
+        tab.clear()
+        cshape = tuple(cs_c.shape)
+        while True:
+            vox = dev.extract_cs_syntype(tab, cs_c, masks[0][crop], masks[1][crop], masks[2][crop])
+            n, ovf = tab.count()
+            if not ovf:
+                break
+            tab.close()
+            tab = dev.IdTable(tab.capacity * 4)
+        cs_rec = dev.records_numpy(tab.export(dev.geoms([[0, 0, 0]], [list(cshape)])))
+    finally:
+        tab.close()
+    v = vox.cpu().numpy().view(_lib.SYNVOX_DTYPE).reshape(-1)
+    off = np.asarray(offset, np.int64) + overlap                       # :470
+    res = syntype_to_dicts(cs_rec, v, cshape, off)
+    cs_seg = cs_c.cpu().numpy().view(np.uint64)
+    syn_seg = torch.where(masks[0][crop] != 0, cs_c, torch.zeros_like(cs_c)).cpu().numpy().view(np.uint64)   # :476
+    return res[0], res[1], res[2], res[3], res[4], cs_seg, syn_seg

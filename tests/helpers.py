@@ -73,3 +73,18 @@ def check_cs64_against_golden(detect_cs_64bit, find_props_64bit, g):
         got = pair_props_to_arrays(find_props_64bit(vol))
         for name, a in zip(("keys", "sizes", "bbox", "rep"), got):
             assert np.array_equal(a, g[f"props_{tag}_{name}"]), f"{tag}: {name} differ"
+
+
+def reference_contact_site_chunk(oracle, data, sj_d, asym_d, sym_d, offset, stencil, cs_dilation):
+    """The chunk-loop body of _contact_site_extraction_thread (cs_extraction_steps.py:381-486) composed from the oracle's
+    restatements; ids are closed in ascending order (the reference's order is its hash-map order)."""
+    overlap = int(max(np.array(stencil) // 2))
+    contacts = np.asarray(oracle.detect_cs(data, stencil))
+    bb = oracle.find_object_properties(contacts)[1]
+    oracle.close_contact_sites(contacts, {k: bb[k] for k in sorted(bb)}, overlap, cs_dilation)
+    c = (slice(overlap, -overlap),) * 3
+    res = oracle.extract_cs_syntype(contacts[c], sj_d[c], asym_d[c], sym_d[c], np.asarray(offset) + overlap)
+    cs_seg = contacts[c].copy()
+    syn = contacts.copy()
+    syn[sj_d == 0] = 0
+    return res[0], res[1], res[2], res[3], res[4], cs_seg, syn[c]

@@ -374,3 +374,29 @@ def test_close_contact_sites(mods, monkeypatch):
     assert np.array_equal(close_contact_sites(cs.copy(), {}, 3, 2), cs)
     z = np.zeros((4, 4, 4), np.uint64)
     assert not close_contact_sites(z).any()
+
+
+def test_contact_site_extraction_chunk(mods):
+    """the numeric body of the contact-site worker for one chunk (detect_cs -> props -> closing -> extract_cs_syntype),
+    device resident, against the same composition of the oracle's restatements"""
+    from helpers import reference_contact_site_chunk
+    from syconn_b200.extraction.cs_extraction_steps import contact_site_extraction_chunk
+    oracle = mods["oracle"]
+    rng = np.random.default_rng(4)
+    for st, dil, size, lay in (((7, 7, 3), 2, (40, 36, 30), "zyx"), ((5, 5, 5), 1, (33, 31, 35), "xyz")):
+        so, ov = np.array(st) // 2, max(np.array(st) // 2)
+        full = tuple(int(size[i] + 2 * ov + 2 * so[i]) for i in range(3))
+        data = mods["synth"](full, origin=(100, 50, 7), pitch=(13, 11, 8), warp_amp=3, seed=6, dtype=np.uint32)
+        oshape = tuple(full[i] - st[i] + 1 for i in range(3))
+        sj = ((rng.random(oshape) < 0.4) * rng.integers(1, 3, size=oshape)).astype(np.uint8)
+        asym, sym = rng.integers(0, 3, size=oshape).astype(np.uint8), rng.integers(0, 3, size=oshape).astype(np.uint8)
+        if lay == "zyx":  # production: ZYX memory seen as XYZ (kd.load_seg(...).swapaxes(0, 2))
+            data, sj, asym, sym = (np.ascontiguousarray(a.transpose(2, 1, 0)).transpose(2, 1, 0) for a in (data, sj, asym, sym))
+        offset = np.array([100, 50, 7]) + so                     # position of the contact volume in the dataset
+        got = contact_site_extraction_chunk(data, sj, asym, sym, offset, st, dil)
+        want = reference_contact_site_chunk(oracle, data, sj, asym, sym, offset, st, dil)
+        assert_props_equal(tuple(got[0]), tuple(want[0]), "cs")
+        assert_props_equal(tuple(got[1]), tuple(want[1]), "syn")
+        assert got[2] == want[2] and got[3] == want[3] and got[4] == want[4]
+        assert got[5].dtype == np.uint64 and np.array_equal(got[5], want[5]) and np.array_equal(got[6], want[6])
+        assert len(want[4]) > 5 and (want[5] != 0).sum() > 1000
