@@ -362,8 +362,11 @@ struct MapArgs {
 //   MODE 0: labels only (find_object_properties); 1: organelle-first scan of one channel; 2: fused, run-time channel count.
 //   With MODE 0/1 the per-warp shared-memory layout is a compile-time constant (measured: -19% for MODE 0; the organelle scan
 //   is launched with MODE 2, the specialised instantiation was 7% slower).
+#ifndef SYK_ORG_MINB
+#define SYK_ORG_MINB 3
+#endif
 template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS, int NBUF, bool TMA, int MODE>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : 3) k_scan(const T *__restrict__ cell, ScanGeom G, TableView cell_t, MapArgs A,
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MODE == 2 ? SYK_ORG_MINB : 3)) k_scan(const T *__restrict__ cell, ScanGeom G, TableView cell_t, MapArgs A,
                                                      const __grid_constant__ TmapSet tm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long mbar[WARPS][2];
@@ -644,7 +647,11 @@ static int launch_scan(const void *cell, const ScanGeom &G, const TableView &cel
 #ifndef SYK_TMA_NBUF
 #define SYK_TMA_NBUF 1
 #endif
-    if (tma) return launch_cfg<T, R, TU, TV, WARPS, WS, WSS, PS, SYK_TMA_NBUF, true, MODE>(cell, G, cell_t, A, tm, s);
+#ifndef SYK_ORG_NBUF
+#define SYK_ORG_NBUF SYK_TMA_NBUF
+#endif
+    constexpr int NBUF_TMA = MODE == 2 ? SYK_ORG_NBUF : SYK_TMA_NBUF;
+    if (tma) return launch_cfg<T, R, TU, TV, WARPS, WS, WSS, PS, NBUF_TMA, true, MODE>(cell, G, cell_t, A, tm, s);
     return launch_cfg<T, R, TU, TV, WARPS, WS, WSS, PS, 2, false, MODE>(cell, G, cell_t, A, tm, s);
 }
 
@@ -658,10 +665,18 @@ static int launch_scan(const void *cell, const ScanGeom &G, const TableView &cel
 #define PROPS_CFG PROPS_R, PROPS_TU, PROPS_TV, PROPS_WARPS, 64, 32, 32
 #define MAP_CFG 8, 8, 16, 4, 64, 32, 32
 // organelle-first scan (measured: 4-warp CTAs with 16-row batches and 8-plane tiles, 0.47 vs 0.57 ms per 512^3 channel)
+#ifndef ORG_R
 #define ORG_R 16
+#endif
+#ifndef ORG_TU
 #define ORG_TU 8
+#endif
+#ifndef ORG_TV
 #define ORG_TV 32
+#endif
+#ifndef ORG_WARPS
 #define ORG_WARPS 4
+#endif
 #define ORG_CFG ORG_R, ORG_TU, ORG_TV, ORG_WARPS, 64, 32, 32
 
 SYK_API int syk_find_object_properties(syk_table_t *t, const void *labels_dev, int elem_bytes, const int64_t shape[3],

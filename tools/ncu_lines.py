@@ -1,5 +1,5 @@
 """Aggregate an ncu SASS profile by CUDA source line.
-python tools/ncu_lines.py rep kernel_substr [min_pct]   (needs the same libsyk.so the profile was taken with)"""
+python tools/ncu_lines.py rep kernel_substr [min_pct] [lib.so]   (needs the same libsyk.so the profile was taken with)"""
 import csv
 import os
 import re
@@ -9,7 +9,7 @@ import tempfile
 
 rep, ksub = sys.argv[1], sys.argv[2]
 minpct = float(sys.argv[3]) if len(sys.argv) > 3 else 0.7
-so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "syconn_b200", "libsyk.so")
+so = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "syconn_b200", "libsyk.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
 lines_by_fn = {}
