@@ -1,0 +1,130 @@
+"""Host-side mirrors of the dict-level merge helpers of ``syconn.proc.sd_proc`` that the extraction workers call around the
+hot path (same names, argument meaning and in-place behaviour), plus converters between the reference's dict structures and
+the array/record form of the device pipeline (``syconn_b200.chunked``).
+
+These functions only re-arrange per-chunk RESULTS in Python, exactly where the reference does it in Python; all voxel work
+stays in libsyk.  On the device-resident path the same reductions run as ``syk_table_merge_records`` / ``syk_pairs_merge``
+(``chunked.ExtractionPipeline``); the functions here exist so that code written against the reference's worker API keeps
+working when it merges the dicts returned by the shims.
+"""
+from collections import defaultdict
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from .._lib import PAIR_DTYPE, RECORD_DTYPE
+
+
+def merge_prop_dicts(prop_dicts: List[List[dict]], offset: Optional[np.ndarray] = None):
+    """syconn/proc/sd_proc.py:1248-1273.  Merge property dicts ``[rep_coords, bounding_boxes, sizes]`` in place into
+    ``prop_dicts[0]``: ``offset`` is added to the coordinates of the later entries, representative coordinates are
+    overwritten by later entries (:1261), bounding boxes are APPENDED per id (``prop_dicts[0][1]`` must map to lists, e.g.
+    a ``defaultdict(list)``, :1268) and sizes are summed."""
+    tot_rc, tot_bb, tot_size = prop_dicts[0][0], prop_dicts[0][1], prop_dicts[0][2]
+    for el in prop_dicts[1:]:
+        if len(el[0]) == 0:
+            continue
+        if offset is not None:
+            for k in el[0]:
+                el[0][k] = [el[0][k][ii] + offset[ii] for ii in range(3)]
+        tot_rc.update(el[0])
+        for k, v in el[1].items():
+            if offset is None:
+                bb = v
+            else:
+                bb = [[v[0][ii] + offset[ii] for ii in range(3)], [v[1][ii] + offset[ii] for ii in range(3)]]
+            tot_bb[k].append(bb)
+        for k, v in el[2].items():
+            if k in tot_size:
+                tot_size[k] += v
+            else:
+                tot_size[k] = v
+
+
+def merge_map_dicts(map_dicts: List[Dict[int, Dict[int, int]]]):
+    """syconn/proc/sd_proc.py:1300-1322.  Merge ``{sub_id: {cell_id: n_overlap_voxels}}`` dicts in place into
+    ``map_dicts[0]`` (counts of the same pair are summed)."""
+    tot_map = map_dicts[0]
+    for el in map_dicts[1:]:
+        for sc_id, sc_dc in el.items():
+            if sc_id in tot_map:
+                tgt = tot_map[sc_id]
+                for cellsv_id, ol_vx_cnt in sc_dc.items():
+                    if cellsv_id in tgt:
+                        tgt[cellsv_id] += ol_vx_cnt
+                    else:
+                        tgt[cellsv_id] = ol_vx_cnt
+            else:
+                tot_map[sc_id] = sc_dc
+
+
+def convert_nvox2ratio_mapdict(map_dc):
+    """syconn/proc/sd_proc.py:1275-1285: overlap voxel counts -> fractions of the organelle's overlapping voxels (in place)."""
+    for subcell_id, subcell_dc in map_dc.items():
+        s = np.sum(list(subcell_dc.values()))
+        for k in subcell_dc:
+            map_dc[subcell_id][k] = subcell_dc[k] / s
+
+
+def invert_mdc(mapping_dict):
+    """syconn/proc/sd_proc.py:1288-1297: ``{sub_id: {cell_id: v}}`` -> ``{cell_id: {sub_id: v}}``."""
+    mdc_inv = {}
+    for subcell_id, subcell_dc in mapping_dict.items():
+        for cell_id, v in subcell_dc.items():
+            if cell_id not in mdc_inv:
+                mdc_inv[cell_id] = {subcell_id: v}
+            else:
+                mdc_inv[cell_id][subcell_id] = v
+    return mdc_inv
+
+
+def new_prop_dicts():
+    """the accumulator the workers start from (``[{}, defaultdict(list), {}]``, sd_proc.py:605, cs_extraction_steps.py:370)"""
+    return [{}, defaultdict(list), {}]
+
+
+# ---------------------------------------------------------------------------------------------- dicts <-> arrays
+def reduced_to_prop_dicts(red):
+    """Output of ``chunked.reduce_records`` -> the merged dicts a reference worker ends up with after
+    ``merge_prop_dicts`` over its chunks: ``rep_coords {id: [x, y, z]}``, ``bounding_boxes {id: [bb_chunk0, bb_chunk1, ...]}``
+    (chunk order), ``sizes {id: n}``."""
+    ids = red["id"].tolist()
+    rc = dict(zip(ids, red["rep_coord"].tolist()))
+    bb = defaultdict(list)
+    for k, b in zip(ids, red["bbs"]):
+        bb[k] = b.tolist()
+    sz = dict(zip(ids, red["size"].tolist()))
+    return [rc, bb, sz]
+
+
+def reduced_to_map_dict(red):
+    """Output of ``chunked.reduce_pairs`` -> ``{sub_id: {cell_id: count}}`` (the result of ``merge_map_dicts``)."""
+    out = {}
+    for s, c, n in zip(red["sub_id"].tolist(), red["cell_id"].tolist(), red["count"].tolist()):
+        out.setdefault(s, {})[c] = n
+    return out
+
+
+def prop_dicts_to_records(prop_dicts, chunk_seq=0):
+    """``[rep_coords, bounding_box, sizes]`` of ONE chunk call (bounding boxes not yet appended) -> ``syk_record_t`` array
+    that ``IdTable.merge_records`` / ``reduce_records`` accept (rep_key is left 0: the decoded ``rep`` is carried)."""
+    rc, bb, sz = prop_dicts
+    rec = np.zeros(len(sz), RECORD_DTYPE)
+    for i, k in enumerate(sz):
+        rec["id"][i] = k
+        rec["count"][i] = sz[k]
+        rec["bb_min"][i] = bb[k][0]
+        rec["bb_max"][i] = bb[k][1]
+        rec["rep"][i] = rc[k]
+    rec["chunk_seq"] = chunk_seq
+    return rec
+
+
+def map_dict_to_pairs(map_dc):
+    """``{sub_id: {cell_id: count}}`` -> ``syk_pair_t`` array."""
+    rows = [(s, c, n) for s, d in map_dc.items() for c, n in d.items()]
+    out = np.zeros(len(rows), PAIR_DTYPE)
+    if rows:
+        a = np.array(rows, np.uint64)
+        out["sub_id"], out["cell_id"], out["count"] = a[:, 0], a[:, 1], a[:, 2]
+    return out

@@ -209,3 +209,51 @@ def test_pipeline_reports_table_overflow():
     pipe.process_chunk(0, (0, 0, 0), cell, subs, None)
     with pytest.raises(_lib.SykError):
         pipe.finish()
+
+
+def test_sd_proc_merge_mirrors():
+    """syconn_b200.proc.sd_proc: the dict-level merge helpers behave like the reference's (restated in the oracle), and the
+    array-level reductions of the device pipeline give the same merged result."""
+    import copy
+    from collections import defaultdict
+    from oracle import oracle
+    from syconn_b200.chunked import reduce_pairs, reduce_records
+    from syconn_b200.proc import sd_proc
+    from syconn_b200.synth import synth_labels
+    vol = synth_labels((48, 40, 36), pitch=(9, 8, 7), warp_amp=2, seed=4)
+    subs = np.stack([synth_labels((48, 40, 36), pitch=(5, 4, 4), seed=4, kind=1 + c, density16=5) for c in range(2)])
+    chunks = [((0, 0, 0), (24, 40, 36)), ((24, 0, 0), (24, 40, 36))]
+    per_chunk, per_chunk_maps = [], []
+    for off, size in chunks:
+        sl = tuple(slice(o, o + s) for o, s in zip(off, size))
+        cp, sp, md = oracle.map_subcell_extract_props(vol[sl], subs[(slice(None),) + sl])
+        per_chunk.append((off, cp))
+        per_chunk_maps.append(md)
+    # reference-style worker loop: merge_prop_dicts([acc, chunk_props], offset) per chunk
+    acc_ours, acc_ref = sd_proc.new_prop_dicts(), [{}, defaultdict(list), {}]
+    for off, cp in per_chunk:
+        sd_proc.merge_prop_dicts([acc_ours, copy.deepcopy(cp)], np.array(off))
+        oracle.merge_prop_dicts([acc_ref, copy.deepcopy(cp)], np.array(off))
+    assert acc_ours[0] == acc_ref[0] and dict(acc_ours[1]) == dict(acc_ref[1]) and acc_ours[2] == acc_ref[2]
+    maps_ours, maps_ref = copy.deepcopy(per_chunk_maps), copy.deepcopy(per_chunk_maps)
+    for c in range(2):
+        a, b = [m[c] for m in maps_ours], [m[c] for m in maps_ref]
+        sd_proc.merge_map_dicts(a)
+        oracle.merge_map_dicts(b)
+        assert a[0] == b[0]
+        inv = sd_proc.invert_mdc(a[0])
+        assert all(inv[cid][sid] == n for sid, d in a[0].items() for cid, n in d.items())
+        ratios = copy.deepcopy(a[0])
+        sd_proc.convert_nvox2ratio_mapdict(ratios)
+        assert all(abs(sum(d.values()) - 1.0) < 1e-12 for d in ratios.values())
+        # array-level reduction of the device pipeline == dict-level merge
+        log = np.concatenate([sd_proc.map_dict_to_pairs(m[c]) for m in per_chunk_maps])
+        assert sd_proc.reduced_to_map_dict(reduce_pairs(log)) == a[0]
+    recs = []
+    for seq, (off, cp) in enumerate(per_chunk):
+        r = sd_proc.prop_dicts_to_records(cp, chunk_seq=seq)
+        for f in ("bb_min", "bb_max", "rep"):
+            r[f] += np.array(off, np.int32)
+        recs.append(r)
+    red = sd_proc.reduced_to_prop_dicts(reduce_records(np.concatenate(recs)))
+    assert red[0] == acc_ref[0] and dict(red[1]) == dict(acc_ref[1]) and red[2] == acc_ref[2]

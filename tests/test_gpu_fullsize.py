@@ -140,3 +140,54 @@ def test_map_512_checksums(dev):
         s_t = torch.tensor(np.array([s_id], np.uint64).view(np.int64), device="cuda")
         c_t = torch.tensor(np.array([c_id], np.uint64).view(np.int64), device="cuda")
         assert int(((subs[c] == s_t) & (cell == c_t)).sum()) == int(pairs["count"][j])
+
+
+def test_close_contacts_full_chunk(dev):
+    """f2 at production size (536x536x530 haloed chunk -> 524^3 contacts, ~5e4 contact ids, n_closings 6, cs_dilation 2):
+    size-independent properties, plus the closed mask of sampled ids recomputed with the oracle's restatement."""
+    from oracle import oracle
+    seg = dev.synth_labels((536, 536, 530), pitch=(32, 32, 16), seed=1, dtype=torch.int32, order="F")
+    cs0 = dev.detect_cs(seg, (13, 13, 7))
+    del seg
+    rec = _records(dev, cs0, cap=1 << 21)
+    rec = rec[np.argsort(rec["id"])]
+    ids = rec["id"].copy()
+    bbox = np.stack([rec["bb_min"], rec["bb_max"]], axis=1).astype(np.int32)
+    cs = cs0.clone()
+    dev.close_contacts(cs, ids, bbox, 6, 2)
+    assert cs.stride() == cs0.stride()
+    was = cs0 != 0
+    assert torch.equal(cs[was], cs0[was])                                   # object voxels are never overwritten (:460)
+    filled = (cs != 0) & ~was
+    assert int(filled.sum()) > 10_000_000                                    # the closing does fill the gaps
+    new_ids = torch.unique(cs[filled]).cpu().numpy().view(np.uint64)
+    assert np.isin(new_ids, ids).all()                                       # only ids of the list are written
+    rec2 = _records(dev, cs, cap=1 << 21)
+    rec2 = rec2[np.argsort(rec2["id"])]
+    assert np.array_equal(rec2["id"], ids)                                   # no id appears or disappears
+    assert (rec2["count"] >= rec["count"]).all()
+    assert (rec2["bb_min"] >= np.maximum(rec["bb_min"] - 8, 0)).all() and (rec2["bb_max"] <= rec["bb_max"] + 8).all()
+    # idempotent no-op and determinism
+    again = cs0.clone()
+    dev.close_contacts(again, ids, bbox, 6, 2)
+    assert torch.equal(again, cs)
+    dev.close_contacts(again, ids, bbox, 0, 0)
+    assert torch.equal(again, cs)
+    # sampled ids: the oracle's closed mask of the padded box; background inside the mask must be claimed by somebody,
+    # and whatever the id gained must lie inside its mask
+    rng = np.random.default_rng(0)
+    shape = np.array(cs0.shape)
+    for i in rng.choice(len(ids), size=40, replace=False):
+        lo = np.maximum(bbox[i, 0] - 6, 0)
+        hi = np.minimum(bbox[i, 1] + 6, shape)
+        sl = tuple(slice(int(a), int(b)) for a, b in zip(lo, hi))
+        before = cs0[sl].cpu().numpy().view(np.uint64)
+        after = cs[sl].cpu().numpy().view(np.uint64)
+        mask = oracle.binary_closing_dilation(before == ids[i], 6, 2)
+        assert (after[mask & (before == 0)] != 0).all()
+        gained = (after == ids[i]) & (before != ids[i])
+        assert not (gained & ~mask).any()
+        # the id with the smallest list position among the claimants wins: nobody after it in the list may hold a
+        # background voxel of its mask
+        claimed = after[mask & (before == 0)]
+        assert (np.searchsorted(ids, claimed) <= i).all()
