@@ -24,12 +24,15 @@ namespace csfast {
 #ifndef SYK_LU
 #define SYK_LU 64
 #endif
-constexpr int TV = 16;
+#ifndef SYK_TV
+#define SYK_TV 16
+#endif
+constexpr int TV = SYK_TV;  // multiple of 8
 constexpr int TW = 32;
 constexpr int LU = SYK_LU;
 constexpr int HASH = 256;
 constexpr int NOQ = TV * TW / 4;  // output quads per plane (128)
-constexpr int MAX_NQUAD = 384;    // host guarantees VP*WP/4 <= MAX_NQUAD
+constexpr int MAX_NQUAD = (TV + 16) * 48 / 4;  // host guarantees VP*WP/4 <= MAX_NQUAD (384 for TV = 16)
 constexpr int MAX_WP = 48;        // host guarantees WP <= MAX_WP
 // Two tiers of the same kernel: tier 1 keeps at most 24 ids near the marching plane (small shared-memory footprint,
 // many CTAs per SM); the few segments that need more are redone by tier 2 (64 ids), then by the generic kernel.
@@ -69,7 +72,7 @@ __host__ __device__ __forceinline__ FastSmem fast_layout(int VP, int WP, int CR,
     const int plane = VP * WP;
     const int oplane = TV * WP;
     L.raw = 0;
-    L.comp = L.raw + fast_align16(plane * 4);
+    L.comp = L.raw + 2 * fast_align16(plane * 4);           // two raw planes: the next one streams in with cp.async
     L.ssum = L.comp + fast_align16(CR * plane);            // ring of compact-index planes, 1 byte per voxel
     L.cflag = L.ssum + fast_align16(GMAX * oplane * 8);    // uint2 {even slots, odd slots} in 8-bit fields
     L.elist = L.cflag + fast_align16(CF * TV * TW);
@@ -160,6 +163,14 @@ __device__ __forceinline__ unsigned nz_bytes(unsigned x) {  // 0x80 in every byt
     return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
 }
 
+// 16-byte asynchronous copy global -> shared (L2 only); bytes past src_bytes are zero-filled
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // sliding v-sum (window sv) of the indicator words of one column of a compact plane: acc[q], q = 0..7
 __device__ __forceinline__ void vsum8(const unsigned char *col, int WP, int sv, const unsigned *lut, unsigned (&acc)[8]) {
     unsigned head[8];
@@ -189,7 +200,8 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
     using Hash = HashT<GMAX>;
     constexpr int KMAX = Hash::KMAX;
     constexpr unsigned long long ALL_SLOTS = Hash::ALL_SLOTS;
-    constexpr int MAXQ = (MAX_NQUAD + NT - 1) / NT;             // relabel quads (4 voxels along w) per thread
+    constexpr int NQMAX = SU > 0 ? ((TV + SV - 1) * ((TW + SW - 1 + 3) & ~3)) / 4 : MAX_NQUAD;  // quads per haloed plane
+    constexpr int MAXQ = (NQMAX + NT - 1) / NT;                 // relabel quads (4 voxels along w) per thread
     constexpr int MAXIT = (GMAX * (TV / 8) * MAX_WP + NT - 1) / NT;  // v-pass items (8 outputs each) per thread
     constexpr bool FIX = SU > 0;
     const int su = FIX ? SU : G.sten[0], sv = FIX ? SV : G.sten[1], sw = FIX ? SW : G.sten[2];
@@ -199,7 +211,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
     const bool pair_ok = FIX ? (2 * SU * SV <= 255) : (G.pair_ok != 0);
     const FastSmem L = FIX ? fast_layout(VP, WP, CR, CF, GMAX) : Lrt;
     extern __shared__ __align__(16) unsigned char sm[];
-    unsigned *raw = reinterpret_cast<unsigned *>(sm + L.raw);
+    unsigned *raw = reinterpret_cast<unsigned *>(sm + L.raw);  // raw[(p & 1) * rawpitch ...]: input plane p
     unsigned char *comp = sm + L.comp;
     uint2 *ssum = reinterpret_cast<uint2 *>(sm + L.ssum);
     unsigned char *cflag = sm + L.cflag;
@@ -209,6 +221,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
     const int tid = threadIdx.x;
     const int plane = VP * WP, oplane = TV * WP;
     const int nquad = plane >> 2, qpr = WP >> 2;  // quads per plane / per row
+    const int rawpitch = fast_align16(plane * 4) >> 2;  // words between the two raw planes
 
     for (int i = tid; i < GMAX * (KMAX + 8); i += NT) {
         const int g = i / (KMAX + 8), j = i - g * (KMAX + 8);
@@ -358,20 +371,32 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             const long long gu = u0 + p;
             const int rp1 = rp ? rp - 1 : CR - 1, rp2 = rp1 ? rp1 - 1 : CR - 1, rpn = rp + 1 == CR ? 0 : rp + 1;
             // A. prefetch plane p+1 into registers; relabel pass 1 (find / insert the key of every voxel of plane p)
-            uint4 pre[MAXQ];
+            // (16-byte aligned uint32 rows: cp.async straight into the other raw plane -- nothing waits for it until the
+            // last barrier of this step; otherwise through registers, stored in phase B)
+            const unsigned *rawc = raw + (p & 1) * rawpitch;
+            unsigned *rawn = raw + ((p + 1) & 1) * rawpitch;
+            uint4 pre[VEC4 ? 1 : MAXQ];
             int hidx[MAXQ][4];
 #pragma unroll
             for (int k = 0; k < MAXQ; ++k) {
                 const int q = tid + k * NT;
-                pre[k] = make_uint4(0u, 0u, 0u, 0u);
-                if (q < nquad && p + 1 < NP) load_quad(k, gu + 1, pre[k]);
+                if (VEC4) {
+                    if (q < nquad && p + 1 < NP) {
+                        const bool in = gu + 1 < G.n[0] && qok[k] != 0u;
+                        const unsigned *src = reinterpret_cast<const unsigned *>(arr) + (in ? (gu + 1) * G.ist[0] + qoff[k] : 0);
+                        cp_async16(rawn + 4 * q, src, in ? 4 * __popc(qok[k]) : 0);  // in-bounds voxels of a quad are a prefix
+                    }
+                } else {
+                    pre[k] = make_uint4(0u, 0u, 0u, 0u);
+                    if (q < nquad && p + 1 < NP) load_quad(k, gu + 1, pre[k]);
+                }
             }
 #pragma unroll
             for (int k = 0; k < MAXQ; ++k) {
                 const int q = tid + k * NT;
                 hidx[k][0] = hidx[k][1] = hidx[k][2] = hidx[k][3] = -1;
                 if (q < nquad) {
-                    const uint4 a = reinterpret_cast<const uint4 *>(raw)[q];
+                    const uint4 a = reinterpret_cast<const uint4 *>(rawc)[q];
                     int h0 = -1, h1 = -1, h2 = -1, h3 = -1;
                     if (a.x != 0u) h0 = hash_find_insert(H, a.x, p);
                     if (a.y == a.x) h1 = h0;
@@ -424,7 +449,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                         w4 = j0 | (j1 << 8) | (j2 << 16) | (j3 << 24);
                     }
                     reinterpret_cast<unsigned *>(cp)[q] = w4;
-                    reinterpret_cast<uint4 *>(raw)[q] = pre[k];
+                    if (!VEC4) reinterpret_cast<uint4 *>(rawn)[q] = pre[VEC4 ? 0 : k];
                 }
             }
             __syncthreads();
@@ -479,6 +504,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             }
             if (!early_d) __syncthreads();  // the flags of plane p - ou were written in this very phase
             compact_outputs(p, rf);
+            if (VEC4) cp_async_wait_all();  // this thread's part of raw plane p + 1 has landed; the barrier publishes all parts
             __syncthreads();
             // D. boundary voxels of plane uo = p - su + 1: final sum along w and arg-max
             const int uo = p - su + 1;
@@ -486,7 +512,11 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 const unsigned char *cf = cflag + (rf + 1 == CF ? 0 : rf + 1) * (TV * TW);
                 unsigned long long *orow = out + (u0 + uo) * G.ost[0];
                 const int ne = H.n_edge;
+#ifdef SYK_D_FORWARD
                 for (int e = tid; e < ne; e += NT) {
+#else
+                for (int e = NT - 1 - tid; e < ne; e += NT) {  // from the last thread down: threads 0.. carry the second relabel quad
+#endif
                     const int i = elist[e];
                     const int b = i / TW, c = i - b * TW;
                     const int jc = cf[i] & 0x7F;
@@ -541,6 +571,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             // no barrier here: the next iteration's pass 1 only touches the hash; its barrier orders everything else
         }
         if (aborted) {
+            if (VEC4) cp_async_wait_all();  // the copy of the next plane must not land in the next segment's buffers
             if (tid == 0) hard_list[atomicAdd(hard_count, 1u)] = (unsigned)seg;
         }
     }
