@@ -511,6 +511,17 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
         G.seg_tiles[2] = TW / OW;
         k_detect_cs<<<(unsigned)((long long)sms * bps), CS_THREADS, smem, s>>>(arr, nullptr, o, G);
         SYK_CUDA(cudaGetLastError());
+#ifdef SYK_NG_HIST
+        if (getenv("SYK_CS_DEBUG")) {
+            unsigned long long h[65];
+            cudaStreamSynchronize(s);
+            cudaMemcpyFromSymbol(h, csfast::g_ids_hist, sizeof(h));
+            fprintf(stderr, "[syk] live ids per plane:");
+            for (int i = 0; i < 65; ++i)
+                if (h[i]) fprintf(stderr, " %d:%llu", i, h[i]);
+            fprintf(stderr, "\n");
+        }
+#endif
         if (getenv("SYK_CS_DEBUG")) {
             unsigned nh[2] = {0, 0};
             cudaMemcpyAsync(nh, hard, sizeof(nh), cudaMemcpyDeviceToHost, s);

@@ -21,6 +21,10 @@
 
 namespace csfast {
 
+#ifdef SYK_NG_HIST
+__device__ unsigned long long g_ids_hist[65];
+#endif
+
 #ifndef SYK_LU
 #define SYK_LU 64
 #endif
@@ -434,6 +438,9 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 H.tb[(tid & ~7) | ((n & 1) << 2) | (n & 2) | (n >> 2)] = (unsigned short)(((255 - r) << 8) | tid);
             }
             const int NG = used ? ((64 - __clzll((long long)used) + 7) >> 3) : 0;
+#ifdef SYK_NG_HIST
+            if (tid == 0) atomicAdd(&g_ids_hist[__popcll(used)], 1ull);  // development: live ids per plane
+#endif
             unsigned char *cp = comp + rp * plane;
 #pragma unroll
             for (int k = 0; k < MAXQ; ++k) {

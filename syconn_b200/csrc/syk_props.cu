@@ -363,7 +363,7 @@ struct MapArgs {
 //   With MODE 0/1 the per-warp shared-memory layout is a compile-time constant (measured: -19% for MODE 0; the organelle scan
 //   is launched with MODE 2, the specialised instantiation was 7% slower).
 #ifndef SYK_ORG_MINB
-#define SYK_ORG_MINB 3
+#define SYK_ORG_MINB 5
 #endif
 template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS, int NBUF, bool TMA, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MODE == 2 ? SYK_ORG_MINB : 3)) k_scan(const T *__restrict__ cell, ScanGeom G, TableView cell_t, MapArgs A,
@@ -378,16 +378,18 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
     const int nstage = org_mode ? 1 : nch;  // channels staged by TMA / cp.async (org mode fills channel 1 on demand)
     // per-warp layout: stage[NBUF][nch][R*32] T | WarpTab<WS> cell | n_sub x WarpTab<WSS> | n_sub x WarpPairTab<PS>
     const size_t stage_bytes = (size_t)NBUF * nch * R * 32 * sizeof(T);
-    const size_t per_warp = (stage_bytes + sizeof(WarpTab<WS>) + (size_t)n_sub * (sizeof(WarpTab<WSS>) + sizeof(WarpPairTab<PS>)) + 127) &
-                            ~(size_t)127;
+    const int n_stab = org_mode ? 0 : n_sub;  // org mode keeps no props table for the on-demand (cell) channel
+    const size_t per_warp = (stage_bytes + sizeof(WarpTab<WS>) + (size_t)n_stab * sizeof(WarpTab<WSS>) + (size_t)n_sub * sizeof(WarpPairTab<PS>) +
+                             127) & ~(size_t)127;
     unsigned char *mine = smem_raw + per_warp * wib;
     T *stage = reinterpret_cast<T *>(mine);
     WarpTab<WS> *ctab = reinterpret_cast<WarpTab<WS> *>(mine + stage_bytes);
     WarpTab<WSS> *stab = reinterpret_cast<WarpTab<WSS> *>(ctab + 1);
-    WarpPairTab<PS> *ptab = reinterpret_cast<WarpPairTab<PS> *>(stab + n_sub);
+    WarpPairTab<PS> *ptab = reinterpret_cast<WarpPairTab<PS> *>(stab + n_stab);
     for (int i = lane; i < WS; i += 32) ctab->keys[i] = 0ull;
     for (int c = 0; c < n_sub; ++c) {
-        for (int i = lane; i < WSS; i += 32) stab[c].keys[i] = 0ull;
+        if (c < n_stab)
+            for (int i = lane; i < WSS; i += 32) stab[c].keys[i] = 0ull;
         for (int i = lane; i < PS; i += 32) {
             ptab[c].sub[i] = 0ull;
             ptab[c].cell[i] = 0ull;
@@ -617,8 +619,9 @@ static bool make_tmap(CUtensorMap *m, const void *base, int elem_bytes, const lo
 template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS, int NBUF, bool TMA, int MODE>
 static int launch_cfg(const void *cell, const ScanGeom &G, const TableView &cell_t, const MapArgs &A, const TmapSet &tm, cudaStream_t s) {
     const int nch = 1 + A.n_sub;
-    const size_t per_warp = ((size_t)NBUF * nch * R * 32 * sizeof(T) + sizeof(WarpTab<WS>) +
-                             (size_t)A.n_sub * (sizeof(WarpTab<WSS>) + sizeof(WarpPairTab<PS>)) + 127) & ~(size_t)127;
+    const int n_stab = (MODE == 1 || (MODE == 2 && A.org_mode)) ? 0 : A.n_sub;
+    const size_t per_warp = ((size_t)NBUF * nch * R * 32 * sizeof(T) + sizeof(WarpTab<WS>) + (size_t)n_stab * sizeof(WarpTab<WSS>) +
+                             (size_t)A.n_sub * sizeof(WarpPairTab<PS>) + 127) & ~(size_t)127;
     const size_t smem = per_warp * WARPS;
     auto kern = k_scan<T, R, TU, TV, WARPS, WS, WSS, PS, NBUF, TMA, MODE>;
     SYK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -677,7 +680,11 @@ static int launch_scan(const void *cell, const ScanGeom &G, const TableView &cel
 #ifndef ORG_WARPS
 #define ORG_WARPS 4
 #endif
-#define ORG_CFG ORG_R, ORG_TU, ORG_TV, ORG_WARPS, 64, 32, 32
+// 32-slot private props table + no table for the on-demand channel: 10.1 KB per warp, 5 CTAs/SM (1.55 -> 1.49 ms for three channels)
+#ifndef ORG_WS
+#define ORG_WS 32
+#endif
+#define ORG_CFG ORG_R, ORG_TU, ORG_TV, ORG_WARPS, ORG_WS, 32, 32
 
 SYK_API int syk_find_object_properties(syk_table_t *t, const void *labels_dev, int elem_bytes, const int64_t shape[3],
                                        const int64_t strides[3], const int64_t origin[3], uint32_t chunk_seq, void *stream) {
