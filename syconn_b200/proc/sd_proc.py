@@ -128,3 +128,58 @@ def map_dict_to_pairs(map_dc):
         a = np.array(rows, np.uint64)
         out["sub_id"], out["cell_id"], out["count"] = a[:, 0], a[:, 1], a[:, 2]
     return out
+
+
+# ---------------------------------------------------------------------------------------------- dataset_analysis caches
+def cell_mapping_attributes(cell_ids, pairs_red, organelle_ids, organelle_sizes):
+    """Per cell supervoxel the organelle ids it overlaps and the overlap ratios, as the writers store them
+    (syconn/proc/sd_proc.py:1064-1084 -> ``mapping_{organelle}_ids`` / ``mapping_{organelle}_ratios``, :1172-1177): the
+    ratio is ``overlap voxels / total voxels of the organelle object``; organelles that are not part of the organelle
+    dataset (``organelle_ids``, e.g. removed by the size threshold) are dropped (:1072-1074).
+
+    ``pairs_red`` is the output of ``chunked.reduce_pairs`` (arrays ``sub_id, cell_id, count``).  Returns two object
+    arrays aligned with ``cell_ids``: lists of organelle ids (ascending) and lists of float ratios."""
+    cell_ids = np.asarray(cell_ids, np.uint64)
+    organelle_ids = np.asarray(organelle_ids, np.uint64)
+    organelle_sizes = np.asarray(organelle_sizes, np.int64)
+    order = np.argsort(organelle_ids)
+    sub, cell, cnt = pairs_red["sub_id"], pairs_red["cell_id"], pairs_red["count"]
+    pos = np.searchsorted(organelle_ids[order], sub)
+    pos[pos >= len(order)] = 0
+    known = (organelle_ids[order][pos] == sub) if len(order) else np.zeros(len(sub), bool)
+    sub, cell, cnt, pos = sub[known], cell[known], cnt[known], pos[known]
+    ratio = cnt / organelle_sizes[order][pos] if len(sub) else np.zeros(0)
+    o = np.lexsort((sub, cell))
+    sub, cell, ratio = sub[o], cell[o], ratio[o]
+    ids_out = np.empty(len(cell_ids), dtype=object)
+    rat_out = np.empty(len(cell_ids), dtype=object)
+    lo = np.searchsorted(cell, cell_ids, side="left")
+    hi = np.searchsorted(cell, cell_ids, side="right")
+    sub_l, ratio_l = sub.tolist(), ratio.tolist()
+    for i, (a, b) in enumerate(zip(lo.tolist(), hi.tolist())):
+        ids_out[i] = sub_l[a:b]
+        rat_out[i] = ratio_l[a:b]
+    return ids_out, rat_out
+
+
+def write_dataset_analysis_cache(sd_path, red, extra=None):
+    """Write the ``.npy`` column caches that ``dataset_analysis`` produces and ``SegmentationDataset`` reads back
+    (syconn/proc/sd_proc.py:138-155, :244-251; reps/segmentation.py:1601-1621, :1765-1784): ``ids.npy`` uint64,
+    ``sizes.npy`` int64, ``bounding_boxs.npy`` int32 [N, 2, 3], ``rep_coords.npy`` int32 [N, 3], plus one
+    ``{attribute}s.npy`` per entry of ``extra`` (e.g. ``mapping_mi_ids`` / ``mapping_mi_ratios`` object arrays from
+    ``cell_mapping_attributes``).  ``red`` is the output of ``chunked.reduce_records``.  Returns the written paths."""
+    import os
+    os.makedirs(sd_path, exist_ok=True)
+    n = len(red["id"])
+    cols = {"id": np.asarray(red["id"], np.uint64), "size": np.asarray(red["size"], np.int64),
+            "bounding_box": np.asarray(red["bounding_box"], np.int32).reshape(n, 2, 3),
+            "rep_coord": np.asarray(red["rep_coord"], np.int32).reshape(n, 3)}
+    for k, v in (extra or {}).items():
+        assert len(v) == n, f"attribute {k} has {len(v)} entries for {n} objects"
+        cols[k] = v
+    paths = []
+    for k, v in cols.items():
+        p = os.path.join(sd_path, f"{k}s.npy")
+        np.save(p, v)
+        paths.append(p)
+    return paths

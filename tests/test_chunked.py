@@ -257,3 +257,44 @@ def test_sd_proc_merge_mirrors():
         recs.append(r)
     red = sd_proc.reduced_to_prop_dicts(reduce_records(np.concatenate(recs)))
     assert red[0] == acc_ref[0] and dict(red[1]) == dict(acc_ref[1]) and red[2] == acc_ref[2]
+
+
+def test_dataset_analysis_cache(tmp_path):
+    """f3 (numpy column caches only): arrays written by write_dataset_analysis_cache read back with the dtypes of
+    dataset_analysis (sd_proc.py:244-251); mapping ids / ratios follow the writers' dict logic (:1064-1084)."""
+    from oracle import oracle
+    from syconn_b200.chunked import reduce_pairs, reduce_records
+    from syconn_b200.proc import sd_proc
+    from syconn_b200.synth import synth_labels
+    vol = synth_labels((40, 36, 32), pitch=(9, 8, 7), warp_amp=2, seed=7)
+    subs = np.stack([synth_labels((40, 36, 32), pitch=(5, 4, 4), seed=7, kind=1, density16=6)])
+    cp, sp, md = oracle.map_subcell_extract_props(vol, subs)
+    red_cell = reduce_records(sd_proc.prop_dicts_to_records(cp))
+    red_org = reduce_records(sd_proc.prop_dicts_to_records([sp[0][0], sp[1][0], sp[2][0]]))
+    pairs = reduce_pairs(sd_proc.map_dict_to_pairs(md[0]))
+    keep = red_org["size"] >= 4                                   # organelle dataset after a size threshold
+    m_ids, m_rat = sd_proc.cell_mapping_attributes(red_cell["id"], pairs, red_org["id"][keep], red_org["size"][keep])
+    # the writers' dict logic: invert -> drop unknown organelles -> normalise by the organelle size -> invert back
+    size_dc = dict(zip(red_org["id"][keep].tolist(), red_org["size"][keep].tolist()))
+    want = {}
+    for sid, d in md[0].items():
+        if sid in size_dc:
+            for cid, n in d.items():
+                want.setdefault(cid, {})[sid] = n / size_dc[sid]
+    for cid, ids, rat in zip(red_cell["id"].tolist(), m_ids, m_rat):
+        assert dict(zip(ids, rat)) == want.get(cid, {})
+    paths = sd_proc.write_dataset_analysis_cache(str(tmp_path / "sv_0"), red_cell,
+                                                 extra={"mapping_mi_id": m_ids, "mapping_mi_ratio": m_rat})
+    assert sorted(os.path.basename(p) for p in paths) == ["bounding_boxs.npy", "ids.npy", "mapping_mi_ids.npy",
+                                                          "mapping_mi_ratios.npy", "rep_coords.npy", "sizes.npy"]
+    ids = np.load(tmp_path / "sv_0" / "ids.npy")
+    assert ids.dtype == np.uint64 and np.array_equal(ids, red_cell["id"])
+    assert np.load(tmp_path / "sv_0" / "sizes.npy").dtype == np.int64
+    bb = np.load(tmp_path / "sv_0" / "bounding_boxs.npy")
+    assert bb.dtype == np.int32 and bb.shape == (len(ids), 2, 3)
+    rc = np.load(tmp_path / "sv_0" / "rep_coords.npy")
+    assert rc.dtype == np.int32 and rc.shape == (len(ids), 3)
+    back = np.load(tmp_path / "sv_0" / "mapping_mi_ids.npy", allow_pickle=True)
+    assert back.dtype == object and list(back[0]) == list(m_ids[0])
+    for k, i in zip(ids.tolist(), range(len(ids))):
+        assert cp[2][k] == int(np.load(tmp_path / "sv_0" / "sizes.npy")[i]) if i < 3 else True
