@@ -313,6 +313,11 @@ def run_ours(args):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
                 "share_of_step": float(np.sum(cs_ms)) / ms}
+    # the whole step against the same peak: compulsory bytes of all three stages per chunk: detect_cs 4 B in +
+    # 8 B out, props of the contact volume 8 B, mapping 8 B x (1 + N_SUB) per voxel
+    step_bytes = len(chunks) * (alg_bytes + out_vox * 8 + int(np.prod(chunks[0][2].shape)) * 8 * (1 + N_SUB))
+    roofline["step"] = {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                        "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
 
     line = {"metric": "GVoxels/s contact-site+property extraction", "value": value, "unit": "GVoxels/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
