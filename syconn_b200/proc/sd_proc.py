@@ -15,67 +15,60 @@ import numpy as np
 from .._lib import PAIR_DTYPE, RECORD_DTYPE
 
 
+def _shift(coord, offset):
+    return [int(c) + int(o) for c, o in zip(coord, offset)]
+
+
 def merge_prop_dicts(prop_dicts: List[List[dict]], offset: Optional[np.ndarray] = None):
-    """syconn/proc/sd_proc.py:1248-1273.  Merge property dicts ``[rep_coords, bounding_boxes, sizes]`` in place into
-    ``prop_dicts[0]``: ``offset`` is added to the coordinates of the later entries, representative coordinates are
-    overwritten by later entries (:1261), bounding boxes are APPENDED per id (``prop_dicts[0][1]`` must map to lists, e.g.
-    a ``defaultdict(list)``, :1268) and sizes are summed."""
-    tot_rc, tot_bb, tot_size = prop_dicts[0][0], prop_dicts[0][1], prop_dicts[0][2]
-    for el in prop_dicts[1:]:
-        if len(el[0]) == 0:
+    """syconn/proc/sd_proc.py:1248-1273.  Fold the property triples ``[rep_coords, bounding_boxes, sizes]`` of
+    ``prop_dicts[1:]`` into ``prop_dicts[0]`` (in place, nothing is returned).  Per id: the representative coordinate of
+    the LATEST triple wins (:1261), every bounding box is appended to the id's list -- the accumulator's second dict must
+    map to lists, e.g. ``defaultdict(list)`` (:1268) -- and sizes add up.  With ``offset`` the coordinates of the incoming
+    triples are translated first; like the reference, the incoming representative coordinates are rewritten in place."""
+    acc_rep, acc_boxes, acc_size = prop_dicts[0]
+    for rep, boxes, sizes in prop_dicts[1:]:
+        if not rep:
             continue
         if offset is not None:
-            for k in el[0]:
-                el[0][k] = [el[0][k][ii] + offset[ii] for ii in range(3)]
-        tot_rc.update(el[0])
-        for k, v in el[1].items():
-            if offset is None:
-                bb = v
-            else:
-                bb = [[v[0][ii] + offset[ii] for ii in range(3)], [v[1][ii] + offset[ii] for ii in range(3)]]
-            tot_bb[k].append(bb)
-        for k, v in el[2].items():
-            if k in tot_size:
-                tot_size[k] += v
-            else:
-                tot_size[k] = v
+            for key in rep:
+                rep[key] = _shift(rep[key], offset)
+        acc_rep.update(rep)
+        for key, box in boxes.items():
+            acc_boxes[key].append(box if offset is None else [_shift(box[0], offset), _shift(box[1], offset)])
+        for key, n_vox in sizes.items():
+            acc_size[key] = acc_size[key] + n_vox if key in acc_size else n_vox
 
 
 def merge_map_dicts(map_dicts: List[Dict[int, Dict[int, int]]]):
-    """syconn/proc/sd_proc.py:1300-1322.  Merge ``{sub_id: {cell_id: n_overlap_voxels}}`` dicts in place into
-    ``map_dicts[0]`` (counts of the same pair are summed)."""
-    tot_map = map_dicts[0]
-    for el in map_dicts[1:]:
-        for sc_id, sc_dc in el.items():
-            if sc_id in tot_map:
-                tgt = tot_map[sc_id]
-                for cellsv_id, ol_vx_cnt in sc_dc.items():
-                    if cellsv_id in tgt:
-                        tgt[cellsv_id] += ol_vx_cnt
-                    else:
-                        tgt[cellsv_id] = ol_vx_cnt
-            else:
-                tot_map[sc_id] = sc_dc
+    """syconn/proc/sd_proc.py:1300-1322.  Fold ``{sub_id: {cell_id: n_overlap_voxels}}`` dicts into ``map_dicts[0]`` in
+    place: counts of the same (organelle, cell) pair add up; an organelle seen for the first time adopts the incoming
+    inner dict as is (no copy, like the reference)."""
+    acc = map_dicts[0]
+    for incoming in map_dicts[1:]:
+        for sub_id, per_cell in incoming.items():
+            mine = acc.get(sub_id)
+            if mine is None:
+                acc[sub_id] = per_cell
+                continue
+            for cell_id, n_vox in per_cell.items():
+                mine[cell_id] = mine.get(cell_id, 0) + n_vox
 
 
 def convert_nvox2ratio_mapdict(map_dc):
     """syconn/proc/sd_proc.py:1275-1285: overlap voxel counts -> fractions of the organelle's overlapping voxels (in place)."""
-    for subcell_id, subcell_dc in map_dc.items():
-        s = np.sum(list(subcell_dc.values()))
-        for k in subcell_dc:
-            map_dc[subcell_id][k] = subcell_dc[k] / s
+    for per_cell in map_dc.values():
+        total = np.sum(list(per_cell.values()))
+        for cell_id in per_cell:
+            per_cell[cell_id] = per_cell[cell_id] / total
 
 
 def invert_mdc(mapping_dict):
     """syconn/proc/sd_proc.py:1288-1297: ``{sub_id: {cell_id: v}}`` -> ``{cell_id: {sub_id: v}}``."""
-    mdc_inv = {}
-    for subcell_id, subcell_dc in mapping_dict.items():
-        for cell_id, v in subcell_dc.items():
-            if cell_id not in mdc_inv:
-                mdc_inv[cell_id] = {subcell_id: v}
-            else:
-                mdc_inv[cell_id][subcell_id] = v
-    return mdc_inv
+    inverted = {}
+    for outer, inner in mapping_dict.items():
+        for key, value in inner.items():
+            inverted.setdefault(key, {})[outer] = value
+    return inverted
 
 
 def new_prop_dicts():
