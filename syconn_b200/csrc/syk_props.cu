@@ -376,8 +376,10 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
     const bool org_mode = MODE == 1 ? true : (MODE == 0 ? false : A.org_mode != 0);
     const int nch = 1 + n_sub;
     const int nstage = org_mode ? 1 : nch;  // channels staged by TMA / cp.async (org mode fills channel 1 on demand)
-    // per-warp layout: stage[NBUF][nch][R*32] T | WarpTab<WS> cell | n_sub x WarpTab<WSS> | n_sub x WarpPairTab<PS>
-    const size_t stage_bytes = (size_t)NBUF * nch * R * 32 * sizeof(T);
+    // per-warp layout: stage[NBUF][nch][R*32] T (org mode: stage[NBUF][R*32] of the staged channel + ONE on-demand plane)
+    //                  | WarpTab<WS> cell | n_stab x WarpTab<WSS> | n_sub x WarpPairTab<PS>
+    const int buf_elems = (org_mode ? 1 : nch) * R * 32;  // elements between two stage buffers
+    const size_t stage_bytes = (size_t)(org_mode ? NBUF + 1 : NBUF * nch) * R * 32 * sizeof(T);
     const int n_stab = org_mode ? 0 : n_sub;  // org mode keeps no props table for the on-demand (cell) channel
     const size_t per_warp = (stage_bytes + sizeof(WarpTab<WS>) + (size_t)n_stab * sizeof(WarpTab<WSS>) + (size_t)n_sub * sizeof(WarpPairTab<PS>) +
                              127) & ~(size_t)127;
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
             if (lane == 0) {
                 const int c0 = (int)(t.tw * TW), c1 = (int)(t.tv * TV + (b % (TV / R)) * R), c2 = (int)(t.tu * TU + b / (TV / R));
                 mbar_expect_tx(bar_addr[sb], (unsigned)(nstage * R * 32 * sizeof(T)));
-                const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage + (size_t)sb * nch * R * 32);
+                const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage + (size_t)sb * buf_elems);
                 for (int c = 0; c < nstage; ++c) tma_load_3d(dst0 + c * R * 32 * (unsigned)sizeof(T), &tm.m[c], c0, c1, c2, bar_addr[sb]);
             }
             return;
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
         const long long u = t.tu * TU + b / (TV / R);
         const long long v0 = t.tv * TV + (b % (TV / R)) * R;
         const bool ok = (w < G.n[2]) && (u < G.n[0]);
-        T *dst = stage + (size_t)sb * nch * R * 32 + lane;
+        T *dst = stage + (size_t)sb * buf_elems + lane;
         const T *src = ok ? cell + w * G.st[2] + u * G.st[0] + v0 * G.st[1] : cell;
 #pragma unroll
         for (int j = 0; j < R; ++j) {
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
             __syncwarp();
             const unsigned lu = (unsigned)(b / (TV / R));
             const unsigned lv0 = (unsigned)((b % (TV / R)) * R);
-            const T *cb = stage + (size_t)sb * nch * R * 32;
+            const T *cb = stage + (size_t)sb * buf_elems;
             unsigned nzs = 0u;
             if (A.do_cell_props) {
                 const unsigned bnd = run_starts<T, R>(cb, lane, nzs);
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
                 // volume, fetched only where the organelle is non-zero
                 if (!A.do_cell_props) run_starts<T, R>(cb, lane, nzs);
                 if (__any_sync(FULL, nzs != 0u)) {
-                    T *cbuf = stage + (size_t)sb * nch * R * 32 + R * 32;
+                    T *cbuf = stage + (size_t)NBUF * R * 32;  // shared by the stage buffers
                     const long long w = cur.tw * TW + lane, u = cur.tu * TU + lu, v0 = cur.tv * TV + lv0;
                     const T *cp = reinterpret_cast<const T *>(A.sub[0]) + w * G.sst[2] + u * G.sst[0] + v0 * G.sst[1];
 #pragma unroll
@@ -620,7 +622,8 @@ template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS,
 static int launch_cfg(const void *cell, const ScanGeom &G, const TableView &cell_t, const MapArgs &A, const TmapSet &tm, cudaStream_t s) {
     const int nch = 1 + A.n_sub;
     const int n_stab = (MODE == 1 || (MODE == 2 && A.org_mode)) ? 0 : A.n_sub;
-    const size_t per_warp = ((size_t)NBUF * nch * R * 32 * sizeof(T) + sizeof(WarpTab<WS>) + (size_t)n_stab * sizeof(WarpTab<WSS>) +
+    const bool org = MODE == 1 || (MODE == 2 && A.org_mode);
+    const size_t per_warp = ((size_t)(org ? NBUF + 1 : NBUF * nch) * R * 32 * sizeof(T) + sizeof(WarpTab<WS>) + (size_t)n_stab * sizeof(WarpTab<WSS>) +
                              (size_t)A.n_sub * sizeof(WarpPairTab<PS>) + 127) & ~(size_t)127;
     const size_t smem = per_warp * WARPS;
     auto kern = k_scan<T, R, TU, TV, WARPS, WS, WSS, PS, NBUF, TMA, MODE>;
@@ -628,9 +631,9 @@ static int launch_cfg(const void *cell, const ScanGeom &G, const TableView &cell
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int bps = (int)((226 * 1024) / (smem + 1024 + 256));
+    int bps = 1;
+    SYK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
     if (bps < 1) bps = 1;
-    if (bps * WARPS > 64) bps = 64 / WARPS;
     long long want = (G.ntiles + WARPS - 1) / WARPS;
     long long grid = (long long)sms * bps;
     if (grid > want) grid = want < 1 ? 1 : want;
