@@ -483,28 +483,35 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
             const unsigned lv0 = (unsigned)((b % (TV / R)) * R);
             const T *cb = stage + (size_t)sb * buf_elems;
             unsigned nzs = 0u;
-            if (A.do_cell_props) {
-                const unsigned bnd = run_starts<T, R>(cb, lane, nzs);
-                acc_batch<T, R, WS>(cb, bnd, nzs, *ctab, cell_t, G, Tc, lu, lv0, lane);
-            }
             if (org_mode) {
-                // staged channel 0 = organelle (props done above as the "cell" channel); overlap with the real cell
-                // volume, fetched only where the organelle is non-zero
-                if (!A.do_cell_props) run_starts<T, R>(cb, lane, nzs);
-                if (__any_sync(FULL, nzs != 0u)) {
-                    T *cbuf = stage + (size_t)NBUF * R * 32;  // shared by the stage buffers
+                // staged channel 0 = organelle (its props are accumulated as the "cell" channel); the real cell volume is
+                // fetched only where the organelle is non-zero -- asynchronously (cp.async, zero fill elsewhere), so that
+                // the DRAM round trip overlaps the props work of the same batch instead of stalling the warp
+                const unsigned bnd = run_starts<T, R>(cb, lane, nzs);
+                const bool any = __any_sync(FULL, nzs != 0u);
+                T *cbuf = stage + (size_t)NBUF * R * 32;  // shared by the stage buffers
+                if (any) {
                     const long long w = cur.tw * TW + lane, u = cur.tu * TU + lu, v0 = cur.tv * TV + lv0;
-                    const T *cp = reinterpret_cast<const T *>(A.sub[0]) + w * G.sst[2] + u * G.sst[0] + v0 * G.sst[1];
+                    const T *cbase = reinterpret_cast<const T *>(A.sub[0]);
+                    const T *cp = cbase + w * G.sst[2] + u * G.sst[0] + v0 * G.sst[1];
 #pragma unroll
                     for (int j = 0; j < R; ++j) {
-                        T cval = 0;
-                        if (cb[j * 32 + lane] != 0) cval = __ldg(cp + j * G.sst[1]);
-                        cbuf[j * 32 + lane] = cval;
+                        const bool need = cb[j * 32 + lane] != 0;
+                        cp_async_elem<T>(cbuf + j * 32 + lane, need ? cp + j * G.sst[1] : cbase, need);
                     }
+                    cp_async_commit();
+                }
+                if (A.do_cell_props) acc_batch<T, R, WS>(cb, bnd, nzs, *ctab, cell_t, G, Tc, lu, lv0, lane);
+                if (any) {
+                    cp_async_wait<0>();
                     __syncwarp();
                     acc_pairs<T, R, PS>(cb, cbuf, ptab[0], A.pair_t[0], lane);
                 }
-            } else {
+            } else if (A.do_cell_props) {
+                const unsigned bnd = run_starts<T, R>(cb, lane, nzs);
+                acc_batch<T, R, WS>(cb, bnd, nzs, *ctab, cell_t, G, Tc, lu, lv0, lane);
+            }
+            if (!org_mode) {
                 for (int c = 0; c < n_sub; ++c) {
                     const T *sbuf = cb + (size_t)(1 + c) * R * 32;
                     unsigned snz;
