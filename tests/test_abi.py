@@ -75,3 +75,35 @@ def test_shim_error_behaviour():
         map_subcell_extract_props(np.zeros((3, 3, 3), np.uint64), np.zeros((1, 3, 3, 3), np.uint32))
     with pytest.raises(AssertionError):
         detect_cs(np.zeros((9, 9, 9), np.uint32), stencil=(3, 2, 3))
+
+
+def test_new_shims_host_logic():
+    """argument checks and the trivial cases of the f2 / 64-bit shims run before any device call"""
+    from syconn_b200.extraction import cs_extraction_steps as ces
+    from syconn_b200.extraction.find_object_properties import (convert_nvox2ratio_syntype, detect_contact_partners,
+                                                               extract_cs_syntype_64bit, find_object_properties_cs_64bit,
+                                                               merge_type_dicts, merge_voxel_dicts)
+    vol = np.zeros((4, 5, 6), np.uint64)
+    assert ces.close_contact_sites(vol, {}, 3, 2) is vol                       # no ids: untouched, no device needed
+    assert ces.close_contact_sites(vol, {7: [[0, 0, 0], [1, 1, 1]]}, 0, 0) is vol   # no iterations: untouched
+    with pytest.raises(ValueError):
+        ces.close_contact_sites(np.zeros((4, 4, 4), np.float32), {}, 3, 2)
+    ids, bb = ces._boxes({9: [[1, 2, 3], [4, 5, 6]], 2 ** 63 + 1: [[0, 0, 0], [1, 1, 1]]})
+    assert ids.dtype == np.uint64 and ids.tolist() == [9, 2 ** 63 + 1]         # dict order kept, 64-bit ids exact
+    assert bb.dtype == np.int32 and bb.shape == (2, 2, 3) and bb[0].tolist() == [[1, 2, 3], [4, 5, 6]]
+    with pytest.raises(ValueError):
+        ces.contact_site_extraction_chunk(np.zeros((30, 30, 30), np.uint64), None, None, None, (0, 0, 0), (7, 7, 3), 2)
+    with pytest.raises(NotImplementedError):                                    # asymmetric windows are not provided
+        detect_contact_partners(np.zeros((5, 5, 5), np.uint64), None, np.array([(-1, 2), (-1, 1), (-1, 1)]))
+    with pytest.raises(NotImplementedError):                                    # dead code in the reference
+        extract_cs_syntype_64bit(None, None, None, None)
+    assert find_object_properties_cs_64bit(np.zeros((0, 3, 3, 2), np.uint64)) == ({}, {}, {})
+    # pure-Python helpers of the facade (find_object_properties.py:272-344)
+    asym, sym = convert_nvox2ratio_syntype({1: 4, 2: 10}, {1: 1}, {2: 5})
+    assert sym == {1: 0.25, 2: 0} and asym == {1: 0, 2: 0.5}
+    tot = [{1: 2}, {1: 3, 5: 1}]
+    merge_type_dicts(tot)
+    assert tot[0] == {1: 5, 5: 1}
+    vx = [{1: [[0, 0, 0]]}, {1: [[1, 1, 1]], 2: np.array([[2, 2, 2]])}]
+    merge_voxel_dicts(vx)
+    assert vx[0] == {1: [[0, 0, 0], [1, 1, 1]], 2: [[2, 2, 2]]}
