@@ -37,7 +37,7 @@ CS_FILTERSIZE = (13, 13, 7)  # syconn/handler/config.yml:148
 def build(force=False):
     """Compile the C restatement (gcc only; a few seconds)."""
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
-        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-shared", "-fvisibility=hidden",
+        subprocess.check_call(["gcc", "-O3", "-fPIC", "-shared", "-fvisibility=hidden",
                                "-o", _SO, _SRC])
     return _SO
 
