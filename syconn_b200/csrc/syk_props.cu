@@ -694,7 +694,10 @@ static int launch_scan(const void *cell, const ScanGeom &G, const TableView &cel
 #ifndef ORG_WS
 #define ORG_WS 32
 #endif
-#define ORG_CFG ORG_R, ORG_TU, ORG_TV, ORG_WARPS, ORG_WS, 32, 32
+#ifndef ORG_PS
+#define ORG_PS 32
+#endif
+#define ORG_CFG ORG_R, ORG_TU, ORG_TV, ORG_WARPS, ORG_WS, 32, ORG_PS
 
 SYK_API int syk_find_object_properties(syk_table_t *t, const void *labels_dev, int elem_bytes, const int64_t shape[3],
                                        const int64_t strides[3], const int64_t origin[3], uint32_t chunk_seq, void *stream) {
