@@ -1,5 +1,5 @@
 """Aggregate an ncu SASS profile by CUDA source line.
-python tools/ncu_lines.py rep kernel_substr [min_pct] [lib.so]   (needs the same libsyk.so the profile was taken with)"""
+NCU_RESULT=i python tools/ncu_lines.py rep kernel_substr [min_pct] [lib.so]   (i = result index in a multi-kernel report; needs the same libsyk.so the profile was taken with)"""
 import csv
 import os
 import re
@@ -33,10 +33,13 @@ for f in os.listdir(tmp):
             seq.append(cur)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-hi = next(i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r)
+which = int(os.environ.get("NCU_RESULT", "0"))  # index of the result inside a multi-kernel report (listed back to back)
+heads = [i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r]
+hi = heads[which]
+end = heads[which + 1] - 1 if which + 1 < len(heads) else len(rows)
 hdr = rows[hi]
 ia, ismp = hdr.index("Instructions Executed"), hdr.index("# Samples")
-data = [r for r in rows[hi + 1:] if len(r) > ia and r[ia].isdigit()]
+data = [r for r in rows[hi + 1:end] if len(r) > ia and r[ia].isdigit()]
 cands = [k for k in lines_by_fn if ksub in k and len(lines_by_fn[k]) == len(data)] or [k for k in lines_by_fn if ksub in k]
 fn = cands[0]
 seq = lines_by_fn[fn]
