@@ -218,8 +218,7 @@ def run_ours(args):
     geoms = {"cell": np.zeros(len(plan), GEOM_DTYPE), "cs": np.zeros(len(plan), GEOM_DTYPE)}
     for s in range(len(plan)):
         lo, ls, oo, os_ = cs_halo_geometry(plan.offsets[s], plan.sizes[s], STENCIL)
-        geoms["cell"][s] = (plan.offsets[s], plan.sizes[s])
-        geoms["cs"][s] = (oo, os_)
+        geoms["cell"][s] = geoms["cs"][s] = (plan.offsets[s], plan.sizes[s])   # contact props: cropped to the chunk
 
     # ---- inputs resident in HBM before the timed region (production layout: x fastest in memory) ----
     chunks = []
@@ -328,8 +327,13 @@ def run_ours(args):
                        "objects": {k: int(v.shape[0]) for k, v in res[0].items()}},
             "clocks": clk.summary(), "roofline": roofline, "gpu_launches": int(launches)}
 
-    if rank == 0 and world == 1 and not args.no_e2e:
-        line["e2e"] = e2e_host(args, chunks)
+    # ---- parity of the step's result (untimed): the merged tables against independent voxel counts of the inputs,
+    #      ownership of every final id, and (N > 1) the sharded pipeline against a single-rank fold ----
+    line["parity"] = parity_block(pipe, chunks, res, rank, world)
+    if not args.no_e2e:  # every rank drives its own GPU over its own PCIe link; whole-job value = sum of voxels / max time
+        e2e = e2e_host(args, chunks, rank, world)
+        if rank == 0:
+            line["e2e"] = e2e
     elif rank == 0:
         line["e2e"] = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -341,13 +345,85 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
 
 
-def e2e_host(args, chunks):
+def parity_block(pipe, chunks, res, rank, world):
+    """Post-step checks at every N (not timed).  (1) Per kind, the sum of `count` over all ranks' owned final tables
+    equals the number of non-zero voxels counted independently with torch on the inputs (for "cs": on the cropped
+    contact volume recomputed per chunk); same for the overlap pairs.  (2) Every final id is owned by the rank that
+    holds it (owner_of == rank) and appears once.  (3) N > 1: tools/mgpu_check.sharded_equals_single on a small
+    geometry -- the sharded pipeline + NCCL exchange gives exactly the rows of a rank-0 single-rank fold."""
+    import torch
+    import torch.distributed as dist
+    from syconn_b200 import device as dev
+    from syconn_b200.chunked import owner_of
+    final, final_pairs = res
+    kinds = ["cell", "cs"] + [f"sub{c}" for c in range(N_SUB)]
+    ov = max(s // 2 for s in STENCIL)
+    want = torch.zeros(len(kinds) + N_SUB, dtype=torch.int64, device="cuda")
+    for (s, off, cell, subs, halo) in chunks:
+        cs = dev.detect_cs(halo, STENCIL, out=pipe.cs_out)
+        want[0] += torch.count_nonzero(cell)
+        want[1] += torch.count_nonzero(cs[ov:cs.shape[0] - ov, ov:cs.shape[1] - ov, ov:cs.shape[2] - ov])
+        for c in range(N_SUB):
+            nz = subs[c] != 0
+            want[2 + c] += torch.count_nonzero(nz)
+            want[len(kinds) + c] += torch.count_nonzero(nz & (cell != 0))
+    got = torch.zeros_like(want)
+    n_ids = torch.zeros(len(kinds), dtype=torch.int64, device="cuda")
+    problems = []
+    for i, k in enumerate(kinds):
+        r = dev.records_numpy(final[k])
+        got[i] = int(r["count"].sum())
+        n_ids[i] = len(r)
+        if len(np.unique(r["id"])) != len(r):
+            problems.append(f"rank {rank}: duplicate ids in the final '{k}' table")
+        if world > 1 and not np.all(owner_of(r["id"], world) == rank):
+            problems.append(f"rank {rank}: final '{k}' table holds ids it does not own")
+    for c in range(N_SUB):
+        p = dev.pairs_numpy(final_pairs[c])
+        got[len(kinds) + c] = int(p["count"].sum())
+        if world > 1 and not np.all(owner_of(p["sub_id"], world) == rank):
+            problems.append(f"rank {rank}: final pair table {c} holds organelle ids it does not own")
+    bad = torch.tensor([len(problems)], dtype=torch.int64, device="cuda")
+    if world > 1:
+        for t in (want, got, n_ids, bad):
+            dist.all_reduce(t)
+    names = kinds + [f"pairs{c}" for c in range(N_SUB)]
+    w, g = want.tolist(), got.tolist()
+    for nm, a, b in zip(names, w, g):
+        if a != b:
+            problems.append(f"{nm}: merged count {b} != {a} non-zero voxels")
+    out = {"voxel_sums": dict(zip(names, g)), "voxel_sums_expected": dict(zip(names, w)),
+           "distinct_ids": dict(zip(kinds, n_ids.tolist())), "ownership": "ok" if int(bad.item()) == 0 else "violated"}
+    if world > 1:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from tools.mgpu_check import sharded_equals_single
+        msgs = []
+        same = sharded_equals_single(rank, world, log=msgs.append)
+        out["sharded_vs_single_rank"] = {"geometry": "2x2x2 chunks of 96^3, stencil 13x13x7, 3 organelle channels",
+                                         "equal": same, "detail": msgs}
+        if not same:
+            problems.append("sharded result differs from the single-rank fold")
+    out["status"] = "ok" if not problems and int(bad.item()) == 0 else "FAILED"
+    if problems:
+        out["problems"] = problems
+    return out
+
+
+def e2e_host(args, chunks, rank=0, world=1):
     """Same stages through the reference-facing C-ABI *_host entry points with HOST buffers: every call uploads its
     inputs and downloads its results inside the timed region."""
     import torch
+    import torch.distributed as dist
     from syconn_b200.extraction import _host
     from syconn_b200.extraction.find_object_properties import detect_cs
     n = min(args.e2e_chunks, len(chunks))
+    try:  # pinned host copies: ~7.2 GB per chunk and rank; stay well inside the box's RAM at N = 8
+        import psutil
+        avail = psutil.virtual_memory().available / max(1, world)
+        per_chunk = sum(t.numel() * t.element_size() for t in chunks[0][2:5]) + chunks[0][4].numel() * 8
+        n = max(1, min(n, int(0.5 * avail // max(per_chunk, 1))))
+    except Exception:
+        pass
 
     def pinned(t):  # host copy in pinned memory (what a loader thread would hand to the plugin)
         # keep the device tensor's memory order (x fastest) so that the host array is the production ZYX block
@@ -405,17 +481,32 @@ def e2e_host(args, chunks):
     reps = max(1, min(args.steps, 3))
     vox = sum(int(c[0].size) for c in host)
 
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
     def measure(fused, pool):
         one_pass(fused, pool)
-        torch.cuda.synchronize()
+        sync_all()
         ts = []
         for _ in range(reps):
             t0 = time.perf_counter()
             one_pass(fused, pool)
             torch.cuda.synchronize()
-            ts.append(time.perf_counter() - t0)
-        return {"value": vox / float(np.median(ts)) / 1e9, "unit": "GVoxels/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "pass_seconds": [round(t, 4) for t in ts]}
+            dt = time.perf_counter() - t0
+            if world > 1:  # all ranks run the pass at the same time (one PCIe link each): the job's time is the slowest
+                t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+                dist.barrier()
+            ts.append(dt)
+        tot = torch.tensor([vox, h2d, d2h], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot)
+        tv, th, td = tot.tolist()
+        return {"value": tv / float(np.median(ts)) / 1e9, "unit": "GVoxels/s", "h2d_bytes_per_step": int(th),
+                "d2h_bytes_per_step": int(td), "pass_seconds": [round(t, 4) for t in ts]}
 
     seq_api = ("syk_detect_cs_host + syk_find_object_properties_host + syk_map_subcell_extract_props_host (pinned host buffers, "
                "one synchronous call per stage and chunk)")
@@ -430,7 +521,7 @@ def e2e_host(args, chunks):
     serial_fused["api"] = fused_api
     par_fused["api"] = fused_api + f", {W} worker threads"
     out = dict(par)
-    out.update({"chunks_per_step": n, "workers": W,
+    out.update({"chunks_per_step": n * world, "ranks": world, "copies_declared": True, "workers": W,
                 "api": seq_api + f"; the calls are issued from {W} worker threads (the reference fans the same calls out over worker "
                                  "processes), each thread's copies and kernels run on its own stream",
                 "single_thread": serial, "fused_variant": par_fused, "fused_single_thread": serial_fused})

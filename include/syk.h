@@ -112,6 +112,7 @@ int syk_records_decode_rep(syk_record_t *records_dev, uint64_t n, const syk_chun
                            void *stream);
 
 int syk_pairs_create(syk_pairs_t **out, uint64_t capacity);
+uint64_t syk_pairs_capacity(const syk_pairs_t *t);
 int syk_pairs_destroy(syk_pairs_t *t);
 int syk_pairs_clear(syk_pairs_t *t, void *stream);
 int syk_pairs_export(syk_pairs_t *t, syk_pair_t *pairs_dev, uint64_t max_pairs, uint64_t *n_out_host, void *stream);

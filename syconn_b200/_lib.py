@@ -25,7 +25,7 @@ EXPORTS = [
     "syk_version", "syk_last_error", "syk_device_count", "syk_set_device",
     "syk_table_create", "syk_table_destroy", "syk_table_clear", "syk_table_capacity", "syk_table_count",
     "syk_table_export", "syk_table_append_records", "syk_table_merge_records", "syk_records_bucket", "syk_records_decode_rep",
-    "syk_pairs_create", "syk_pairs_destroy", "syk_pairs_clear", "syk_pairs_export", "syk_pairs_append", "syk_pairs_merge",
+    "syk_pairs_create", "syk_pairs_capacity", "syk_pairs_destroy", "syk_pairs_clear", "syk_pairs_export", "syk_pairs_append", "syk_pairs_merge",
     "syk_pairs_bucket",
     "syk_find_object_properties", "syk_map_subcell_extract_props", "syk_detect_seg_boundaries",
     "syk_process_block_nonzero", "syk_detect_cs", "syk_extract_cs_syntype", "syk_synth_labels",
@@ -74,6 +74,8 @@ def load():
     L.syk_records_bucket.argtypes = [vp, u64, u32, vp, vp, vp]
     L.syk_records_decode_rep.argtypes = [vp, u64, vp, u32, vp]
     L.syk_pairs_create.argtypes = [C.POINTER(vp), u64]
+    L.syk_pairs_capacity.argtypes = [vp]
+    L.syk_pairs_capacity.restype = u64
     L.syk_pairs_destroy.argtypes = [vp]
     L.syk_pairs_clear.argtypes = [vp, vp]
     L.syk_pairs_export.argtypes = [vp, vp, u64, u64p, vp]
@@ -107,7 +109,7 @@ def load():
     L.syk_free.restype = None
     for name in EXPORTS:
         f = getattr(L, name)
-        if name not in ("syk_version", "syk_last_error", "syk_device_count", "syk_table_capacity", "syk_free"):
+        if name not in ("syk_version", "syk_last_error", "syk_device_count", "syk_table_capacity", "syk_pairs_capacity", "syk_free"):
             f.restype = ci
     _lib = L
     return L

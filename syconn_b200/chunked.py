@@ -65,20 +65,69 @@ def cs_halo_geometry(offset, size, stencil=(13, 13, 7)):
 
 
 # ------------------------------------------------------------------------------------------------ exchange
-def exchange_buckets(bucketed: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
-    """Hash-owner all-to-all: ``bucketed`` [n, k] holds this rank's rows grouped per destination rank
-    (``counts[d]`` rows for rank d, in rank order).  Returns the rows this rank owns (from all ranks)."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    if world == 1:
-        return bucketed
-    counts = [int(c) for c in counts]
-    assert len(counts) == world and sum(counts) == bucketed.shape[0]
-    send_counts = torch.tensor(counts, dtype=torch.int64, device=bucketed.device)
-    recv_counts = torch.empty_like(send_counts)
-    dist.all_to_all_single(recv_counts, send_counts, group=group)
-    recv = [int(c) for c in recv_counts.tolist()]
-    out = torch.empty((sum(recv), bucketed.shape[1]), dtype=bucketed.dtype, device=bucketed.device)
-    dist.all_to_all_single(out, bucketed.contiguous(), output_split_sizes=recv, input_split_sizes=counts, group=group)
+_M64 = (1 << 64) - 1
+
+
+def owner_of(ids, n_owners: int) -> np.ndarray:
+    """Rank that owns each id in the final reduce: NumPy mirror of ``syk_owner_of`` (csrc/syk_table.cu), the
+    counterpart of the reference's id -> reducer hash (syconn/reps/rep_helper.py:143-163).  Host-side bookkeeping
+    only (e.g. "which rank's table holds object X"); the records themselves are bucketed on the device."""
+    k = np.asarray(ids, np.uint64) ^ np.uint64(0x5bd1e9955bd1e995)
+    with np.errstate(over="ignore"):
+        k ^= k >> np.uint64(33)
+        k *= np.uint64(0xff51afd7ed558ccd)
+        k ^= k >> np.uint64(33)
+        k *= np.uint64(0xc4ceb9fe1a85ec53)
+        k ^= k >> np.uint64(33)
+    return ((k >> np.uint64(20)) % np.uint64(n_owners)).astype(np.int64)
+
+
+def exchange_logs(bucketed: Sequence[torch.Tensor], counts: Sequence[torch.Tensor], world: int, group=None):
+    """The hash-owner exchange of ``ExtractionPipeline.finish`` (the reference's reduce keyed by object id,
+    syconn/proc/sd_proc.py:511-556): ``bucketed[j]`` is log j of this rank with its rows grouped per destination rank
+    (``counts[j][d]`` rows for rank d, rank order).  ONE count all-to-all for all logs, then one all-to-all-v per row
+    width.  Returns the list of owned logs (rows received from all ranks, source-rank order).  Device-agnostic: NCCL
+    on CUDA tensors, gloo on CPU tensors (tests/test_chunked.py drives this very function)."""
+    n_logs = len(bucketed)
+    if world == 1 or n_logs == 0:
+        return list(bucketed)
+    dev = bucketed[0].device
+    send_mat = torch.stack([c.to(torch.int64) for c in counts], dim=1).contiguous()   # [dest, log] rows this rank sends
+    recv_mat = torch.empty_like(send_mat)                                            # [source, log] rows it receives
+    dist.all_to_all_single(recv_mat, send_mat, group=group)
+    send_h, recv_h = send_mat.tolist(), recv_mat.tolist()                            # one host sync for both matrices
+    out = [None] * n_logs
+    widths = sorted(set(int(b.shape[1]) for b in bucketed))
+    for width in widths:
+        log_ids = [j for j in range(n_logs) if bucketed[j].shape[1] == width]
+        dtype = bucketed[log_ids[0]].dtype
+        parts, in_split = [], []
+        offs = {j: 0 for j in log_ids}
+        for d in range(world):
+            tot = 0
+            for j in log_ids:
+                m = send_h[d][j]
+                if m:
+                    parts.append(bucketed[j][offs[j]:offs[j] + m])
+                offs[j] += m
+                tot += m
+            in_split.append(tot)
+        for j in log_ids:
+            assert offs[j] == bucketed[j].shape[0], "bucket counts do not add up to the log length"
+        send = torch.cat(parts) if parts else torch.empty((0, width), dtype=dtype, device=dev)
+        out_split = [sum(recv_h[src][j] for j in log_ids) for src in range(world)]
+        recv = torch.empty((sum(out_split), width), dtype=dtype, device=dev)
+        dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=out_split, input_split_sizes=in_split, group=group)
+        per_log = {j: [] for j in log_ids}
+        pos = 0
+        for src in range(world):
+            for j in log_ids:
+                m = recv_h[src][j]
+                if m:
+                    per_log[j].append(recv[pos:pos + m])
+                pos += m
+        for j, v in per_log.items():
+            out[j] = torch.cat(v) if v else torch.empty((0, width), dtype=dtype, device=dev)
     return out
 
 
@@ -158,11 +207,12 @@ class ExtractionPipeline:
         """One chunk: ``cell`` [X,Y,Z] and ``subcell`` [C,X,Y,Z] 64-bit labels at ``offset``; ``cell_halo`` the
         uint32 block of cs_halo_geometry (or None to skip contact sites)."""
         dev, L = self.dev, self.dev._lib.load()
-        # stage 1: contact sites + their properties (cs_extraction_steps.py:391,439)
+        # stage 1: contact sites (cs_extraction_steps.py:391) and the properties the worker merges across chunks:
+        # those of the contact volume cropped by `overlap`, at the chunk's own offset (:465-486) -- neighbouring chunks
+        # overlap by 2*overlap voxels in the un-cropped volume, which must not be counted twice
         if cell_halo is not None:
             so = [s // 2 for s in self.stencil]
             overlap = max(so)
-            out_off = [offset[i] - overlap for i in range(3)]
             buf = self._cs_buffer(cell_halo)
             if self.cs_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -171,9 +221,11 @@ class ExtractionPipeline:
             if self.cs_events is not None:
                 e1.record()
                 self.cs_events.append((e0, e1))
+            crop = self.cs_out[overlap:self.cs_out.shape[0] - overlap, overlap:self.cs_out.shape[1] - overlap,
+                               overlap:self.cs_out.shape[2] - overlap]
             self.t_cs.clear()
-            dev.find_object_properties(self.t_cs, self.cs_out, origin=out_off, chunk_seq=seq)
-            self._append(self.t_cs, 1, self.logs["cs"], out_off, self.cs_out.shape)
+            dev.find_object_properties(self.t_cs, crop, origin=offset, chunk_seq=seq)
+            self._append(self.t_cs, 1, self.logs["cs"], offset, crop.shape)
             self.launches += 3 + 1  # k_cs_fast tier 1, tier 2, k_detect_cs (list mode) + k_scan on the contact volume
         # stages 2+3: cell / organelle properties and overlap mapping (sd_proc.py:646-684)
         self.t_cell.clear()
@@ -215,7 +267,7 @@ class ExtractionPipeline:
             for c in range(self.n_sub):
                 owned_pairs.append(self.pair_logs[c][:n[len(self.kinds) + c]])
             return owned, owned_pairs
-        # ---- hash-owner exchange: ONE count exchange and one all-to-all per payload width for all logs together ----
+        # ---- hash-owner exchange (exchange_logs): bucket every log by owner on the device, then exchange ----
         W, nk = self.world, len(self.kinds)
         bucketed, cnts = [], []
         for i, k in enumerate(self.kinds):
@@ -227,47 +279,10 @@ class ExtractionPipeline:
             bucketed.append(b)
             cnts.append(cc)
         self.launches += 3 * len(bucketed)
-        send_mat = torch.stack(cnts, dim=1).contiguous()            # [dest, log] rows this rank sends
-        recv_mat = torch.empty_like(send_mat)                       # [source, log] rows this rank receives
-        dist.all_to_all_single(recv_mat, send_mat, group=self.group)
-        send_h, recv_h = send_mat.tolist(), recv_mat.tolist()       # one host sync for both matrices
-
-        def exchange(log_ids):
-            """all-to-all of the given logs (same row width): send buffer ordered by destination, then by log."""
-            parts, in_split = [], []
-            offs = {j: 0 for j in log_ids}
-            for d in range(W):
-                tot = 0
-                for j in log_ids:
-                    m = send_h[d][j]
-                    if m:
-                        parts.append(bucketed[j][offs[j]:offs[j] + m])
-                    offs[j] += m
-                    tot += m
-                in_split.append(tot)
-            width = bucketed[log_ids[0]].shape[1]
-            send = torch.cat(parts) if parts else torch.empty((0, width), dtype=torch.int64, device="cuda")
-            out_split = [sum(recv_h[src][j] for j in log_ids) for src in range(W)]
-            recv = torch.empty((sum(out_split), width), dtype=torch.int64, device="cuda")
-            dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split, group=self.group)
-            # split the received rows back into logs
-            per_log = {j: [] for j in log_ids}
-            pos = 0
-            for src in range(W):
-                for j in log_ids:
-                    m = recv_h[src][j]
-                    if m:
-                        per_log[j].append(recv[pos:pos + m])
-                    pos += m
-            return {j: (torch.cat(v) if v else torch.empty((0, width), dtype=torch.int64, device="cuda"))
-                    for j, v in per_log.items()}
-
-        got = exchange(list(range(nk)))
+        got = exchange_logs(bucketed, cnts, W, self.group)
         for i, k in enumerate(self.kinds):
             owned[k] = got[i]
-        if self.n_sub:
-            gotp = exchange(list(range(nk, nk + self.n_sub)))
-            owned_pairs = [gotp[nk + c] for c in range(self.n_sub)]
+        owned_pairs = [got[nk + c] for c in range(self.n_sub)]
         self.launches += 3
         return owned, owned_pairs
 

@@ -16,6 +16,10 @@ void syk_pool_keep_warm();  // raise the release threshold of the default stream
 // Stream of the calling host thread for the *_host entry points (non-blocking, created on first use): calls made
 // from different threads overlap their PCIe copies and kernels instead of serialising on the default stream.
 cudaStream_t syk_host_stream();
+// Raise (never lower) a kernel's opt-in dynamic shared-memory limit.  The *_host API is thread-concurrent: setting the
+// attribute to the size of the current call would let two threads with different stencils undo each other between
+// set and launch; a monotone, mutex-guarded maximum cannot.
+int syk_ensure_dyn_smem(const void *func, int bytes);
 
 #define SYK_CUDA(call)                                                                             \
     do {                                                                                           \

@@ -452,7 +452,7 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
     const size_t smem = tile_n * 4 + (size_t)((G.total + 1) & ~1) * 2 * (first_seen ? 2 : 1) + (size_t)OT * 2 * 2 +
                         (size_t)G.hslots * (first_seen ? 12 : 8);
     SYK_CHECK_ARG(smem <= 220 * 1024, "stencil too large for shared memory");
-    SYK_CUDA(cudaFuncSetAttribute(k_detect_cs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if ((rc = syk_ensure_dyn_smem((const void *)k_detect_cs, (int)smem))) return rc;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -498,8 +498,8 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
             k1 = k_cs_fast<false, GMAX_T1, NT_T1, MINB1>;
             k2 = k_cs_fast<false, GMAX_T2, NT_T2, MINB2>;
         }
-        SYK_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, L1.total));
-        SYK_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
+        if ((rc = syk_ensure_dyn_smem((const void *)k1, L1.total))) return rc;
+        if ((rc = syk_ensure_dyn_smem((const void *)k2, L2.total))) return rc;
         k1<<<(unsigned)g1, NT_T1, L1.total, s>>>(arr, o, F, L1, nullptr, nullptr, list1, cnt1);
         k2<<<(unsigned)g2, NT_T2, L2.total, s>>>(arr, o, F, L2, list1, cnt1, list2, cnt2);
         SYK_CUDA(cudaGetLastError());

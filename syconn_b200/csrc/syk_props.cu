@@ -634,7 +634,7 @@ static int launch_cfg(const void *cell, const ScanGeom &G, const TableView &cell
                              (size_t)A.n_sub * sizeof(WarpPairTab<PS>) + 127) & ~(size_t)127;
     const size_t smem = per_warp * WARPS;
     auto kern = k_scan<T, R, TU, TV, WARPS, WS, WSS, PS, NBUF, TMA, MODE>;
-    SYK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int rc_ = syk_ensure_dyn_smem((const void *)kern, (int)smem); if (rc_) return rc_; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

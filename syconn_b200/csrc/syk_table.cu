@@ -5,6 +5,9 @@
 //   id -> reducer hash  syconn/reps/rep_helper.py:143-163  -> syk_records_bucket / syk_pairs_bucket
 #include <stdarg.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "syk_common.cuh"
 
 // ---- errors ---------------------------------------------------------------------------------------------------
@@ -38,10 +41,27 @@ void syk_pool_keep_warm() {
     int dev = 0;
     cudaMemPool_t pool;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long thr = ~0ull;
+        // keep up to SYK_POOL_KEEP_MB (default 32768, i.e. 32 of the 180 GB) of freed scratch in the pool; beyond that it goes back to the driver
+        // so that other allocators in the process (e.g. torch's caching allocator) are not starved
+        const char *e = getenv("SYK_POOL_KEEP_MB");
+        unsigned long long thr = (unsigned long long)(e ? atoll(e) : 32768) << 20;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     cudaGetLastError();
+}
+
+int syk_ensure_dyn_smem(const void *func, int bytes) {
+    static std::mutex mu;
+    static std::unordered_map<const void *, int> cur[16];
+    int dev = 0;
+    SYK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    int &have = cur[dev & 15][func];
+    if (bytes > have) {
+        SYK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        have = bytes;
+    }
+    return SYK_OK;
 }
 
 cudaStream_t syk_host_stream() {
@@ -104,6 +124,9 @@ int syk_table_create_on(syk_table **out, uint64_t capacity, cudaStream_t s) {
     t->counter = (unsigned long long *)((char *)ctl + 32);
     SYK_CUDA(cudaMemsetAsync(t->slots, 0, t->capacity * sizeof(SykSlot), s));
     SYK_CUDA(cudaMemsetAsync(ctl, 0, 64, s));
+    // the table is used from whatever stream the caller passes later (torch side streams do not synchronise with the
+    // creating stream): creation is rare, so simply finish the allocation + clear here
+    SYK_CUDA(cudaStreamSynchronize(s));
     *out = t;
     return SYK_OK;
 }
@@ -111,6 +134,8 @@ SYK_API int syk_table_create(syk_table_t **out, uint64_t capacity) { return syk_
 
 SYK_API int syk_table_destroy(syk_table_t *t) {
     if (!t) return SYK_OK;
+    cudaDeviceSynchronize();  // kernels on any stream may still use the slots; destruction is rare
+    cudaGetLastError();
     cudaFreeAsync(t->slots, t->stream);
     cudaFreeAsync(t->flags, t->stream);
     free(t);
@@ -497,12 +522,16 @@ int syk_pairs_create_on(syk_pairs **out, uint64_t capacity, cudaStream_t s) {
     t->counter = (unsigned long long *)((char *)ctl + 32);
     SYK_CUDA(cudaMemsetAsync(t->slots, 0, t->capacity * sizeof(SykPairSlot), s));
     SYK_CUDA(cudaMemsetAsync(ctl, 0, 64, s));
+    SYK_CUDA(cudaStreamSynchronize(s));  // see syk_table_create_on
     *out = t;
     return SYK_OK;
 }
 SYK_API int syk_pairs_create(syk_pairs_t **out, uint64_t capacity) { return syk_pairs_create_on(out, capacity, (cudaStream_t)0); }
+SYK_API uint64_t syk_pairs_capacity(const syk_pairs_t *t) { return t ? t->capacity : 0; }
 SYK_API int syk_pairs_destroy(syk_pairs_t *t) {
     if (!t) return SYK_OK;
+    cudaDeviceSynchronize();
+    cudaGetLastError();
     cudaFreeAsync(t->slots, t->stream);
     cudaFreeAsync(t->flags, t->stream);
     free(t);

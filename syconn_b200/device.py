@@ -88,9 +88,7 @@ class PairTable:
         h = C.c_void_p()
         check(self._L.syk_pairs_create(C.byref(h), int(capacity)))
         self.h = h
-        self.capacity = 1024
-        while self.capacity < capacity:
-            self.capacity *= 2
+        self.capacity = int(self._L.syk_pairs_capacity(h))
 
     def clear(self, stream=None):
         check(self._L.syk_pairs_clear(self.h, _stream_ptr(stream)))

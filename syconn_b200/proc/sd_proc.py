@@ -100,7 +100,8 @@ def reduced_to_map_dict(red):
 
 def prop_dicts_to_records(prop_dicts, chunk_seq=0):
     """``[rep_coords, bounding_box, sizes]`` of ONE chunk call (bounding boxes not yet appended) -> ``syk_record_t`` array
-    that ``IdTable.merge_records`` / ``reduce_records`` accept (rep_key is left 0: the decoded ``rep`` is carried)."""
+    that the host-side ``reduce_records`` accepts.  ``rep_key`` is left 0 (only the decoded ``rep`` is carried), so these
+    records are NOT valid input for the device fold ``IdTable.merge_records``, which recomputes ``rep`` from ``rep_key``."""
     rc, bb, sz = prop_dicts
     rec = np.zeros(len(sz), RECORD_DTYPE)
     for i, k in enumerate(sz):

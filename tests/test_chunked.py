@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from oracle import oracle
 from syconn_b200._lib import PAIR_DTYPE, RECORD_DTYPE
-from syconn_b200.chunked import ChunkPlan, cs_halo_geometry, exchange_buckets, reduce_pairs, reduce_records
+from syconn_b200.chunked import ChunkPlan, cs_halo_geometry, exchange_logs, owner_of, reduce_pairs, reduce_records
 from syconn_b200.synth import synth_labels
 
 
@@ -88,36 +88,81 @@ def _free_port():
     return p
 
 
+def _sharded_logs(rank, world):
+    """Per-(id, chunk) record log and pair log of this rank's chunks (oracle, chunk by chunk) on a 3x2x2 chunk grid."""
+    cell = synth_labels((48, 32, 32), pitch=(14, 12, 9), seed=4)
+    sub = synth_labels((48, 32, 32), pitch=(5, 5, 4), seed=4, kind=1, density16=5)
+    plan = ChunkPlan(cell.shape, (16, 16, 16))
+    seqs = plan.chunks_of_rank(rank, world)
+    log, _ = _oracle_chunk_log(cell, plan, seqs)
+    rows = []
+    for s in seqs:
+        off, size = plan.offsets[s], plan.sizes[s]
+        sl = tuple(slice(off[i], off[i] + size[i]) for i in range(3))
+        for a, d in oracle.map_subcell_C(cell[sl], sub[sl][None])[0].items():
+            rows += [(a, b, n, 0) for b, n in d.items()]
+    return log, np.array(rows, dtype=PAIR_DTYPE)
+
+
+def _bucket(arr, key, world):
+    """host stand-in of syk_records_bucket / syk_pairs_bucket: rows grouped by owner rank + per-owner counts"""
+    o = owner_of(arr[key], world)
+    order = np.argsort(o, kind="stable")
+    mat = arr[order].view(np.int64).reshape(len(arr), -1)
+    return torch.from_numpy(mat.copy()), torch.from_numpy(np.bincount(o, minlength=world).astype(np.int64))
+
+
 def _gloo_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        # rank r sends (r+1)*(d+2) rows to rank d; row = [src, dst, k, ...]
-        counts = [(rank + 1) * (d + 2) for d in range(world)]
-        rows = []
-        for d in range(world):
-            for k in range(counts[d]):
-                rows.append([rank, d, k, 7, 8, 9, 10, 11])
-        got = exchange_buckets(torch.tensor(rows, dtype=torch.int64), counts)
-        ok = all(int(r[1]) == rank for r in got)
-        exp = sum((s + 1) * (rank + 2) for s in range(world))
-        srcs = sorted(set(int(r[0]) for r in got))
-        # empty buckets must work too
-        e = exchange_buckets(torch.zeros((0, 4), dtype=torch.int64), [0] * world)
-        q.put((rank, ok and got.shape[0] == exp and srcs == list(range(world)) and e.shape[0] == 0))
+        log, pairs = _sharded_logs(rank, world)
+        b0, c0 = _bucket(log, "id", world)
+        b1, c1 = _bucket(pairs, "sub_id", world)
+        empty = torch.zeros((0, 8), dtype=torch.int64)                     # an empty log must pass through too
+        got = exchange_logs([b0, b1, empty], [c0, c1, torch.zeros(world, dtype=torch.int64)], world)
+        recs = got[0].numpy().view(RECORD_DTYPE).reshape(-1)
+        prs = got[1].numpy().view(PAIR_DTYPE).reshape(-1)
+        ok = got[2].shape == (0, 8) and bool(np.all(owner_of(recs["id"], world) == rank)) and \
+            bool(np.all(owner_of(prs["sub_id"], world) == rank))
+        q.put((rank, ok, recs, prs))
     finally:
         dist.destroy_process_group()
 
 
-def test_exchange_buckets_gloo_world2():
+def test_exchange_logs_gloo_world2():
+    """The product's exchange (chunked.exchange_logs, what ExtractionPipeline.finish calls) under gloo with 2 ranks:
+    owner fold of the exchanged logs == single-rank fold of all chunks (sd_proc.py:511-556, 1248-1322)."""
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     ps = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
     [p.start() for p in ps]
-    res = [q.get(timeout=120) for _ in ps]
+    res = sorted([q.get(timeout=180) for _ in ps], key=lambda r: r[0])
     [p.join(timeout=60) for p in ps]
-    assert sorted(res) == [(0, True), (1, True)]
+    assert [r[:2] for r in res] == [(0, True), (1, True)]
+    log_all, pairs_all = _sharded_logs(0, 1)
+    want, want_p = reduce_records(log_all), reduce_pairs(pairs_all)
+    parts = [reduce_records(r[2]) for r in res]
+    pparts = [reduce_pairs(r[3]) for r in res]
+    ids = np.concatenate([p["id"] for p in parts])
+    o = np.argsort(ids)
+    assert np.array_equal(ids[o], want["id"]) and len(set(ids.tolist())) == len(ids)
+    for f in ("size", "bounding_box", "rep_coord"):
+        assert np.array_equal(np.concatenate([p[f] for p in parts])[o], want[f]), f
+    bbs = [b for p in parts for b in p["bbs"]]
+    assert all(np.array_equal(bbs[i], w) for i, w in zip(o, want["bbs"]))
+    key = np.concatenate([np.stack([p["sub_id"], p["cell_id"], p["count"].astype(np.uint64)], 1) for p in pparts])
+    key = key[np.lexsort((key[:, 1], key[:, 0]))]
+    assert np.array_equal(key, np.stack([want_p["sub_id"], want_p["cell_id"], want_p["count"].astype(np.uint64)], 1))
+
+
+def test_owner_of_matches_device_hash_constants():
+    """owner_of is a pure function of the id with every rank in range; the GPU test checks it against syk_records_bucket."""
+    ids = np.arange(1, 5000, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    for w in (1, 2, 3, 8):
+        o = owner_of(ids, w)
+        assert o.min() >= 0 and o.max() < w and (w == 1 or len(np.unique(o)) == w)
 
 
 @pytest.mark.gpu
@@ -136,15 +181,17 @@ def test_pipeline_small_volume_vs_oracle():
         for s in range(len(plan)):
             off, size = plan.offsets[s], plan.sizes[s]
             lo, ls, oo, os_ = cs_halo_geometry(off, size, st)
-            geoms["cell"][s], geoms["cs"][s] = (off, size), (oo, os_)
+            geoms["cell"][s], geoms["cs"][s] = (off, size), (off, size)
             cell = dev.synth_labels(size, off, (13, 11, 7), 3, 2, 0, order="F")
             subs = torch.stack([dev.synth_labels(size, off, (6, 5, 4), 3, 2, 1 + c, 3) for c in range(nsub)])
             halo = dev.synth_labels(ls, lo, (13, 11, 7), 3, 2, 0, dtype=torch.int32, order="F")
             pipe.process_chunk(s, off, cell, subs, halo)
             if rep == 0:
                 hn = synth_labels(ls, lo, (13, 11, 7), 3, 2, 0, dtype=np.uint32)
-                cs = oracle.detect_cs(hn, st)
-                for arrs, origin, dst in ((oracle.find_object_properties_arrays(cs), oo, want_cs),
+                ov = max(x // 2 for x in st)       # the worker merges the props of the CROPPED contacts (:465-486)
+                cs = np.ascontiguousarray(oracle.detect_cs(hn, st)[ov:-ov, ov:-ov, ov:-ov])
+                assert cs.shape == tuple(size)
+                for arrs, origin, dst in ((oracle.find_object_properties_arrays(cs), off, want_cs),
                                           (oracle.find_object_properties_arrays(cell.cpu().numpy().view(np.uint64)), off, want_cell)):
                     dst.append((s, origin, arrs))
                 c_, s_, p_ = oracle.map_subcell_extract_props_arrays(cell.cpu().numpy().view(np.uint64),
@@ -188,11 +235,9 @@ def test_pipeline_small_volume_vs_oracle():
     b, counts = dev.bucket_records(owned["cell"], 4)
     bn, cn = dev.records_numpy(b), counts.tolist()
     assert sum(cn) == owned["cell"].shape[0]
-    owner_of = {}
     pos = 0
     for o, n in enumerate(cn):
-        for i in bn["id"][pos:pos + n].tolist():
-            assert owner_of.setdefault(i, o) == o
+        assert np.all(owner_of(bn["id"][pos:pos + n], 4) == o)      # host mirror == device hash
         pos += n
     assert sorted(bn["id"].tolist()) == sorted(dev.records_numpy(owned["cell"])["id"].tolist())
 
