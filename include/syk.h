@@ -235,6 +235,14 @@ int syk_close_contacts_host(void *cs_host, int elem_bytes, const int64_t shape[3
                             const int32_t *bbox_host, uint64_t n_ids, int n_closings, int n_dilations);
 void syk_free(void *p);
 
+/* ---- storage codec (row f3; host code, no GPU needed) ----------------------------------------------------- */
+/* LZ4 block format, the codec behind the reference's CompressedStorage / VoxelStorageDyn values
+ * (python-lz4 `lz4.block.compress/decompress`, syconn/handler/compression.py:83-127, backend/storage.py:52-93).
+ * Raw blocks, without python-lz4's 4-byte length prefix (syconn_b200/handler/compression.py adds it). */
+uint64_t syk_lz4_compress_bound(uint64_t n);
+int syk_lz4_compress_block(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t *out_n);
+int syk_lz4_decompress_block(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t *out_n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,7 @@ EXPORTS = [
     "syk_detect_contact_partners", "syk_cs64_unpack", "syk_dense_relabel",
     "syk_detect_contact_partners_host", "syk_find_object_properties_cs_64bit_host",
     "syk_close_contacts", "syk_close_contacts_host",
+    "syk_lz4_compress_bound", "syk_lz4_compress_block", "syk_lz4_decompress_block",
 ]
 
 
@@ -105,11 +106,15 @@ def load():
     L.syk_find_object_properties_cs_64bit_host.argtypes = [vp, i64p, i64p, C.POINTER(vp), C.POINTER(vp), u64p]
     L.syk_close_contacts.argtypes = [vp, ci, i64p, i64p, vp, vp, u64, ci, ci, vp]
     L.syk_close_contacts_host.argtypes = [vp, ci, i64p, i64p, vp, vp, u64, ci, ci]
+    L.syk_lz4_compress_bound.argtypes = [u64]
+    L.syk_lz4_compress_bound.restype = u64
+    L.syk_lz4_compress_block.argtypes = [vp, u64, vp, u64, u64p]
+    L.syk_lz4_decompress_block.argtypes = [C.c_char_p, u64, vp, u64, u64p]
     L.syk_free.argtypes = [vp]
     L.syk_free.restype = None
     for name in EXPORTS:
         f = getattr(L, name)
-        if name not in ("syk_version", "syk_last_error", "syk_device_count", "syk_table_capacity", "syk_pairs_capacity", "syk_free"):
+        if name not in ("syk_version", "syk_last_error", "syk_device_count", "syk_table_capacity", "syk_pairs_capacity", "syk_free", "syk_lz4_compress_bound"):
             f.restype = ci
     _lib = L
     return L

@@ -1,5 +1,6 @@
 // syk_common.cuh -- shared device/host helpers of libsyk (sm_100a).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -20,6 +21,12 @@ cudaStream_t syk_host_stream();
 // attribute to the size of the current call would let two threads with different stencils undo each other between
 // set and launch; a monotone, mutex-guarded maximum cannot.
 int syk_ensure_dyn_smem(const void *func, int bytes);
+// Rank-3 TMA tensor map over a label volume given by its internal axes (u, v, w; w contiguous): dims {n[2], n[1], n[0]},
+// box {box_w, box_v, 1}, no swizzle, out-of-bounds elements read as zero.  cuTensorMapEncodeTiled is resolved through the
+// runtime (no link against libcuda).  false: the view cannot be described (unaligned base / strides) or TMA is disabled
+// (SYK_NO_TMA) -- callers then use their LDG / cp.async path.
+bool syk_make_tmap3(CUtensorMap *m, const void *base, int elem_bytes, const long long n[3], const long long st[3], int box_w,
+                    int box_v);
 
 #define SYK_CUDA(call)                                                                             \
     do {                                                                                           \

@@ -13,6 +13,7 @@
 
 #include "syk_common.cuh"
 #include "syk_cs_fast.cuh"
+#include "syk_cs_march.cuh"
 
 namespace {
 
@@ -498,9 +499,36 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
             k1 = k_cs_fast<false, GMAX_T1, NT_T1, MINB1>;
             k2 = k_cs_fast<false, GMAX_T2, NT_T2, MINB2>;
         }
-        if ((rc = syk_ensure_dyn_smem((const void *)k1, L1.total))) return rc;
         if ((rc = syk_ensure_dyn_smem((const void *)k2, L2.total))) return rc;
-        k1<<<(unsigned)g1, NT_T1, L1.total, s>>>(arr, o, F, L1, nullptr, nullptr, list1, cnt1);
+        // Experimental tier 1 (SYK_CS_MARCH=1): the u -> v -> w marching kernel of syk_cs_march.cuh (TMA planes, two barriers
+        // per plane).  Bit-exact, but measured SLOWER than k_cs_fast on the production chunk (3.98 vs 2.74 ms,
+        // profiles/r2_ncu_cs_march_summary.txt: its relabel / u-sum update run with few active lanes), so it is opt-in.
+        CUtensorMap tmap;
+        bool marched = false;
+        if (F.vec4 && (s7 || s13) && getenv("SYK_CS_MARCH")) {
+            constexpr int GM = 3, MB = 3;
+            using C7 = csm::Cfg<7, 13, 13, GM>;
+            using C13 = csm::Cfg<13, 13, 7, GM>;
+            if (syk_make_tmap3(&tmap, arr, 4, F.n, F.ist, s7 ? C7::WP : C13::WP, s7 ? C7::VP : C13::VP)) {
+                auto km7 = csm::k_cs_march<7, 13, 13, GM, MB>;
+                auto km13 = csm::k_cs_march<13, 13, 7, GM, MB>;
+                const int dyn = s7 ? C7::DYN_BYTES : C13::DYN_BYTES, nt = s7 ? C7::NT : C13::NT;
+                if ((rc = syk_ensure_dyn_smem(s7 ? (const void *)km7 : (const void *)km13, dyn))) return rc;
+                int per_sm = 1;
+                SYK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s7 ? (const void *)km7 : (const void *)km13, nt, dyn));
+                if (per_sm < 1) per_sm = 1;
+                long long gm = (long long)sms * per_sm;
+                if (gm > F.nsegs) gm = F.nsegs;
+                ctas1 = per_sm;
+                if (s7) km7<<<(unsigned)gm, nt, dyn, s>>>(tmap, o, F, list1, cnt1);
+                else km13<<<(unsigned)gm, nt, dyn, s>>>(tmap, o, F, list1, cnt1);
+                marched = true;
+            }
+        }
+        if (!marched) {
+            if ((rc = syk_ensure_dyn_smem((const void *)k1, L1.total))) return rc;
+            k1<<<(unsigned)g1, NT_T1, L1.total, s>>>(arr, o, F, L1, nullptr, nullptr, list1, cnt1);
+        }
         k2<<<(unsigned)g2, NT_T2, L2.total, s>>>(arr, o, F, L2, list1, cnt1, list2, cnt2);
         SYK_CUDA(cudaGetLastError());
         G.seg_list = list2;

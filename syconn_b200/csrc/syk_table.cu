@@ -4,6 +4,7 @@
 //   merge_map_dicts   syconn/proc/sd_proc.py:1300-1322     -> syk_pairs_merge
 //   id -> reducer hash  syconn/reps/rep_helper.py:143-163  -> syk_records_bucket / syk_pairs_bucket
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -62,6 +63,36 @@ int syk_ensure_dyn_smem(const void *func, int bytes) {
         have = bytes;
     }
     return SYK_OK;
+}
+
+typedef CUresult (*SykEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool syk_make_tmap3(CUtensorMap *m, const void *base, int elem_bytes, const long long n[3], const long long st[3], int box_w,
+                    int box_v) {
+    static SykEncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (SykEncodeTiledFn)p;
+        cudaGetLastError();
+    });
+    if (!fn || getenv("SYK_NO_TMA")) return false;
+    if (st[2] != 1 || ((uintptr_t)base & 15) || box_w > 256 || box_v > 256 || ((box_w * elem_bytes) & 15)) return false;
+    for (int a = 0; a < 2; ++a)
+        if (st[a] <= 0 || ((st[a] * elem_bytes) & 15) || st[a] * elem_bytes >= (1ll << 40)) return false;
+    for (int a = 0; a < 3; ++a)
+        if (n[a] <= 0 || n[a] >= (1ll << 31)) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)n[2], (cuuint64_t)n[1], (cuuint64_t)n[0]};
+    cuuint64_t strides[2] = {(cuuint64_t)(st[1] * elem_bytes), (cuuint64_t)(st[0] * elem_bytes)};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_v, 1u};
+    cuuint32_t es[3] = {1u, 1u, 1u};
+    return fn(m, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(base), dims,
+              strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 cudaStream_t syk_host_stream() {

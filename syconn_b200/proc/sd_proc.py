@@ -177,3 +177,70 @@ def write_dataset_analysis_cache(sd_path, red, extra=None):
         np.save(p, v)
         paths.append(p)
     return paths
+
+
+# ---------------------------------------------------------------------------------------------- storage writers (f3)
+def subfold_from_ix(ix, n_folders):
+    """reps/rep_helper.py:143-163 (``use_new_subfold``): the storage sub-folder of object ``ix``."""
+    assert n_folders % 10 == 0
+    order = int(np.log10(n_folders))
+    ix = int(int(ix) // 1e3 % n_folders)  # float floor division like the reference (div_base = 1e3): ids >= 2^53 round
+    id_str = "{num:0{w}d}".format(num=ix, w=order)
+    subfold = "/"
+    for idx in range(0, order, 2):
+        subfold += "%s/" % id_str[idx: idx + 2]
+    return subfold
+
+
+def write_segmentation_objects(sd_path, red, mapping=None, min_obj_vx=1, n_folders_fs=10000, voxeldata_path=None,
+                               extra_attrs=None):
+    """The writer loop of ``_write_props_to_sc_thread`` / ``_write_props_to_sv_thread`` (syconn/proc/sd_proc.py:788-1000,
+    :1003-1215) on the reduced records of ``chunked.reduce_records``: one ``attr_dict.pkl`` (``AttributeDict``) and one
+    ``voxel.pkl`` (``VoxelStorageDyn``, voxel_mode=False) per storage folder ``<sd_path>/so_storage_<n>/<subfold>/``
+    (reps/segmentation.py:336-416).  Per object with ``size >= min_obj_vx`` (:929-931): ``rep_coord`` int32 [3] (:939),
+    ``bounding_box`` [2, 3] = min / max over the object's per-chunk boxes (:940-944), ``size`` (:945), the per-chunk boxes
+    themselves as the object's voxel index ``voxel_dc[id] = bbs`` with its size and rep coord (:946-950), and
+
+      * organelle objects: ``mapping_ids`` / ``mapping_ratios`` from ``mapping = {sub_id: {cell_id: count}}``, ratios
+        normalised by the object's size (:929-937);
+      * cell supervoxels: ``extra_attrs = {name: object array aligned with red['id']}``, e.g. ``mapping_mi_ids`` /
+        ``mapping_mi_ratios`` from ``cell_mapping_attributes`` (:1166-1171).
+
+    Returns the list of written folder paths."""
+    import os
+    from ..backend.storage import AttributeDict, VoxelStorageDyn
+    ids = np.asarray(red["id"], np.uint64)
+    by_folder = defaultdict(list)
+    for i, k in enumerate(ids.tolist()):
+        by_folder[subfold_from_ix(k, n_folders_fs)].append(i)
+    base = os.path.join(sd_path, "so_storage_%d" % n_folders_fs)
+    written = []
+    for sub, rows in by_folder.items():
+        folder = base + sub
+        os.makedirs(folder, exist_ok=True)
+        attr_dc = AttributeDict(folder + "attr_dict.pkl", read_only=False, disable_locking=True)
+        voxel_dc = VoxelStorageDyn(folder + "voxel", voxel_mode=False, read_only=False, disable_locking=True,
+                                   voxeldata_path=voxeldata_path)
+        for i in rows:
+            k = int(ids[i])
+            size = int(red["size"][i])
+            if size < min_obj_vx:
+                continue
+            if mapping is not None:
+                m = mapping.get(k)
+                attr_dc[k]["mapping_ids"] = list(m.keys()) if m else []
+                attr_dc[k]["mapping_ratios"] = [v / size for v in m.values()] if m else []
+            for name, col in (extra_attrs or {}).items():
+                attr_dc[k][name] = col[i]
+            rp = np.array(red["rep_coord"][i], dtype=np.int32)
+            bbs = np.asarray(red["bbs"][i]).reshape(-1, 2, 3).astype(np.int64)   # np.concatenate of lists of lists (:940)
+            attr_dc[k]["rep_coord"] = rp
+            attr_dc[k]["bounding_box"] = np.array([bbs[:, 0].min(axis=0), bbs[:, 1].max(axis=0)])
+            attr_dc[k]["size"] = size
+            voxel_dc[k] = bbs
+            voxel_dc.increase_object_size(k, size)
+            voxel_dc.set_object_repcoord(k, rp)
+        attr_dc.push()
+        voxel_dc.push()
+        written.append(folder)
+    return written

@@ -400,3 +400,19 @@ def test_contact_site_extraction_chunk(mods):
         assert got[2] == want[2] and got[3] == want[3] and got[4] == want[4]
         assert got[5].dtype == np.uint64 and np.array_equal(got[5], want[5]) and np.array_equal(got[6], want[6])
         assert len(want[4]) > 5 and (want[5] != 0).sum() > 1000
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", ["F", "C"])
+def test_detect_cs_marching_variant_vs_oracle(order, monkeypatch):
+    """The opt-in u -> v -> w marching tier 1 (csrc/syk_cs_march.cuh, SYK_CS_MARCH=1; TMA plane loads, two barriers per
+    plane) is bit-exact too: production stencil, both memory orders, a pitch that forces slot recycling and tier-2 hand-over."""
+    import torch
+    from oracle import oracle
+    from syconn_b200 import device as dev
+    monkeypatch.setenv("SYK_CS_MARCH", "1")
+    for shape, pitch in (((90, 80, 100), (16, 16, 8)), ((150, 100, 140), (32, 32, 16)), ((100, 100, 100), (7, 7, 5))):
+        seg = dev.synth_labels(shape, origin=(5, -3, 11), pitch=pitch, seed=2, dtype=torch.int32, order=order)
+        got = dev.detect_cs(seg, (13, 13, 7)).cpu().numpy().view(np.uint64)
+        want = oracle.detect_cs(seg.cpu().numpy().view(np.uint32), (13, 13, 7))
+        assert np.array_equal(got, want), (shape, pitch, order)
