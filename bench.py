@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-workers", type=int, default=4, help="host threads issuing the host-buffer calls")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stress", action="store_true", help="skip the config-5 stress section (N = 1 only)")
     return ap.parse_args()
 
 
@@ -336,6 +337,8 @@ def run_ours(args):
             line["e2e"] = e2e
     elif rank == 0:
         line["e2e"] = None
+    if rank == 0 and world == 1 and not args.no_stress:
+        line["stress"] = stress_section(local)
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"], _ = cpu_baseline(args.cpu_seconds)
     if world > 1:
@@ -406,6 +409,72 @@ def parity_block(pipe, chunks, res, rank, world):
     out["status"] = "ok" if not problems and int(bad.item()) == 0 else "FAILED"
     if problems:
         out["problems"] = problems
+    return out
+
+
+def stress_section(local):
+    """BASELINE config 5 and the second workload point, measured inside the same run (device-resident, CUDA events, min
+    of 3 after a warm-up): 1e7 distinct ids through find_object_properties, the stencil sweep of detect_cs, supervoxel
+    pitch 16x16x8 on the production chunk (runs in the 64-id tier), near-random labels (generic kernel)."""
+    import torch
+    from syconn_b200 import device as dev
+
+    def timeit(fn, n=3, warm=1):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return min(ts)
+
+    out = {"unit": "GVoxels/s", "timing": "CUDA events, min of 3 after 1 warm-up, device-resident inputs"}
+    with ClockSampler(local) as clk:
+        S = 224
+        ar = torch.arange(S ** 3, dtype=torch.int64, device="cuda")
+        props = {}
+        for name, lab in (("unique_id_per_voxel_11.2M_ids", (ar * 2654435761 + 1).reshape(S, S, S)),
+                          ("objects_of_2x2x2_voxels_1.4M_ids", dev.synth_labels((S, S, S), pitch=(2, 2, 2), warp_amp=0, seed=3))):
+            tab = dev.IdTable(1 << 25)
+
+            def run():
+                tab.clear()
+                dev.find_object_properties(tab, lab)
+            ms = timeit(run)
+            n, ovf = tab.count()
+            props[name] = {"ms": ms, "value": S ** 3 / ms / 1e6, "ids": int(n), "ids_expected": int((torch.unique(lab) != 0).sum()),
+                           "table_overflow": bool(ovf)}
+            tab.close()
+        del ar
+        out["find_object_properties_224^3"] = props
+        sweep = {}
+        for st in ((3, 3, 3), (5, 5, 3), (7, 7, 3), (9, 9, 5), (13, 13, 7), (15, 15, 9), (17, 17, 9)):
+            shape = tuple(256 + s - 1 for s in st)
+            seg = dev.synth_labels(shape, pitch=CELL_PITCH, seed=1, dtype=torch.int32, order="F")
+            o = dev.detect_cs(seg, st)
+            ms = timeit(lambda: dev.detect_cs(seg, st, out=o))
+            sweep["x".join(map(str, st))] = {"ms": ms, "value": 256 ** 3 / ms / 1e6,
+                                             "contact_fraction": float((o != 0).float().mean())}
+        out["detect_cs_stencil_sweep_256^3_pitch_32x32x16"] = sweep
+        pitches = {}
+        for pitch in ((32, 32, 16), (16, 16, 8)):
+            seg = dev.synth_labels((536, 536, 530), origin=(500, -12, 1015), pitch=pitch, seed=0, dtype=torch.int32, order="F")
+            o = dev.detect_cs(seg, STENCIL)
+            ms = timeit(lambda: dev.detect_cs(seg, STENCIL, out=o))
+            pitches["x".join(map(str, pitch))] = {"ms": ms, "value": 512 ** 3 / ms / 1e6,
+                                                  "contact_fraction": float((o != 0).float().mean())}
+            del seg, o
+        out["detect_cs_production_chunk_by_supervoxel_pitch"] = pitches
+        rnd = torch.randint(1, 2 ** 31 - 1, (96 + 12, 96 + 12, 96 + 6), dtype=torch.int32, device="cuda")
+        o = dev.detect_cs(rnd, STENCIL)
+        ms = timeit(lambda: dev.detect_cs(rnd, STENCIL, out=o), n=2)
+        out["detect_cs_random_labels_96^3"] = {"ms": ms, "value": 96 ** 3 / ms / 1e6}
+    out["clocks"] = clk.summary()
     return out
 
 

@@ -235,6 +235,20 @@ int syk_close_contacts_host(void *cs_host, int elem_bytes, const int64_t shape[3
                             const int32_t *bbox_host, uint64_t n_ids, int n_closings, int n_dilations);
 void syk_free(void *p);
 
+/* ---- organelle instance segmentation, first slice (row f4) --------------------------------------------------- */
+/* scipy.ndimage.label(vol > threshold) with the default 6-connectivity structure, as called by
+ * _object_segmentation_thread (syconn/extraction/object_extraction_steps.py:302-303, :350-352).  labels_dev receives
+ * uint32 labels 1..n in the order of each component's first voxel in LOGICAL (x, y, z) scan order -- bit-identical to
+ * scipy -- whatever the memory order of the view; *n_labels_host = n.  elem_bytes 1, 2, 4 or 8; fewer than 2^32 - 16
+ * voxels per call.  Synchronises `stream` (the number of components sizes the ranking buffers). */
+int syk_label_components(const void *vol_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3], uint64_t threshold,
+                         uint32_t *labels_dev, const int64_t label_strides[3], uint64_t *n_labels_host, void *stream);
+/* The co-located label pairs of two label blocks over the same voxels (the stitch region of two neighbouring chunks,
+ * _make_stitch_list_thread, object_extraction_steps.py:583-606): for every voxel with a != 0 and b != 0 the pair
+ * (a + a_offset, b + b_offset) is counted in `pairs` (export it with syk_pairs_export). */
+int syk_label_overlap_pairs(syk_pairs_t *pairs, const uint32_t *a_dev, const int64_t a_strides[3], const uint32_t *b_dev,
+                            const int64_t b_strides[3], const int64_t shape[3], uint64_t a_offset, uint64_t b_offset, void *stream);
+
 /* ---- storage codec (row f3; host code, no GPU needed) ----------------------------------------------------- */
 /* LZ4 block format, the codec behind the reference's CompressedStorage / VoxelStorageDyn values
  * (python-lz4 `lz4.block.compress/decompress`, syconn/handler/compression.py:83-127, backend/storage.py:52-93).

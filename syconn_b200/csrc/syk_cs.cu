@@ -10,6 +10,7 @@
 // id).  Windows with more than 32 distinct ids fall back to a block-cooperative shared-memory hash table.
 // The arg-max follows the reference exactly: ids 0 and centre excluded, ties -> smallest id.
 #include <stdlib.h>
+#include <string.h>
 
 #include "syk_common.cuh"
 #include "syk_cs_fast.cuh"
@@ -364,6 +365,14 @@ static void cs_plan(const int64_t shape[3], const int64_t strides[3], const int3
                 ax[i] = ax[j];
                 ax[j] = t;
             }
+    // The box-sum kernels keep the sums along v in 4-bit fields (window <= 15) and those along u, v in 8-bit fields.  Only w
+    // is tied to the memory layout: when the stencil along the natural v axis is too wide but the one along u is not
+    // (e.g. 17 x 17 x 9 on x-fastest data: u = z (9), v = y (17)), march along the other axis instead.
+    if (stencil[ax[1]] > 15 && stencil[ax[0]] <= 15 && stencil[ax[0]] >= 3) {
+        const int t = ax[0];
+        ax[0] = ax[1];
+        ax[1] = t;
+    }
     G.total = 1;
     for (int a = 0; a < 3; ++a) {
         const int l = ax[a];
@@ -423,6 +432,10 @@ static bool fast_plan(const CsGeom &C, csfast::FastGeom &F) {
     F.nsegs = F.segs[0] * F.segs[1] * F.segs[2];
     F.elem_bytes = C.elem_bytes;
     F.vec4 = 0;
+    F.tma = 0;
+    F.edges = nullptr;
+    F.edge_bytes = 0;
+    for (int a = 0; a < 3; ++a) F.est[a] = 0;
     F.pair_ok = (2 * C.sten[0] * C.sten[1] <= 255) ? 1 : 0;
     F.out_vec = 0;
     if (F.VP * F.WP / 4 > MAX_NQUAD || F.WP > MAX_WP || F.nsegs >= (1ll << 30)) return false;
@@ -430,9 +443,9 @@ static bool fast_plan(const CsGeom &C, csfast::FastGeom &F) {
     return L.total <= 200 * 1024;
 }
 
-static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_strides, const void *arr, int elem_bytes,
-                     const int64_t strides[3], const int64_t shape[3], const int32_t stencil[3], uint64_t *out,
-                     const int64_t out_strides[3], cudaStream_t s, int first_seen = 0) {
+static int cs_launch_impl(const void *edges, int edge_bytes, const int64_t *edge_strides, const void *arr, int elem_bytes,
+                          const int64_t strides[3], const int64_t shape[3], const int32_t stencil[3], uint64_t *out,
+                          const int64_t out_strides[3], cudaStream_t s, int first_seen) {
     int rc = syk_require_device();
     if (rc) return rc;
     SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
@@ -463,8 +476,13 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
     long long grid = (long long)sms * bps;
     if (grid > G.ntiles) grid = G.ntiles;
     csfast::FastGeom F;
-    if (edges == nullptr && !first_seen && !getenv("SYK_CS_GENERIC") && fast_plan(G, F)) {
+    if (!first_seen && !getenv("SYK_CS_GENERIC") && fast_plan(G, F)) {
         using namespace csfast;
+        if (edges != nullptr) {  // explicit edge mask: same kernels, the mask replaces the fused boundary test
+            F.edges = edges;
+            F.edge_bytes = edge_bytes;
+            for (int a = 0; a < 3; ++a) F.est[a] = G.est[a];
+        }
         // tier 1 (<= 24 ids near the plane, many CTAs/SM) -> tier 2 (<= 64 ids) on the listed segments -> generic kernel
         unsigned *hard = nullptr;  // [count1, count2, list1[nsegs], list2[nsegs]]
         SYK_CUDA(cudaMallocAsync((void **)&hard, sizeof(unsigned) * (size_t)(2 * F.nsegs + 2), s));
@@ -487,11 +505,25 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
         unsigned long long *o = (unsigned long long *)out;
         // tier 1 is specialised for the production stencil [13, 13, 7] in both memory orders (x fastest: internal
         // (u, v, w) = (7, 13, 13); C order: (13, 13, 7)); any other stencil runs the same kernel with run-time geometry
-        void (*k1)(const void *, unsigned long long *, FastGeom, FastSmem, const unsigned *, const unsigned *, unsigned *, unsigned *);
-        void (*k2)(const void *, unsigned long long *, FastGeom, FastSmem, const unsigned *, const unsigned *, unsigned *, unsigned *);
+        void (*k1)(const void *, unsigned long long *, FastGeom, FastSmem, const unsigned *, const unsigned *, unsigned *, unsigned *,
+                   const CUtensorMap);
+        void (*k2)(const void *, unsigned long long *, FastGeom, FastSmem, const unsigned *, const unsigned *, unsigned *, unsigned *,
+                   const CUtensorMap);
+        // input planes by TMA: one box of WP x VP x 1 uint32 per plane (the haloed cross-section of a segment)
+        CUtensorMap tmap_fast;
+        memset(&tmap_fast, 0, sizeof(tmap_fast));
+        F.tma = (F.vec4 && !getenv("SYK_CS_NO_TMA") && syk_make_tmap3(&tmap_fast, arr, 4, F.n, F.ist, F.WP, F.VP)) ? 1 : 0;
         const bool s7 = F.sten[0] == 7 && F.sten[1] == 13 && F.sten[2] == 13 && !getenv("SYK_CS_NOSPEC");
         const bool s13 = F.sten[0] == 13 && F.sten[1] == 13 && F.sten[2] == 7 && !getenv("SYK_CS_NOSPEC");
-        if (F.vec4) {
+        if (edges != nullptr) {  // explicit edge mask: run-time-geometry kernels with the EDGES variant of the boundary phase
+            if (F.vec4) {
+                k1 = k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 0, 0, 0, true>;
+                k2 = k_cs_fast<true, GMAX_T2, NT_T2, MINB2, 0, 0, 0, true>;
+            } else {
+                k1 = k_cs_fast<false, GMAX_T1, NT_T1, MINB1, 0, 0, 0, true>;
+                k2 = k_cs_fast<false, GMAX_T2, NT_T2, MINB2, 0, 0, 0, true>;
+            }
+        } else if (F.vec4) {
             k1 = s7 ? k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 7, 13, 13>
                     : s13 ? k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 13, 13, 7> : k_cs_fast<true, GMAX_T1, NT_T1, MINB1>;
             k2 = k_cs_fast<true, GMAX_T2, NT_T2, MINB2>;
@@ -505,7 +537,7 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
         // profiles/r2_ncu_cs_march_summary.txt: its relabel / u-sum update run with few active lanes), so it is opt-in.
         CUtensorMap tmap;
         bool marched = false;
-        if (F.vec4 && (s7 || s13) && getenv("SYK_CS_MARCH")) {
+        if (F.vec4 && (s7 || s13) && edges == nullptr && getenv("SYK_CS_MARCH")) {
             constexpr int GM = 3, MB = 3;
             using C7 = csm::Cfg<7, 13, 13, GM>;
             using C13 = csm::Cfg<13, 13, 7, GM>;
@@ -527,9 +559,9 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
         }
         if (!marched) {
             if ((rc = syk_ensure_dyn_smem((const void *)k1, L1.total))) return rc;
-            k1<<<(unsigned)g1, NT_T1, L1.total, s>>>(arr, o, F, L1, nullptr, nullptr, list1, cnt1);
+            k1<<<(unsigned)g1, NT_T1, L1.total, s>>>(arr, o, F, L1, nullptr, nullptr, list1, cnt1, tmap_fast);
         }
-        k2<<<(unsigned)g2, NT_T2, L2.total, s>>>(arr, o, F, L2, list1, cnt1, list2, cnt2);
+        k2<<<(unsigned)g2, NT_T2, L2.total, s>>>(arr, o, F, L2, list1, cnt1, list2, cnt2, tmap_fast);
         SYK_CUDA(cudaGetLastError());
         G.seg_list = list2;
         G.seg_count = cnt2;
@@ -555,7 +587,8 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
             cudaMemcpyAsync(nh, hard, sizeof(nh), cudaMemcpyDeviceToHost, s);
             cudaStreamSynchronize(s);
             fprintf(stderr, "[syk] detect_cs fast path: %lld segments, %u redone by tier 2, %u by the generic kernel; smem %d / %d B, "
-                            "CTAs/SM %d / %d, vec4=%d out_vec=%d\n", F.nsegs, nh[0], nh[1], L1.total, L2.total, ctas1, ctas2, F.vec4, F.out_vec);
+                            "CTAs/SM %d / %d, vec4=%d out_vec=%d tma=%d\n", F.nsegs, nh[0], nh[1], L1.total, L2.total, ctas1, ctas2, F.vec4,
+                    F.out_vec, F.tma);
         }
         SYK_CUDA(cudaFreeAsync(hard, s));
         return SYK_OK;
@@ -563,6 +596,29 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
     k_detect_cs<<<(unsigned)grid, CS_THREADS, smem, s>>>(arr, edges, (unsigned long long *)out, G);
     SYK_CUDA(cudaGetLastError());
     return SYK_OK;
+}
+
+// detect_cs on 64-bit ids: the reference takes the boundary mask on the FULL 64-bit values and only then narrows the ids to
+// uint32 for the window histogram (find_object_properties.py:466-468) -- neighbours that are equal modulo 2^32 are
+// still boundaries.  The mask is therefore computed first (64-bit compares) and handed to the kernels as explicit edges.
+static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_strides, const void *arr, int elem_bytes,
+                     const int64_t strides[3], const int64_t shape[3], const int32_t stencil[3], uint64_t *out,
+                     const int64_t out_strides[3], cudaStream_t s, int first_seen = 0) {
+    if (edges != nullptr || elem_bytes != 8 || first_seen || !shape || !strides || !arr)
+        return cs_launch_impl(edges, edge_bytes, edge_strides, arr, elem_bytes, strides, shape, stencil, out, out_strides, s, first_seen);
+    const long long total = shape[0] * shape[1] * shape[2];
+    if (total <= 0) return cs_launch_impl(nullptr, 0, nullptr, arr, elem_bytes, strides, shape, stencil, out, out_strides, s, 0);
+    int rc = syk_require_device();
+    if (rc) return rc;
+    unsigned char *mask = nullptr;
+    SYK_CUDA(cudaMallocAsync((void **)&mask, (size_t)total, s));
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_seg_boundaries<<<(unsigned)blocks, 256, 0, s>>>(arr, 8, shape[0], shape[1], shape[2], strides[0], strides[1], strides[2], mask);
+    const int64_t est[3] = {shape[1] * shape[2], shape[2], 1};
+    rc = cs_launch_impl(mask, 1, est, arr, 8, strides, shape, stencil, out, out_strides, s, 0);
+    cudaFreeAsync(mask, s);
+    return rc;
 }
 
 }  // namespace

@@ -17,6 +17,8 @@
 //     generic kernel.
 // All arithmetic is integer; results are bit-identical to the generic path.
 #pragma once
+#include <cuda.h>
+
 #include "syk_common.cuh"
 
 namespace csfast {
@@ -64,6 +66,12 @@ struct FastGeom {
     int vec4;          // 16-byte aligned uint32 rows: quads are loaded with one LDG.128
     int pair_ok;       // 2 * su * sv <= 255: two ring sums may be added in 8-bit fields before widening
     int out_vec;       // output rows 16-byte aligned and contiguous along w: zero runs are stored 16 bytes at a time
+    int tma;           // vec4 && a tensor map describes the input: planes arrive as ONE cp.async.bulk.tensor box each
+    // explicit edge mask (process_block_nonzero(edges, arr, ...), block_processing_C.pyx:66): replaces the boundary test;
+    // nullptr = fused detect_seg_boundaries
+    const void *edges;
+    long long est[3];  // edge-volume strides (elements) along u, v, w
+    int edge_bytes;    // 1 or 4
 };
 
 struct FastSmem {  // offsets in bytes into dynamic shared memory
@@ -71,16 +79,17 @@ struct FastSmem {  // offsets in bytes into dynamic shared memory
 };
 
 __host__ __device__ __forceinline__ int fast_align16(int bytes) { return (bytes + 15) & ~15; }  // regions are 16-byte aligned
+__host__ __device__ __forceinline__ int fast_align128(int bytes) { return (bytes + 127) & ~127; }  // TMA destinations
 __host__ __device__ __forceinline__ FastSmem fast_layout(int VP, int WP, int CR, int CF, int GMAX) {
     FastSmem L;
     const int plane = VP * WP;
     const int oplane = TV * WP;
     L.raw = 0;
-    L.comp = L.raw + 2 * fast_align16(plane * 4);           // two raw planes: the next one streams in with cp.async
+    L.comp = L.raw + 2 * fast_align128(plane * 4);          // two raw planes: the next one streams in (TMA box / cp.async)
     L.ssum = L.comp + fast_align16(CR * plane);            // ring of compact-index planes, 1 byte per voxel
     L.cflag = L.ssum + fast_align16(GMAX * oplane * 8);    // uint2 {even slots, odd slots} in 8-bit fields
     L.elist = L.cflag + fast_align16(CF * TV * TW);
-    L.total = L.elist + fast_align16(TV * TW * 2);
+    L.total = L.elist + fast_align16(TV * TW * 2) + 128;    // + slack: the kernel aligns its base to 128 bytes
     return L;
 }
 inline FastSmem fast_layout(const FastGeom &G, int GMAX) { return fast_layout(G.VP, G.WP, G.CR, G.CF, GMAX); }
@@ -175,6 +184,33 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// TMA plane loads: one cp.async.bulk.tensor.3d box (WP x VP x 1 uint32, zero fill outside the volume) per input plane,
+// completion on an mbarrier per raw buffer
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "CSF_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra CSF_DONE;\n"
+        "bra CSF_WAIT;\n"
+        "CSF_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *tm, int c0, int c1, int c2, unsigned bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(reinterpret_cast<unsigned long long>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+
 // sliding v-sum (window sv) of the indicator words of one column of a compact plane: acc[q], q = 0..7
 __device__ __forceinline__ void vsum8(const unsigned char *col, int WP, int sv, const unsigned *lut, unsigned (&acc)[8]) {
     unsigned head[8];
@@ -196,11 +232,12 @@ __device__ __forceinline__ void vsum8(const unsigned char *col, int WP, int sv, 
 // seg_list == nullptr: all G.nsegs segments; otherwise the *seg_count segments named in seg_list (tier 2).
 // SU/SV/SW != 0: stencil known at compile time (must equal G.sten) -- plane pitches, ring depths and the shared-memory
 // layout fold into immediates and the window loops unroll.
-template <bool VEC4, int GMAX, int NT, int MINB, int SU = 0, int SV = 0, int SW = 0>
+// EDGES: explicit edge mask (G.edges) instead of the fused boundary test -- a separate instantiation so that detect_cs pays nothing
+template <bool VEC4, int GMAX, int NT, int MINB, int SU = 0, int SV = 0, int SW = 0, bool EDGES = false>
 __global__ void __launch_bounds__(NT, MINB)
 k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, FastGeom G, FastSmem Lrt,
           const unsigned *__restrict__ seg_list, const unsigned *__restrict__ seg_count,
-          unsigned *__restrict__ hard_list, unsigned *__restrict__ hard_count) {
+          unsigned *__restrict__ hard_list, unsigned *__restrict__ hard_count, const __grid_constant__ CUtensorMap tmap) {
     using Hash = HashT<GMAX>;
     constexpr int KMAX = Hash::KMAX;
     constexpr unsigned long long ALL_SLOTS = Hash::ALL_SLOTS;
@@ -214,7 +251,8 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
     const int CR = FIX ? SU + 1 : G.CR, CF = FIX ? SU / 2 + 1 : G.CF;
     const bool pair_ok = FIX ? (2 * SU * SV <= 255) : (G.pair_ok != 0);
     const FastSmem L = FIX ? fast_layout(VP, WP, CR, CF, GMAX) : Lrt;
-    extern __shared__ __align__(16) unsigned char sm[];
+    extern __shared__ __align__(16) unsigned char sm_base[];
+    unsigned char *sm = sm_base + ((128u - ((unsigned)__cvta_generic_to_shared(sm_base) & 127u)) & 127u);
     unsigned *raw = reinterpret_cast<unsigned *>(sm + L.raw);  // raw[(p & 1) * rawpitch ...]: input plane p
     unsigned char *comp = sm + L.comp;
     uint2 *ssum = reinterpret_cast<uint2 *>(sm + L.ssum);
@@ -225,7 +263,18 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
     const int tid = threadIdx.x;
     const int plane = VP * WP, oplane = TV * WP;
     const int nquad = plane >> 2, qpr = WP >> 2;  // quads per plane / per row
-    const int rawpitch = fast_align16(plane * 4) >> 2;  // words between the two raw planes
+    const int rawpitch = fast_align128(plane * 4) >> 2;  // words between the two raw planes
+    const bool TMA = VEC4 && G.tma != 0;
+    __shared__ __align__(8) unsigned long long mbar[2];
+    const unsigned bar_sa = (unsigned)__cvta_generic_to_shared(&mbar[0]);
+    const unsigned raw_sa = (unsigned)__cvta_generic_to_shared(raw);
+    if (TMA && tid == 0) {
+        mbar_init(bar_sa, 1u);
+        mbar_init(bar_sa + 8u, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned par0 = 0u, par1 = 0u;  // phase parity of the next completion of raw buffer 0 / 1 (uniform over the CTA)
+    int pend = -1;                  // raw buffer with a TMA load in flight that nobody has waited for yet
 
     for (int i = tid; i < GMAX * (KMAX + 8); i += NT) {
         const int g = i / (KMAX + 8), j = i - g * (KMAX + 8);
@@ -359,13 +408,22 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
         };
 
         // prologue: plane 0 -> raw
+        if (TMA) {
+            if (tid == 0) {
+                mbar_expect_tx(bar_sa, (unsigned)plane * 4u);
+                tma_load_3d(raw_sa, &tmap, (int)w0, (int)v0, (int)u0, bar_sa);
+            }
+            mbar_wait(bar_sa, par0);
+            par0 ^= 1u;
+        } else {
 #pragma unroll
-        for (int k = 0; k < MAXQ; ++k) {
-            const int q = tid + k * NT;
-            if (q < nquad) {
-                uint4 v;
-                load_quad(k, u0, v);
-                reinterpret_cast<uint4 *>(raw)[q] = v;
+            for (int k = 0; k < MAXQ; ++k) {
+                const int q = tid + k * NT;
+                if (q < nquad) {
+                    uint4 v;
+                    load_quad(k, u0, v);
+                    reinterpret_cast<uint4 *>(raw)[q] = v;
+                }
             }
         }
         __syncthreads();
@@ -381,10 +439,17 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             unsigned *rawn = raw + ((p + 1) & 1) * rawpitch;
             uint4 pre[VEC4 ? 1 : MAXQ];
             int hidx[MAXQ][4];
+            if (TMA && tid == 0 && p + 1 < NP) {  // everybody left raw plane p - 1 at the last barrier of the previous step
+                const unsigned b = bar_sa + 8u * (unsigned)((p + 1) & 1);
+                mbar_expect_tx(b, (unsigned)plane * 4u);
+                tma_load_3d(raw_sa + (unsigned)(((p + 1) & 1) * rawpitch * 4), &tmap, (int)w0, (int)v0, (int)(u0 + p + 1), b);
+            }
+            if (TMA && p + 1 < NP) pend = (p + 1) & 1;
 #pragma unroll
             for (int k = 0; k < MAXQ; ++k) {
                 const int q = tid + k * NT;
-                if (VEC4) {
+                if (TMA) {
+                } else if (VEC4) {
                     if (q < nquad && p + 1 < NP) {
                         const bool in = gu + 1 < G.n[0] && qok[k] != 0u;
                         const unsigned *src = reinterpret_cast<const unsigned *>(arr) + (in ? (gu + 1) * G.ist[0] + qoff[k] : 0);
@@ -480,7 +545,25 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 unsigned D = ((C ^ ld4(c0 + rowo, col)) & mUlo) | ((C ^ ld4(c2 + rowo, col)) & mUhi);
                 D |= ((C ^ ld4(c1 + rowo - WP, col)) & mVlo) | ((C ^ ld4(c1 + rowo + WP, col)) & mVhi);
                 D |= ((C ^ ld4(c1 + rowo, col - 1)) & mL) | ((C ^ ld4(c1 + rowo, col + 1)) & mR);
-                reinterpret_cast<unsigned *>(cflag + (rf ? rf - 1 : CF - 1) * (TV * TW))[tid] = C | (nz_bytes(D) & nz_bytes(C));
+                unsigned flags = nz_bytes(D) & nz_bytes(C);
+                if (EDGES) {  // the caller's mask decides (a flagged background centre is legal: its id is 0)
+                    flags = 0u;
+                    const long long ev = v0 + oq_b + ov;
+                    if (ev < G.n[1]) {
+                        const long long eb = cu * G.est[0] + ev * G.est[1];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const long long ew = w0 + oq_c + e + ow;
+                            if (ew < G.n[2]) {
+                                const long long a = eb + ew * G.est[2];
+                                const bool on = G.edge_bytes == 4 ? (__ldg((const unsigned *)G.edges + a) != 0u)
+                                                                  : (__ldg((const unsigned char *)G.edges + a) != 0);
+                                flags |= on ? (0x80u << (8 * e)) : 0u;
+                            }
+                        }
+                    }
+                }
+                reinterpret_cast<unsigned *>(cflag + (rf ? rf - 1 : CF - 1) * (TV * TW))[tid] = C | flags;
             }
             // C2. v-sums (4-bit fields) of the entering plane p and of the leaving plane p - su; their difference
             //     advances the running sum over the last su planes (8-bit fields)
@@ -511,7 +594,13 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             }
             if (!early_d) __syncthreads();  // the flags of plane p - ou were written in this very phase
             compact_outputs(p, rf);
-            if (VEC4) cp_async_wait_all();  // this thread's part of raw plane p + 1 has landed; the barrier publishes all parts
+            if (TMA) {  // raw plane p + 1 has landed (every thread observes the completion itself)
+                if (p + 1 < NP) {
+                    if ((p + 1) & 1) { mbar_wait(bar_sa + 8u, par1); par1 ^= 1u; }
+                    else { mbar_wait(bar_sa, par0); par0 ^= 1u; }
+                    pend = -1;
+                }
+            } else if (VEC4) cp_async_wait_all();  // this thread's part of raw plane p + 1 has landed; the barrier publishes all parts
             __syncthreads();
             // D. boundary voxels of plane uo = p - su + 1: final sum along w and arg-max
             const int uo = p - su + 1;
@@ -569,7 +658,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                     }
                     unsigned long long res = 0ull;
                     if (best >> 16) {
-                        const unsigned center = H.ids[jc - 1], key = H.ids[best & 0xFFu];
+                        const unsigned center = (!EDGES || jc) ? H.ids[jc - 1] : 0u, key = H.ids[best & 0xFFu];
                         res = center > key ? (((unsigned long long)key << 32) + center) : (((unsigned long long)center << 32) + key);
                     }
                     orow[(v0 + b) * G.ost[1] + (w0 + c) * G.ost[2]] = res;
@@ -578,7 +667,12 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             // no barrier here: the next iteration's pass 1 only touches the hash; its barrier orders everything else
         }
         if (aborted) {
-            if (VEC4) cp_async_wait_all();  // the copy of the next plane must not land in the next segment's buffers
+            // the copy of the next plane must not land in the next segment's buffers
+            if (TMA) {
+                if (pend == 1) { mbar_wait(bar_sa + 8u, par1); par1 ^= 1u; }
+                else if (pend == 0) { mbar_wait(bar_sa, par0); par0 ^= 1u; }
+                pend = -1;
+            } else if (VEC4) cp_async_wait_all();
             if (tid == 0) hard_list[atomicAdd(hard_count, 1u)] = (unsigned)seg;
         }
     }

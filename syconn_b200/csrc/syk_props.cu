@@ -483,7 +483,19 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
             const unsigned lv0 = (unsigned)((b % (TV / R)) * R);
             const T *cb = stage + (size_t)sb * buf_elems;
             unsigned nzs = 0u;
-            if (org_mode) {
+            bool empty = false;
+            if (org_mode) {  // organelles are sparse: most batches hold no voxel at all -- 16-byte loads, OR-reduced, no run logic
+                const uint4 *q4 = reinterpret_cast<const uint4 *>(cb);
+                uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int i = 0; i < (int)(R * 32 * sizeof(T) / 16 / 32); ++i) {
+                    const uint4 x = q4[i * 32 + lane];
+                    acc.x |= x.x; acc.y |= x.y; acc.z |= x.z; acc.w |= x.w;
+                }
+                empty = !__any_sync(FULL, (acc.x | acc.y | acc.z | acc.w) != 0u);
+            }
+            if (empty) {
+            } else if (org_mode) {
                 // staged channel 0 = organelle (its props are accumulated as the "cell" channel); the real cell volume is
                 // fetched only where the organelle is non-zero -- asynchronously (cp.async, zero fill elsewhere), so that
                 // the DRAM round trip overlaps the props work of the same batch instead of stalling the warp

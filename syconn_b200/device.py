@@ -261,3 +261,24 @@ def bucket_pairs(pairs, n_owners, stream=None):
     check(_lib.load().syk_pairs_bucket(pairs.data_ptr(), pairs.shape[0], n_owners, out.data_ptr(), counts.data_ptr(),
                                        _stream_ptr(stream)))
     return out, counts
+
+
+def label_components(vol, threshold=0, out=None, stream=None):
+    """syk_label_components: ``scipy.ndimage.label(vol > threshold)`` (6-connectivity) on a CUDA tensor [X,Y,Z] of any
+    integer dtype and strides -> (int32 label tensor laid out like ``vol``, number of components)."""
+    eb = vol.element_size()
+    if out is None:
+        order = sorted(range(3), key=lambda a: -abs(vol.stride(a)))
+        phys = torch.empty([vol.shape[a] for a in order], dtype=torch.int32, device=vol.device)
+        out = phys.permute([order.index(a) for a in range(3)])
+    n = C.c_uint64()
+    check(_lib.load().syk_label_components(vol.data_ptr(), eb, i64(vol.shape), i64(_strides(vol)), int(threshold), out.data_ptr(),
+                                           i64(_strides(out)), C.byref(n), _stream_ptr(stream)))
+    return out, int(n.value)
+
+
+def label_overlap_pairs(pairs, a, b, a_offset=0, b_offset=0, stream=None):
+    """syk_label_overlap_pairs: count the (a + a_offset, b + b_offset) pairs of two int32 label blocks of equal shape."""
+    assert tuple(a.shape) == tuple(b.shape) and a.dtype == torch.int32 and b.dtype == torch.int32
+    check(_lib.load().syk_label_overlap_pairs(pairs.h, a.data_ptr(), i64(_strides(a)), b.data_ptr(), i64(_strides(b)), i64(a.shape),
+                                              int(a_offset), int(b_offset), _stream_ptr(stream)))

@@ -147,8 +147,11 @@ def test_detect_cs_vs_oracle_random(mods, seed, shape, st):
     want = oracle.detect_cs(seg, st)
     assert np.array_equal(mods["fop"].detect_cs(seg, st), want)
     assert np.array_equal(mods["fop"].detect_cs(np.asfortranarray(seg), st), want)
-    # uint64 input narrowed like .astype(np.uint32)
+    # uint64 input: boundary mask on the 64-bit values, window histogram on the ids narrowed like .astype(np.uint32)
+    # (find_object_properties.py:466-468); here even the background carries high bits, i.e. it is a 64-bit id of its own
     seg64 = seg.astype(np.uint64) | (np.uint64(3) << np.uint64(40))
+    assert np.array_equal(mods["fop"].detect_cs(seg64, st), oracle.detect_cs(seg64, st))
+    seg64 = np.where(seg != 0, seg64, np.uint64(0))
     assert np.array_equal(mods["fop"].detect_cs(seg64, st), want)
     edges = oracle.detect_seg_boundaries(seg).astype(np.uint32)
     assert np.array_equal(mods["bpc"].process_block_nonzero(edges, seg, st), want)
@@ -416,3 +419,68 @@ def test_detect_cs_marching_variant_vs_oracle(order, monkeypatch):
         got = dev.detect_cs(seg, (13, 13, 7)).cpu().numpy().view(np.uint64)
         want = oracle.detect_cs(seg.cpu().numpy().view(np.uint32), (13, 13, 7))
         assert np.array_equal(got, want), (shape, pitch, order)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_process_block_nonzero_explicit_edges_fast_path(order):
+    """process_block_nonzero(edges, arr, stencil) with a caller-supplied mask (INTEGRATION.md mode 1: the reference's own
+    numba detect_seg_boundaries + the shadowed Cython module) runs the box-sum kernels too: the mask only replaces the
+    fused boundary test.  Random masks flag background centres and interior voxels as well (block_processing_C.pyx:66-73)."""
+    import torch
+    from oracle import oracle
+    from syconn_b200 import device as dev
+    rng = np.random.default_rng(5)
+    for shape, pitch, st in (((70, 64, 90), (16, 16, 8), (13, 13, 7)), ((90, 60, 70), (24, 20, 12), (7, 7, 3)),
+                             ((64, 64, 64), (9, 9, 9), (5, 5, 3))):
+        seg = dev.synth_labels(shape, origin=(3, 1, -2), pitch=pitch, seed=4, dtype=torch.int32, order=order)
+        seg_np = seg.cpu().numpy().view(np.uint32)
+        for kind in ("boundary", "random"):
+            if kind == "boundary":
+                edges_np = oracle.detect_seg_boundaries(seg_np).astype(np.uint32)
+            else:
+                edges_np = (rng.random(shape) < 0.15).astype(np.uint32) * np.uint32(7)
+            want = oracle.process_block_nonzero(edges_np, np.ascontiguousarray(seg_np), st)
+            for edt in (torch.int32, torch.uint8):
+                e = torch.from_numpy((edges_np != 0).astype(np.uint8) if edt == torch.uint8 else edges_np.view(np.int32)).cuda()
+                if order == "F":
+                    e = e.permute(2, 1, 0).contiguous().permute(2, 1, 0)
+                got = dev.process_block_nonzero(e, seg, st).cpu().numpy().view(np.uint64)
+                assert np.array_equal(got, want), (shape, st, kind, edt, order)
+
+
+@pytest.mark.gpu
+def test_detect_cs_uint64_boundaries_use_all_64_bits():
+    """find_object_properties.py:466-468: detect_seg_boundaries sees the 64-bit ids, the window histogram the ids narrowed to
+    uint32.  Two neighbours that are equal modulo 2^32 still form a boundary, whose voxels then report the most frequent
+    OTHER narrowed id of the window."""
+    import torch
+    from oracle import oracle
+    from syconn_b200 import device as dev
+    from syconn_b200.extraction.find_object_properties import detect_cs
+    a = np.zeros((30, 24, 26), np.uint64)
+    a[:, :12, :] = np.uint64(5) | (np.uint64(1) << np.uint64(32))
+    a[:, 12:, :] = np.uint64(5) | (np.uint64(2) << np.uint64(32))     # same low word, different id
+    a[:, 13:, 13:] = np.uint64(9)                                     # a third id inside the window of the 5|5 interface
+    for st in ((13, 13, 7), (5, 5, 3)):
+        want = oracle.detect_cs(a, st)
+        assert want[:, 11 - st[1] // 2, :].any()                      # the equal-mod-2^32 interface does produce contacts
+        got_host = detect_cs(a, st)
+        got_dev = dev.detect_cs(torch.from_numpy(a.view(np.int64)).cuda(), st).cpu().numpy().view(np.uint64)
+        assert np.array_equal(got_host, want) and np.array_equal(got_dev, want), st
+
+
+@pytest.mark.gpu
+def test_detect_cs_wide_stencils_march_along_the_other_axis():
+    """Stencils wider than 15 along the natural v axis (17 x 17 x 9 on x-fastest data) stay on the box-sum path by marching
+    along v instead of u (csrc/syk_cs.cu::cs_plan); C-order data with 17 along both slow axes uses the generic kernel.
+    Both must equal the oracle."""
+    import torch
+    from oracle import oracle
+    from syconn_b200 import device as dev
+    for order in ("F", "C"):
+        for st in ((17, 17, 9), (9, 17, 17), (17, 9, 17), (15, 17, 5)):
+            seg = dev.synth_labels((60, 58, 56), origin=(1, 2, 3), pitch=(16, 16, 8), seed=6, dtype=torch.int32, order=order)
+            got = dev.detect_cs(seg, st).cpu().numpy().view(np.uint64)
+            want = oracle.detect_cs(seg.cpu().numpy().view(np.uint32), st)
+            assert np.array_equal(got, want), (order, st)
