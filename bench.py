@@ -338,6 +338,7 @@ def run_ours(args):
     elif rank == 0:
         line["e2e"] = None
     if rank == 0 and world == 1 and not args.no_stress:
+        line["worker_body"] = worker_body_section(args, plan, chunks)
         line["stress"] = stress_section(local)
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"], _ = cpu_baseline(args.cpu_seconds)
@@ -410,6 +411,58 @@ def parity_block(pipe, chunks, res, rank, world):
     if problems:
         out["problems"] = problems
     return out
+
+
+def worker_body_section(args, plan, chunks):
+    """Second metric: the FULL numeric body of the two workers per chunk, device resident -- contact-site worker
+    (cs_extraction_steps.py:381-486: detect_cs -> props of the un-cropped contacts -> per-id closing + dilation -> crop ->
+    extract_cs_syntype -> syn props) plus the mapping worker with its small-object drop (sd_proc.py:646-684), merged
+    like the primary metric, then the mapping inversion (:1054-1084).  The closing step needs the contact boxes on the
+    host (one round trip per chunk)."""
+    import torch
+    from syconn_b200 import device as dev
+    from syconn_b200._lib import GEOM_DTYPE
+    from syconn_b200.chunked import ExtractionPipeline, cs_halo_geometry
+    n = min(2, len(chunks))
+    ov = max(s // 2 for s in STENCIL)
+    pipe = ExtractionPipeline(N_SUB, STENCIL, chunk_table_capacity=1 << 18, log_capacity=1 << 20, pair_log_capacity=1 << 20,
+                              with_syn=True, cs_dilation=2, min_obj_vx={"cell": 10, "sub0": 10, "sub1": 10, "sub2": 10})
+    geoms = {"cell": np.zeros(len(plan), GEOM_DTYPE), "cs": np.zeros(len(plan), GEOM_DTYPE)}
+    for s in range(len(plan)):
+        geoms["cell"][s] = geoms["cs"][s] = (plan.offsets[s], plan.sizes[s])
+    masks = []
+    for (s, off, cell, subs, halo) in chunks[:n]:
+        _, _, oo, os_ = cs_halo_geometry(off, plan.sizes[s], STENCIL)
+        m = []
+        for kind in (3, 4, 5):   # synaptic junction, asymmetric, symmetric type masks (coordinate hashed, ~6 % / 25 % foreground)
+            lab = dev.synth_labels(os_, oo, ORG_PITCH, 4, 0, kind, 1 if kind == 3 else 4, order="F")
+            m.append((lab != 0).to(torch.uint8))
+            del lab
+        masks.append(m)
+
+    def one():
+        pipe.reset()
+        for (s, off, cell, subs, halo), m in zip(chunks[:n], masks):
+            pipe.process_chunk(s, off, cell, subs, halo, syn_masks=m)
+        owned, owned_pairs = pipe.finish()
+        final, final_pairs = pipe.reduce_on_device(owned, owned_pairs, geoms)
+        return final, pipe.invert_mapping(final_pairs)
+    res = one()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = one()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = float(np.median(ts))
+    vox = sum(int(np.prod(c[2].shape)) for c in chunks[:n])
+    return {"value": vox / (ms * 1e-3) / 1e9, "unit": "GVoxels/s", "chunks": n, "ms_per_chunk": ms / n,
+            "objects": {k: int(v.shape[0]) for k, v in res[0].items()}, "mapping_rows": [int(x[0].shape[0]) for x in res[1]],
+            "what": "detect_cs + props(contacts) + closing/dilation (6 closings, dilation 2) + crop + extract_cs_syntype + syn "
+                    "props + map_subcell_extract_props with min_obj_vx = 10 + merge + mapping inversion; CUDA events, median of 3"}
 
 
 def stress_section(local):

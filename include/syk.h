@@ -111,12 +111,25 @@ int syk_records_bucket(const syk_record_t *records_dev, uint64_t n, uint32_t n_o
 int syk_records_decode_rep(syk_record_t *records_dev, uint64_t n, const syk_chunk_geom_t *geoms_host, uint32_t n_geoms,
                            void *stream);
 
+/* syk_table_append_records with the worker's small-object drop (syconn/proc/sd_proc.py:650-661, :667-680): an object that
+ * lies purely inside the chunk `geom_host` (its box touches none of the six faces) and has fewer than min_vx voxels is not
+ * appended.  min_vx <= 1: identical to syk_table_append_records. */
+int syk_table_append_records_min_vx(syk_table_t *t, const syk_chunk_geom_t *geom_host, syk_record_t *log_dev, uint64_t max_records,
+                                    uint64_t *counter_dev, uint64_t min_vx, void *stream);
+
 int syk_pairs_create(syk_pairs_t **out, uint64_t capacity);
 uint64_t syk_pairs_capacity(const syk_pairs_t *t);
 int syk_pairs_destroy(syk_pairs_t *t);
 int syk_pairs_clear(syk_pairs_t *t, void *stream);
 int syk_pairs_export(syk_pairs_t *t, syk_pair_t *pairs_dev, uint64_t max_pairs, uint64_t *n_out_host, void *stream);
 int syk_pairs_append(syk_pairs_t *t, syk_pair_t *log_dev, uint64_t max_pairs, uint64_t *counter_dev, void *stream);
+/* syk_pairs_append that skips the pairs of organelle objects removed by the small-object drop (sd_proc.py:678-679);
+ * sub_t is the chunk's organelle table (the one syk_table_append_records_min_vx exports) */
+int syk_pairs_append_min_vx(syk_pairs_t *t, syk_table_t *sub_t, const syk_chunk_geom_t *geom_host, uint64_t min_vx,
+                            syk_pair_t *log_dev, uint64_t max_pairs, uint64_t *counter_dev, void *stream);
+/* pairs_dev[i]._pad = total size of organelle pairs_dev[i].sub_id in the owner's final table (0 = not in the table):
+ * the normalisation step of the mapping inversion, sd_proc.py:1054-1084 (ratio = count / organelle size) */
+int syk_pairs_attach_size(syk_pair_t *pairs_dev, uint64_t n, syk_table_t *sub_final, void *stream);
 /* merge_map_dicts (syconn/proc/sd_proc.py:1300-1322): counts summed per (sub_id, cell_id) */
 int syk_pairs_merge(syk_pairs_t *t, const syk_pair_t *pairs_dev, uint64_t n, void *stream);
 /* owner = hash(sub_id) mod n_owners (the reference reduces per organelle object, sd_proc.py:830-853) */

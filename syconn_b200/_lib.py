@@ -36,6 +36,7 @@ EXPORTS = [
     "syk_close_contacts", "syk_close_contacts_host",
     "syk_lz4_compress_bound", "syk_lz4_compress_block", "syk_lz4_decompress_block",
     "syk_label_components", "syk_label_overlap_pairs",
+    "syk_table_append_records_min_vx", "syk_pairs_append_min_vx", "syk_pairs_attach_size",
 ]
 
 
@@ -72,6 +73,9 @@ def load():
     L.syk_table_export.argtypes = [vp, vp, u32, vp, u64, u64p, vp]
     L.syk_table_append_records.argtypes = [vp, vp, vp, u64, vp, vp]
     L.syk_pairs_append.argtypes = [vp, vp, u64, vp, vp]
+    L.syk_table_append_records_min_vx.argtypes = [vp, vp, vp, u64, vp, u64, vp]
+    L.syk_pairs_append_min_vx.argtypes = [vp, vp, vp, u64, vp, u64, vp, vp]
+    L.syk_pairs_attach_size.argtypes = [vp, u64, vp, vp]
     L.syk_table_merge_records.argtypes = [vp, vp, u64, vp]
     L.syk_records_bucket.argtypes = [vp, u64, u32, vp, vp, vp]
     L.syk_records_decode_rep.argtypes = [vp, u64, vp, u32, vp]

@@ -171,7 +171,9 @@ class ExtractionPipeline:
     """Per-rank driver of the three hot-path stages over this rank's chunks (device-resident inputs)."""
 
     def __init__(self, n_sub: int, stencil=(13, 13, 7), chunk_table_capacity=1 << 18, log_capacity=1 << 21,
-                 pair_log_capacity=1 << 21, rank=0, world=1, group=None):
+                 pair_log_capacity=1 << 21, rank=0, world=1, group=None, min_obj_vx=None, with_syn=False, cs_dilation=2):
+        """``min_obj_vx``: {"cell": n, "sub0": n, ...} -- the worker's small-object drop (sd_proc.py:650-661, :667-680): objects
+        that lie purely inside a chunk with fewer voxels are not reported (nor are their overlap pairs)."""
         from . import device as dev
         self.dev = dev
         self.n_sub, self.stencil, self.rank, self.world, self.group = n_sub, tuple(stencil), rank, world, group
@@ -179,7 +181,13 @@ class ExtractionPipeline:
         self.t_cs = dev.IdTable(chunk_table_capacity)
         self.t_sub = [dev.IdTable(chunk_table_capacity) for _ in range(n_sub)]
         self.t_pair = [dev.PairTable(chunk_table_capacity) for _ in range(n_sub)]
-        self.kinds = ["cell", "cs"] + [f"sub{c}" for c in range(n_sub)]
+        self.kinds = ["cell", "cs"] + [f"sub{c}" for c in range(n_sub)] + (["syn"] if with_syn else [])
+        self.min_obj_vx = dict(min_obj_vx or {})
+        # with_syn: process_chunk(..., syn_masks=...) runs the whole numeric body of the contact-site worker
+        # (cs_extraction_steps.py:381-486): closing / dilation of every contact, then extract_cs_syntype on the cropped volumes
+        self.with_syn, self.cs_dilation = with_syn, int(cs_dilation)
+        self.t_syn = dev.IdTable(chunk_table_capacity) if with_syn else None
+        self.syn_voxels = []   # (chunk seq, offset, cropped shape, int64 tensor [n, 4] of syk_synvox_t rows) per chunk
         self.log_capacity, self.pair_log_capacity = log_capacity, pair_log_capacity
         self.logs = {k: torch.empty((log_capacity, 8), dtype=torch.int64, device="cuda") for k in self.kinds}
         self.pair_logs = [torch.empty((pair_log_capacity, 4), dtype=torch.int64, device="cuda") for _ in range(n_sub)]
@@ -193,20 +201,28 @@ class ExtractionPipeline:
     def reset(self):
         self.counters.zero_()
         self.launches = 0
+        self.syn_voxels = []
 
     def _append(self, table, kind_idx, log, origin, shape):
         L = self.dev._lib.load()
         g = np.zeros(1, GEOM_DTYPE)
         g["origin"][0] = origin
         g["shape"][0] = shape
-        self.dev.check(L.syk_table_append_records(table.h, g.ctypes.data, log.data_ptr(), log.shape[0],
-                                                  self.counters[kind_idx:].data_ptr(), self.dev._stream_ptr()))
+        min_vx = int(self.min_obj_vx.get(self.kinds[kind_idx], 0))
+        self.dev.check(L.syk_table_append_records_min_vx(table.h, g.ctypes.data, log.data_ptr(), log.shape[0],
+                                                         self.counters[kind_idx:].data_ptr(), min_vx, self.dev._stream_ptr()))
         self.launches += 2  # k_table_export + k_poison_on_overflow
 
-    def process_chunk(self, seq, offset, cell, subcell, cell_halo):
+    def process_chunk(self, seq, offset, cell, subcell, cell_halo, syn_masks=None):
         """One chunk: ``cell`` [X,Y,Z] and ``subcell`` [C,X,Y,Z] 64-bit labels at ``offset``; ``cell_halo`` the
-        uint32 block of cs_halo_geometry (or None to skip contact sites)."""
+        uint32 block of cs_halo_geometry (or None to skip contact sites).  ``syn_masks`` = (sj, asym, sym) uint8 tensors
+        of the un-cropped contact volume (``size + 2 * overlap`` at ``offset - overlap``, cs_extraction_steps.py:394-434)
+        switches the contact-site stage to the full worker body (needs ``with_syn=True``)."""
         dev, L = self.dev, self.dev._lib.load()
+        if syn_masks is not None:
+            assert self.with_syn and cell_halo is not None
+            self._contact_site_worker(seq, offset, cell_halo, syn_masks)
+            cell_halo = None
         # stage 1: contact sites (cs_extraction_steps.py:391) and the properties the worker merges across chunks:
         # those of the contact volume cropped by `overlap`, at the chunk's own offset (:465-486) -- neighbouring chunks
         # overlap by 2*overlap voxels in the un-cropped volume, which must not be counted twice
@@ -236,9 +252,42 @@ class ExtractionPipeline:
         self._append(self.t_cell, 0, self.logs["cell"], offset, cell.shape)
         for c in range(self.n_sub):
             self._append(self.t_sub[c], 2 + c, self.logs[f"sub{c}"], offset, cell.shape)
-            dev.check(L.syk_pairs_append(self.t_pair[c].h, self.pair_logs[c].data_ptr(), self.pair_logs[c].shape[0],
-                                         self.counters[len(self.kinds) + c:].data_ptr(), dev._stream_ptr()))
+            g = np.zeros(1, GEOM_DTYPE)
+            g["origin"][0], g["shape"][0] = offset, cell.shape
+            dev.check(L.syk_pairs_append_min_vx(self.t_pair[c].h, self.t_sub[c].h, g.ctypes.data,
+                                                int(self.min_obj_vx.get(f"sub{c}", 0)), self.pair_logs[c].data_ptr(),
+                                                self.pair_logs[c].shape[0], self.counters[len(self.kinds) + c:].data_ptr(),
+                                                dev._stream_ptr()))
             self.launches += 2  # k_pairs_export + k_poison_on_overflow
+
+    def _contact_site_worker(self, seq, offset, cell_halo, syn_masks):
+        """detect_cs (:391) -> find_object_properties of the un-cropped contacts for the closing boxes (:439) -> per-id closing
+        + dilation in ascending id order (:440-461) -> extract_cs_syntype on the volumes cropped by ``overlap`` at the
+        chunk's own offset (:465-470).  Logs the cs records and the records of the synaptic parts (``syn``); the synaptic
+        voxel tuples (id, linear index, sym / asym flags) stay on the device in ``self.syn_voxels``."""
+        dev = self.dev
+        overlap = max(s // 2 for s in self.stencil)
+        self.cs_out = dev.detect_cs(cell_halo, self.stencil, out=self._cs_buffer(cell_halo))
+        full_shape = tuple(self.cs_out.shape)
+        self.t_cs.clear()
+        dev.find_object_properties(self.t_cs, self.cs_out)
+        rec = dev.records_numpy(self.t_cs.export(dev.geoms([[0, 0, 0]], [list(full_shape)])))   # host round trip: box list
+        rec = rec[np.argsort(rec["id"])]
+        if len(rec):
+            dev.close_contacts(self.cs_out, rec["id"].copy(), np.stack([rec["bb_min"], rec["bb_max"]], axis=1).astype(np.int32),
+                               overlap, self.cs_dilation)
+        crop = tuple(slice(overlap, n - overlap) for n in full_shape)
+        cs_c = self.cs_out[crop]
+        sj, asym, sym = (m[crop] for m in syn_masks)
+        self.t_cs.clear()
+        vox = dev.extract_cs_syntype(self.t_cs, cs_c, sj, asym, sym, origin=offset, chunk_seq=seq)
+        self._append(self.t_cs, 1, self.logs["cs"], offset, cs_c.shape)
+        syn_seg = torch.where(sj != 0, cs_c, torch.zeros_like(cs_c))                            # :476
+        self.t_syn.clear()
+        dev.find_object_properties(self.t_syn, syn_seg, origin=offset, chunk_seq=seq)
+        self._append(self.t_syn, self.kinds.index("syn"), self.logs["syn"], offset, cs_c.shape)
+        self.syn_voxels.append((seq, tuple(offset), tuple(cs_c.shape), vox))
+        self.launches += 3 + 2 + 4 + 3 + 1   # detect_cs tiers, props + export, morphology, extract_cs_syntype, syn props
 
     def _cs_buffer(self, cell_halo):
         """Contact volume of one chunk, laid out like the input (same fastest axis) with the row pitch padded to a multiple
@@ -327,3 +376,60 @@ class ExtractionPipeline:
             outp.append(t.export(max_pairs=max(p.shape[0], 1)))
             self.launches += 2  # k_pairs_merge + k_pairs_export
         return out, outp
+
+    # ------------------------------------------------------------------------------------------ writers' inputs
+    @staticmethod
+    def voxel_index(owned_records: torch.Tensor):
+        """Per-object voxel index of the writers (sd_proc.py:940-946, :1173-1178: ``bbs = np.concatenate(prop_dict[1][id])``,
+        the object's per-chunk bounding boxes in chunk order) from the owned per-(id, chunk) record log, on the device:
+        returns ``(ids int64 [N], start int64 [N + 1], boxes int32 [M, 2, 3])`` with the boxes of object ``i`` at
+        ``boxes[start[i]:start[i + 1]]``, sorted by chunk sequence number."""
+        if owned_records.shape[0] == 0:
+            z = torch.zeros(0, dtype=torch.int64, device=owned_records.device)
+            return z, torch.zeros(1, dtype=torch.int64, device=owned_records.device), \
+                torch.zeros((0, 2, 3), dtype=torch.int32, device=owned_records.device)
+        rec32 = owned_records.view(torch.int32).view(-1, 16)            # syk_record_t as 16 x int32
+        seq = rec32[:, 15].to(torch.int64) & 0xFFFFFFFF
+        o1 = torch.sort(seq, stable=True).indices                       # chunk order ...
+        o2 = torch.sort(owned_records[o1, 0], stable=True).indices      # ... within every id (ids grouped as int64 bit patterns)
+        order = o1[o2]
+        ids_sorted = owned_records[order, 0]
+        first = torch.ones(ids_sorted.shape[0], dtype=torch.bool, device=ids_sorted.device)
+        first[1:] = ids_sorted[1:] != ids_sorted[:-1]
+        start = torch.nonzero(first).flatten()
+        boxes = rec32[order][:, 6:12].reshape(-1, 2, 3).contiguous()
+        start = torch.cat([start, torch.tensor([ids_sorted.shape[0]], dtype=torch.int64, device=start.device)])
+        return ids_sorted[start[:-1]], start, boxes
+
+    def invert_mapping(self, final_pairs):
+        """The second, smaller exchange of the reduce (sd_proc.py:1054-1084): every final (organelle, cell, count) pair gets
+        the organelle's total size from its owner's final table (``syk_pairs_attach_size``), the pairs are re-bucketed by
+        the owner of the CELL id and exchanged, and organelles that are not part of the organelle dataset (size 0: removed
+        by the size threshold, :1072-1074) are dropped.  Must follow ``reduce_on_device``.  Returns, per organelle channel,
+        ``(cell_id int64 [n], sub_id int64 [n], ratio float64 [n])`` sorted by (cell, organelle) bit patterns -- the
+        ``mapping_{organelle}_ids`` / ``mapping_{organelle}_ratios`` of the cell supervoxels this rank owns."""
+        dev, L = self.dev, self.dev._lib.load()
+        out, bucketed, cnts = [], [], []
+        for c, p in enumerate(final_pairs):
+            p = p.clone() if p.shape[0] else p
+            t = self._final.get(f"sub{c}")
+            assert t is not None, "invert_mapping needs the final organelle tables of reduce_on_device"
+            if p.shape[0]:
+                dev.check(L.syk_pairs_attach_size(p.data_ptr(), p.shape[0], t.h, dev._stream_ptr()))
+            self.launches += 1
+            if self.world > 1:
+                b, cc = dev.bucket_pairs(p[:, [1, 0, 2, 3]].contiguous(), self.world)   # owner key = first column = cell id
+                bucketed.append(b)
+                cnts.append(cc)
+                self.launches += 3
+            else:
+                bucketed.append(p[:, [1, 0, 2, 3]])
+        got = exchange_logs(bucketed, cnts, self.world, self.group) if self.world > 1 else bucketed
+        for p in got:
+            p = p[p[:, 3] != 0]
+            o1 = torch.sort(p[:, 1], stable=True).indices
+            o2 = torch.sort(p[o1, 0], stable=True).indices
+            p = p[o1[o2]]
+            out.append((p[:, 0], p[:, 1], p[:, 2].to(torch.float64) / p[:, 3].to(torch.float64)))
+        return out
+

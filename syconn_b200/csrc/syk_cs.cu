@@ -516,6 +516,7 @@ static int cs_launch_impl(const void *edges, int edge_bytes, const int64_t *edge
         const bool s7 = F.sten[0] == 7 && F.sten[1] == 13 && F.sten[2] == 13 && !getenv("SYK_CS_NOSPEC");
         const bool s13 = F.sten[0] == 13 && F.sten[1] == 13 && F.sten[2] == 7 && !getenv("SYK_CS_NOSPEC");
         if (edges != nullptr) {  // explicit edge mask: run-time-geometry kernels with the EDGES variant of the boundary phase
+            F.tma = 0;
             if (F.vec4) {
                 k1 = k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 0, 0, 0, true>;
                 k2 = k_cs_fast<true, GMAX_T2, NT_T2, MINB2, 0, 0, 0, true>;
@@ -523,6 +524,11 @@ static int cs_launch_impl(const void *edges, int edge_bytes, const int64_t *edge
                 k1 = k_cs_fast<false, GMAX_T1, NT_T1, MINB1, 0, 0, 0, true>;
                 k2 = k_cs_fast<false, GMAX_T2, NT_T2, MINB2, 0, 0, 0, true>;
             }
+        } else if (F.tma) {
+            k1 = s7 ? k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 7, 13, 13, false, true>
+                    : s13 ? k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 13, 13, 7, false, true>
+                          : k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 0, 0, 0, false, true>;
+            k2 = k_cs_fast<true, GMAX_T2, NT_T2, MINB2, 0, 0, 0, false, true>;
         } else if (F.vec4) {
             k1 = s7 ? k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 7, 13, 13>
                     : s13 ? k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 13, 13, 7> : k_cs_fast<true, GMAX_T1, NT_T1, MINB1>;
@@ -569,7 +575,7 @@ static int cs_launch_impl(const void *edges, int edge_bytes, const int64_t *edge
         G.seg_tiles[0] = LU / OU;
         G.seg_tiles[1] = TV / OV;
         G.seg_tiles[2] = TW / OW;
-        k_detect_cs<<<(unsigned)((long long)sms * bps), CS_THREADS, smem, s>>>(arr, nullptr, o, G);
+        k_detect_cs<<<(unsigned)((long long)sms * bps), CS_THREADS, smem, s>>>(arr, edges, o, G);  // listed segments only
         SYK_CUDA(cudaGetLastError());
 #ifdef SYK_NG_HIST
         if (getenv("SYK_CS_DEBUG")) {

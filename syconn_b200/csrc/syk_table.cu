@@ -228,17 +228,39 @@ __device__ __forceinline__ void decode_rep(syk_record_t &r, const syk_chunk_geom
     r.rep[2] = (int32_t)((long long)z + g.origin[2]);
 }
 
+// min_vx > 1: the worker's small-object drop (syconn/proc/sd_proc.py:650-661, :667-680): an object that lies purely inside the
+// chunk (its box touches none of the six chunk faces -- equivalent to "its id is on no face") and has fewer than min_vx
+// voxels is not reported.  `geoms[0]` must then be the chunk of the call.
+__device__ __forceinline__ bool small_inside(const syk_record_t &r, const syk_chunk_geom_t &g, unsigned long long min_vx) {
+    if (r.count >= min_vx) return false;
+    for (int a = 0; a < 3; ++a)
+        if ((long long)r.bb_min[a] <= g.origin[a] || (long long)r.bb_max[a] >= g.origin[a] + g.shape[a]) return false;
+    return true;
+}
+
 __global__ void k_table_export(const SykSlot *slots, uint64_t cap, syk_record_t *out, unsigned long long max_out,
-                               unsigned long long *counter, const syk_chunk_geom_t *geoms, uint32_t n_geoms) {
+                               unsigned long long *counter, const syk_chunk_geom_t *geoms, uint32_t n_geoms,
+                               unsigned long long min_vx = 0ull) {
     uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
     for (uint64_t base = i0 - lane; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t i = base + lane;
         SykSlot s;
+        syk_record_t r;
         bool occ = false;
         if (i < cap) {
             s = slots[i];
             occ = s.key != 0ull;
+        }
+        if (occ) {
+            r.id = s.key;
+            r.count = s.count;
+            r.rep_key = s.rep_enc - 1ull;
+            for (int a = 0; a < 3; ++a) {
+                r.bb_min[a] = (int32_t)((0xFFFFFFFFu - s.min_enc[a]) - SYK_COORD_BIAS);
+                r.bb_max[a] = (int32_t)(s.max_enc[a] - SYK_COORD_BIAS);
+            }
+            if (min_vx > 1ull && geoms != nullptr && small_inside(r, geoms[0], min_vx)) occ = false;
         }
         unsigned m = __ballot_sync(0xffffffffu, occ);
         if (!m) continue;
@@ -248,14 +270,6 @@ __global__ void k_table_export(const SykSlot *slots, uint64_t cap, syk_record_t 
         if (occ) {
             unsigned long long pos = pos0 + __popc(m & ((1u << lane) - 1u));
             if (pos < max_out) {
-                syk_record_t r;
-                r.id = s.key;
-                r.count = s.count;
-                r.rep_key = s.rep_enc - 1ull;
-                for (int a = 0; a < 3; ++a) {
-                    r.bb_min[a] = (int32_t)((0xFFFFFFFFu - s.min_enc[a]) - SYK_COORD_BIAS);
-                    r.bb_max[a] = (int32_t)(s.max_enc[a] - SYK_COORD_BIAS);
-                }
                 decode_rep(r, geoms, n_geoms);
                 out[pos] = r;
             }
@@ -308,8 +322,19 @@ __global__ void k_poison_on_overflow(const int *flags, unsigned long long *count
     if (threadIdx.x == 0 && blockIdx.x == 0 && flags[0]) atomicOr(counter, 1ull << 62);
 }
 
+static int append_records(syk_table_t *t, const syk_chunk_geom_t *geom_host, syk_record_t *log_dev, uint64_t max_records,
+                          uint64_t *counter_dev, uint64_t min_vx, void *stream);
 SYK_API int syk_table_append_records(syk_table_t *t, const syk_chunk_geom_t *geom_host, syk_record_t *log_dev,
                                      uint64_t max_records, uint64_t *counter_dev, void *stream) {
+    return append_records(t, geom_host, log_dev, max_records, counter_dev, 0, stream);
+}
+SYK_API int syk_table_append_records_min_vx(syk_table_t *t, const syk_chunk_geom_t *geom_host, syk_record_t *log_dev,
+                                            uint64_t max_records, uint64_t *counter_dev, uint64_t min_vx, void *stream) {
+    SYK_CHECK_ARG(geom_host != nullptr || min_vx <= 1, "the small-object drop needs the chunk geometry");
+    return append_records(t, geom_host, log_dev, max_records, counter_dev, min_vx, stream);
+}
+static int append_records(syk_table_t *t, const syk_chunk_geom_t *geom_host, syk_record_t *log_dev, uint64_t max_records,
+                          uint64_t *counter_dev, uint64_t min_vx, void *stream) {
     SYK_CHECK_ARG(t != nullptr && log_dev != nullptr && counter_dev != nullptr, "NULL argument");
     cudaStream_t s = (cudaStream_t)stream;
     syk_chunk_geom_t *gd = nullptr;
@@ -318,7 +343,7 @@ SYK_API int syk_table_append_records(syk_table_t *t, const syk_chunk_geom_t *geo
     int blocks = (int)((t->capacity + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_table_export<<<blocks, 256, 0, s>>>(t->slots, t->capacity, log_dev, max_records, (unsigned long long *)counter_dev, gd,
-                                          gd ? 0xFFFFFFFFu : 0u);
+                                          gd ? 0xFFFFFFFFu : 0u, (unsigned long long)min_vx);
     k_poison_on_overflow<<<1, 32, 0, s>>>(t->flags, (unsigned long long *)counter_dev);
     SYK_CUDA(cudaGetLastError());
     if (gd) SYK_CUDA(cudaFreeAsync(gd, s));
@@ -576,8 +601,24 @@ SYK_API int syk_pairs_clear(syk_pairs_t *t, void *stream) {
     return SYK_OK;
 }
 
+// read-only lookup (no insertion)
+__device__ __forceinline__ const SykSlot *table_find(const TableView &t, unsigned long long key) {
+    if (t.slots == nullptr) return nullptr;
+    uint64_t h = syk_mix64(key) & t.mask;
+    for (uint64_t probes = 0; probes <= t.mask; ++probes) {
+        const SykSlot *s = t.slots + h;
+        const unsigned long long cur = s->key;
+        if (cur == key) return s;
+        if (cur == 0ull) return nullptr;
+        h = (h + 1) & t.mask;
+    }
+    return nullptr;
+}
+
+// sub_t / geom / min_vx: drop the pairs of organelle objects that the small-object drop removed (sd_proc.py:678-679)
 __global__ void k_pairs_export(const SykPairSlot *slots, uint64_t cap, syk_pair_t *out, unsigned long long max_out,
-                               unsigned long long *counter) {
+                               unsigned long long *counter, TableView sub_t = TableView{nullptr, 0, nullptr},
+                               const syk_chunk_geom_t *geom = nullptr, unsigned long long min_vx = 0ull) {
     uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
     for (uint64_t base = i0 - lane; base < cap; base += (uint64_t)gridDim.x * blockDim.x) {
@@ -587,6 +628,18 @@ __global__ void k_pairs_export(const SykPairSlot *slots, uint64_t cap, syk_pair_
         if (i < cap) {
             s = slots[i];
             occ = s.sub != 0ull;
+        }
+        if (occ && min_vx > 1ull && geom != nullptr) {
+            const SykSlot *o = table_find(sub_t, s.sub);
+            if (o != nullptr) {
+                syk_record_t r;
+                r.count = o->count;
+                for (int a = 0; a < 3; ++a) {
+                    r.bb_min[a] = (int32_t)((0xFFFFFFFFu - o->min_enc[a]) - SYK_COORD_BIAS);
+                    r.bb_max[a] = (int32_t)(o->max_enc[a] - SYK_COORD_BIAS);
+                }
+                if (small_inside(r, geom[0], min_vx)) occ = false;
+            }
         }
         unsigned m = __ballot_sync(0xffffffffu, occ);
         if (!m) continue;
@@ -639,6 +692,43 @@ SYK_API int syk_pairs_append(syk_pairs_t *t, syk_pair_t *log_dev, uint64_t max_p
     k_pairs_export<<<blocks, 256, 0, (cudaStream_t)stream>>>(t->slots, t->capacity, log_dev, max_pairs,
                                                              (unsigned long long *)counter_dev);
     k_poison_on_overflow<<<1, 32, 0, (cudaStream_t)stream>>>(t->flags, (unsigned long long *)counter_dev);
+    SYK_CUDA(cudaGetLastError());
+    return SYK_OK;
+}
+
+// syk_pairs_append with the worker's small-object drop: pairs whose organelle object (looked up in the chunk's organelle table
+// `sub_t`) lies inside the chunk `geom_host` with fewer than min_vx voxels are skipped (sd_proc.py:667-680)
+SYK_API int syk_pairs_append_min_vx(syk_pairs_t *t, syk_table_t *sub_t, const syk_chunk_geom_t *geom_host, uint64_t min_vx,
+                                    syk_pair_t *log_dev, uint64_t max_pairs, uint64_t *counter_dev, void *stream) {
+    SYK_CHECK_ARG(t != nullptr && log_dev != nullptr && counter_dev != nullptr, "NULL argument");
+    SYK_CHECK_ARG(min_vx <= 1 || (sub_t != nullptr && geom_host != nullptr), "the small-object drop needs the organelle table and the chunk geometry");
+    cudaStream_t s = (cudaStream_t)stream;
+    syk_chunk_geom_t *gd = nullptr;
+    int rc = upload_geoms(geom_host, geom_host ? 1 : 0, s, &gd);
+    if (rc) return rc;
+    int blocks = (int)((t->capacity + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_pairs_export<<<blocks, 256, 0, s>>>(t->slots, t->capacity, log_dev, max_pairs, (unsigned long long *)counter_dev, view_of(sub_t), gd,
+                                          (unsigned long long)min_vx);
+    k_poison_on_overflow<<<1, 32, 0, s>>>(t->flags, (unsigned long long *)counter_dev);
+    SYK_CUDA(cudaGetLastError());
+    if (gd) SYK_CUDA(cudaFreeAsync(gd, s));
+    return SYK_OK;
+}
+
+// Second, smaller exchange of the reduce (sd_proc.py:1054-1084): every overlap pair learns the total size of its organelle
+// object from the owner's final organelle table (written to the pair's `_pad` field; 0 = organelle not in the table, e.g.
+// removed by the size threshold), so that after re-bucketing by cell id the receiver can form count / size ratios.
+__global__ void k_pairs_attach_size(syk_pair_t *pairs, uint64_t n, TableView sub_t) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SykSlot *o = table_find(sub_t, pairs[i].sub_id);
+    pairs[i]._pad = o ? o->count : 0ull;
+}
+SYK_API int syk_pairs_attach_size(syk_pair_t *pairs_dev, uint64_t n, syk_table_t *sub_final, void *stream) {
+    SYK_CHECK_ARG(sub_final != nullptr && (pairs_dev != nullptr || n == 0), "NULL argument");
+    if (n == 0) return SYK_OK;
+    k_pairs_attach_size<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pairs_dev, n, view_of(sub_final));
     SYK_CUDA(cudaGetLastError());
     return SYK_OK;
 }

@@ -343,3 +343,133 @@ def test_dataset_analysis_cache(tmp_path):
     assert back.dtype == object and list(back[0]) == list(m_ids[0])
     for k, i in zip(ids.tolist(), range(len(ids))):
         assert cp[2][k] == int(np.load(tmp_path / "sv_0" / "sizes.npy")[i]) if i < 3 else True
+
+
+@pytest.mark.gpu
+def test_pipeline_contact_site_worker_body_vs_oracle():
+    """ExtractionPipeline(with_syn=True): detect_cs -> closing / dilation -> crop -> extract_cs_syntype per chunk on the device,
+    merged across a 2x2x2 chunk grid == the same composition of the oracle's restatements per chunk
+    (cs_extraction_steps.py:381-486) merged with merge_prop_dicts (:481-486).  The merged sizes do not double-count the
+    overlap between neighbouring chunks."""
+    from helpers import reference_contact_site_chunk
+    from syconn_b200 import device as dev
+    from syconn_b200.chunked import ExtractionPipeline
+    E, st, dil = 40, (7, 7, 3), 2
+    so, ov = [s // 2 for s in st], max(s // 2 for s in st)
+    plan = ChunkPlan((2 * E, 2 * E, 2 * E), (E, E, E))
+    rng = np.random.default_rng(9)
+    G = 2 * E + 2 * ov                                                     # global masks incl. the outer overlap
+    sj_g = ((rng.random((G, G, G)) < 0.4) * rng.integers(1, 3, size=(G, G, G))).astype(np.uint8)
+    asym_g, sym_g = rng.integers(0, 3, size=(G, G, G)).astype(np.uint8), rng.integers(0, 3, size=(G, G, G)).astype(np.uint8)
+    pipe = ExtractionPipeline(0, st, chunk_table_capacity=1 << 14, log_capacity=1 << 15, pair_log_capacity=16, with_syn=True,
+                              cs_dilation=dil)
+    pipe.reset()
+    acc_cs, acc_syn, asym_tot, sym_tot, vox_tot = oracle.new_prop_acc(), oracle.new_prop_acc(), {}, {}, {}
+    empty = torch.empty((0, E, E, E), dtype=torch.int64, device="cuda")
+    for s in range(len(plan)):
+        off, size = plan.offsets[s], plan.sizes[s]
+        lo, ls, oo, os_ = cs_halo_geometry(off, size, st)
+        halo = dev.synth_labels(ls, lo, (13, 11, 7), 3, 2, 0, dtype=torch.int32, order="F")
+        cell = dev.synth_labels(size, off, (13, 11, 7), 3, 2, 0, order="F")
+        msl = tuple(slice(off[i], off[i] + size[i] + 2 * ov) for i in range(3))        # mask block at offset - overlap
+        masks = [torch.from_numpy(np.ascontiguousarray(m[msl])).cuda() for m in (sj_g, asym_g, sym_g)]
+        pipe.process_chunk(s, off, cell, empty, halo, syn_masks=masks)
+        data = halo.cpu().numpy().view(np.uint32)
+        want = reference_contact_site_chunk(oracle, data, sj_g[msl], asym_g[msl], sym_g[msl], np.array(off) - ov, st, dil)
+        # the props are chunk-local; the worker adds offset + overlap when it merges them (cs_extraction_steps.py:481-482)
+        oracle.merge_prop_dicts([acc_cs, [dict(want[0][0]), dict(want[0][1]), dict(want[0][2])]], offset=np.array(off))
+        oracle.merge_prop_dicts([acc_syn, [dict(want[1][0]), dict(want[1][1]), dict(want[1][2])]], offset=np.array(off))
+        for k, n in want[2].items():
+            asym_tot[k] = asym_tot.get(k, 0) + n
+        for k, n in want[3].items():
+            sym_tot[k] = sym_tot.get(k, 0) + n
+        for k, v in want[4].items():
+            vox_tot.setdefault(k, []).extend([tuple(int(c) for c in x) for x in v])
+    owned, _ = pipe.finish()
+    for kind, acc in (("cs", acc_cs), ("syn", acc_syn)):
+        red = reduce_records(dev.records_numpy(owned[kind]))
+        rc, bb, sz = acc
+        assert red["id"].tolist() == sorted(sz) and len(sz) > 20, kind
+        for i, k in enumerate(red["id"].tolist()):
+            assert red["size"][i] == sz[k] and red["rep_coord"][i].tolist() == list(rc[k]), (kind, k)
+            assert np.array_equal(red["bbs"][i], np.array(bb[k])), (kind, k)
+    # synaptic voxel tuples of all chunks: coordinates, sym / asym counts
+    got_vox, got_asym, got_sym = {}, {}, {}
+    for seq, off, shape, vox in pipe.syn_voxels:
+        v = vox.cpu().numpy().view(_lib_synvox()).reshape(-1)
+        lin = v["lin"].astype(np.int64)
+        xyz = np.stack([lin // (shape[1] * shape[2]), lin // shape[2] % shape[1], lin % shape[2]], axis=1) + np.array(off)
+        for k, c, f in zip(v["id"].tolist(), xyz.tolist(), v["flags"].tolist()):
+            got_vox.setdefault(k, []).append(tuple(c))
+            got_asym[k] = got_asym.get(k, 0) + (f & 1)
+            got_sym[k] = got_sym.get(k, 0) + ((f >> 1) & 1)
+    assert {k: sorted(v) for k, v in got_vox.items()} == {k: sorted(v) for k, v in vox_tot.items()}
+    assert {k: n for k, n in got_asym.items() if n} == {k: n for k, n in asym_tot.items() if n}
+    assert {k: n for k, n in got_sym.items() if n} == {k: n for k, n in sym_tot.items() if n}
+
+
+def _lib_synvox():
+    from syconn_b200._lib import SYNVOX_DTYPE
+    return SYNVOX_DTYPE
+
+
+@pytest.mark.gpu
+def test_pipeline_small_object_drop_mapping_inversion_and_voxel_index():
+    """min_obj_vx drop inside the worker (sd_proc.py:650-661, :667-680), the device-side mapping inversion / normalisation
+    (:1054-1084) and the per-object voxel index (:940-946) against the oracle driven like the reference worker."""
+    from syconn_b200 import device as dev
+    from syconn_b200._lib import GEOM_DTYPE
+    from syconn_b200.chunked import ExtractionPipeline
+    E, nsub = 40, 2
+    min_vx = {"cell": 208, "sub0": 36, "sub1": 37}       # cuts into the size distributions (cells ~ 210, organelles ~ 36 voxels)
+    plan = ChunkPlan((2 * E, 2 * E, E), (E, E, E))
+    pipe = ExtractionPipeline(nsub, (3, 3, 3), chunk_table_capacity=1 << 14, log_capacity=1 << 15, pair_log_capacity=1 << 15,
+                              min_obj_vx=min_vx)
+    geoms = {"cell": np.zeros(len(plan), GEOM_DTYPE), "cs": np.zeros(len(plan), GEOM_DTYPE)}
+    pipe.reset()
+    acc = {k: oracle.new_prop_acc() for k in ("cell", "sub0", "sub1")}
+    maps = [{} for _ in range(nsub)]
+    dropped = {k: 0 for k in acc}
+    for s in range(len(plan)):
+        off, size = plan.offsets[s], plan.sizes[s]
+        geoms["cell"][s] = geoms["cs"][s] = (off, size)
+        cell = dev.synth_labels(size, off, (7, 6, 5), 2, 2, 0, order="F")
+        subs = torch.stack([dev.synth_labels(size, off, (4, 3, 3), 2, 2, 1 + c, 4) for c in range(nsub)])
+        pipe.process_chunk(s, off, cell, subs, None)
+        cn, sn = cell.cpu().numpy().view(np.uint64), subs.cpu().numpy().view(np.uint64)
+        cp, sp, md = oracle.map_subcell_extract_props(cn, sn)
+
+        def faces(a):
+            return set(np.unique(np.concatenate([a[0].ravel(), a[-1].ravel(), a[:, 0].ravel(), a[:, -1].ravel(),
+                                                 a[:, :, 0].ravel(), a[:, :, -1].ravel()])).tolist())
+        props = {"cell": [dict(d) for d in cp], "sub0": [dict(sp[k][0]) for k in range(3)], "sub1": [dict(sp[k][1]) for k in range(3)]}
+        for kind, arr in (("cell", cn), ("sub0", sn[0]), ("sub1", sn[1])):
+            rc, bb, sz = props[kind]
+            for ix in set(sz) - faces(arr):
+                if sz[ix] < min_vx[kind]:
+                    del rc[ix], bb[ix], sz[ix]
+                    dropped[kind] += 1
+                    if kind != "cell":
+                        md[int(kind[3])].pop(ix, None)
+            oracle.merge_prop_dicts([acc[kind], props[kind]], offset=np.array(off))
+        for c in range(nsub):
+            oracle.merge_map_dicts([maps[c], {k: dict(v) for k, v in md[c].items()}])
+    assert all(n > 0 for n in dropped.values()), dropped
+    owned, owned_pairs = pipe.finish()
+    final, final_pairs = pipe.reduce_on_device(owned, owned_pairs, geoms)
+    for kind in acc:
+        red = reduce_records(dev.records_numpy(owned[kind]))
+        rc, bb, sz = acc[kind]
+        assert red["id"].tolist() == sorted(sz), kind
+        assert all(red["size"][i] == sz[k] for i, k in enumerate(red["id"].tolist()))
+        # per-object voxel index on the device == the per-chunk boxes of merge_prop_dicts, chunk order
+        ids, start, boxes = (t.cpu().numpy() for t in ExtractionPipeline.voxel_index(owned[kind]))
+        for i, k in enumerate(ids.view(np.uint64).tolist()):
+            assert np.array_equal(boxes[start[i]:start[i + 1]], np.array(bb[k])), (kind, k)
+    inv = pipe.invert_mapping(final_pairs)
+    for c in range(nsub):
+        sizes = acc[f"sub{c}"][2]
+        want = sorted((cid, sid, n / sizes[sid]) for sid, d in maps[c].items() for cid, n in d.items())
+        cid, sid, ratio = (t.cpu().numpy() for t in inv[c])
+        got = sorted(zip(cid.view(np.uint64).tolist(), sid.view(np.uint64).tolist(), ratio.tolist()))
+        assert got == want and len(want) > 50
