@@ -635,7 +635,8 @@ def e2e_host(args, chunks, rank=0, world=1):
     fused_api = "syk_detect_cs_props_host (extension) + syk_map_subcell_extract_props_host"
     serial = measure(False, None)
     serial_fused = measure(True, None)
-    W = max(1, args.e2e_workers)
+    # worker threads per rank: never more threads than cores over all ranks of the box
+    W = max(1, min(args.e2e_workers, (os.cpu_count() or 1) // max(1, world)))
     with ThreadPoolExecutor(max_workers=W) as pool:
         par = measure(False, pool)
         par_fused = measure(True, pool)

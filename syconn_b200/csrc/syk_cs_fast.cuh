@@ -19,8 +19,6 @@
 #pragma once
 #include <cuda.h>
 
-#include <type_traits>
-
 #include "syk_common.cuh"
 
 namespace csfast {
@@ -96,68 +94,74 @@ __host__ __device__ __forceinline__ FastSmem fast_layout(int VP, int WP, int CR,
 }
 inline FastSmem fast_layout(const FastGeom &G, int GMAX) { return fast_layout(G.VP, G.WP, G.CR, G.CF, GMAX); }
 
+constexpr unsigned SL_PENDING = 0xFFFFFFFFu;  // key inserted, slot being allocated
+constexpr unsigned SL_DEAD = 0xFFFFFFFEu;     // id left the su-plane window: its slot was recycled
 template <int GMAX>
 struct HashT {
     static constexpr int KMAX = GMAX * 8;  // <= 64 (slot masks are 64 bit), <= 127 (index + boundary flag in a byte)
     static constexpr unsigned long long ALL_SLOTS = (KMAX >= 64) ? ~0ull : ((1ull << KMAX) - 1ull);
-    unsigned long long ent[HASH];  // id | (slot + 1) << 32: one load gives both; 0 = empty; high word 0 = id known, slot recycled
+    unsigned keys[HASH];
+    unsigned sl[HASH];             // compact slot of the key | SL_PENDING | SL_DEAD
+    int lastp[HASH];               // last plane in which the key was seen
     unsigned ids[KMAX];            // id held by a slot
     int owner[KMAX];               // hash index owning the slot
-    int lastp[KMAX];               // last plane in which the slot was seen
     // ((255 - rank by id) << 8) | slot: tie-break key of the arg-max (smallest id wins).  The 8 entries of a group are
     // stored in the order of the 16-bit count fields {0,4 | 2,6 | 1,5 | 3,7} so that one 16-byte load pairs them up.
     __align__(16) unsigned short tb[KMAX];
     unsigned lut[GMAX][KMAX + 8];  // indicator word of compact index j in group g
     unsigned long long freemask;   // bit s set: slot s is free (lowest free slot is handed out first)
-    unsigned long long seen[2];    // slots met by the relabel of plane p (double buffered by plane parity)
-    unsigned long long used_pub[2];  // slots in use after the recycling of plane p (double buffered)
-    int n_edge[2];
-    int ovf, newflag, ng;
+    int ovf, newflag, n_edge;
 };
 
-// slow path of the relabel: id `lab` != 0 is new, its slot was recycled, or its home entry is taken.  Takes the lowest free
-// slot and publishes {id, slot} with ONE 64-bit CAS, so that a concurrent reader never sees a half-made entry.  Returns the
-// compact index (slot + 1); 0 when no slot / entry is left (H.ovf is raised and the segment is given up).
+// hand out the lowest free compact slot to hash entry h (id lab); raises H.ovf when none is left
 template <typename Hash>
-__device__ __noinline__ unsigned find_slot(Hash &H, unsigned lab) {
-    unsigned i = (lab * 2654435761u) >> (32 - 8);  // HASH == 256
-    for (int probes = 0; probes < 4 * HASH; ++probes) {
-        const unsigned long long e = *(volatile unsigned long long *)&H.ent[i];
-        const bool mine = (unsigned)e == lab;
-        if (mine && (e >> 32)) return (unsigned)(e >> 32);
-        if (mine || e == 0ull) {
-            int s = -1;
-            for (;;) {  // lowest free slot
-                const unsigned long long m = *(volatile unsigned long long *)&H.freemask;
-                if (m == 0ull) break;
-                const unsigned long long bit = m & (0ull - m);
-                if (atomicAnd(&H.freemask, ~bit) & bit) {
-                    s = __ffsll((long long)bit) - 1;
-                    break;
-                }
-            }
-            if (s < 0) break;
-            const unsigned long long want = (unsigned long long)lab | ((unsigned long long)(s + 1) << 32);
-            if (atomicCAS(&H.ent[i], e, want) == e) {
-                H.ids[s] = lab;
-                H.owner[s] = (int)i;
-                H.newflag = 1;
-                return (unsigned)(s + 1);
-            }
-            atomicOr(&H.freemask, 1ull << s);  // somebody else was faster: look at the entry again
-            continue;
+__device__ __forceinline__ void slot_alloc(Hash &H, unsigned h, unsigned lab) {
+    for (;;) {
+        const unsigned long long m = *(volatile unsigned long long *)&H.freemask;
+        if (m == 0ull) {
+            H.ovf = 1;
+            return;
         }
-        i = (i + 1) & (HASH - 1);
+        const unsigned long long bit = m & (0ull - m);
+        if (atomicAnd(&H.freemask, ~bit) & bit) {
+            const int s = __ffsll((long long)bit) - 1;
+            H.ids[s] = lab;
+            H.owner[s] = (int)h;
+            H.sl[h] = (unsigned)s;
+            H.newflag = 1;
+            return;
+        }
     }
-    H.ovf = 1;
-    return 0u;
 }
 
-// compact index of id `lab` (0 for background).  One call site shape for hit, probe and insert: a hash collision must not
-// make a warp run a fast path AND a divergent slow path
+// find the hash index of `lab` (!= 0) at plane p, inserting it (and allocating a compact slot) when it is new or
+// when its slot was recycled; slots become visible to other threads after the next barrier
 template <typename Hash>
-__device__ __forceinline__ unsigned lookup(Hash &H, unsigned lab) {
-    return lab ? find_slot(H, lab) : 0u;
+__device__ __noinline__ int hash_find_insert(Hash &H, unsigned lab, int p) {
+    unsigned h = (lab * 2654435761u) >> (32 - 8);  // HASH == 256
+    for (int probes = 0; probes < HASH; ++probes) {
+        const unsigned cur = H.keys[h];
+        if (cur == lab) {
+            H.lastp[h] = p;
+            if (H.sl[h] == SL_DEAD && atomicCAS(&H.sl[h], SL_DEAD, SL_PENDING) == SL_DEAD) slot_alloc(H, h, lab);
+            return (int)h;
+        }
+        if (cur == 0u) {
+            const unsigned prev = atomicCAS(&H.keys[h], 0u, lab);
+            if (prev == 0u) {
+                H.lastp[h] = p;
+                slot_alloc(H, h, lab);
+                return (int)h;
+            }
+            if (prev == lab) {
+                H.lastp[h] = p;
+                return (int)h;
+            }
+        }
+        h = (h + 1) & (HASH - 1);
+    }
+    H.ovf = 1;  // hash full
+    return 0;
 }
 
 // four consecutive bytes starting at byte column `col` of a row of 8-bit indices (row is 4-byte aligned)
@@ -295,16 +299,16 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             uint4 *p4 = reinterpret_cast<uint4 *>(sm + L.ssum);
             const int n4 = (L.cflag - L.ssum) / 16;
             for (int i = tid; i < n4; i += NT) p4[i] = z;
-            for (int i = tid; i < HASH; i += NT) H.ent[i] = 0ull;
-            if (tid < KMAX) H.lastp[tid] = -(1 << 20);
+            for (int i = tid; i < HASH; i += NT) {
+                H.keys[i] = 0u;
+                H.sl[i] = SL_PENDING;
+                H.lastp[i] = -(1 << 20);
+            }
             if (tid == 0) {
                 H.freemask = ALL_SLOTS;
-                H.seen[0] = H.seen[1] = 0ull;
-                H.used_pub[0] = H.used_pub[1] = 0ull;
-                H.n_edge[0] = H.n_edge[1] = 0;
                 H.ovf = 0;
                 H.newflag = 0;
-                H.ng = 0;
+                H.n_edge = 0;
             }
         }
         // ---- per-thread invariants of the segment (no divisions inside the plane loop) ----
@@ -395,7 +399,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                 reinterpret_cast<uint4 *>(o4)[1] = z;
             } else {
                 const int n = __popc(E);
-                int base = n ? atomicAdd(&H.n_edge[p & 1], n) : 0;
+                int base = n ? atomicAdd(&H.n_edge, n) : 0;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     if (E & (0x80u << (8 * e))) elist[base++] = (unsigned short)(dq * 4 + e);
@@ -435,6 +439,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             const unsigned *rawc = raw + (p & 1) * rawpitch;
             unsigned *rawn = raw + ((p + 1) & 1) * rawpitch;
             uint4 pre[VEC4 ? 1 : MAXQ];
+            int hidx[MAXQ][4];
             if (TMA && tid == 0 && p + 1 < NP) {  // everybody left raw plane p - 1 at the last barrier of the previous step
                 const unsigned b = bar_sa + 8u * (unsigned)((p + 1) & 1);
                 mbar_expect_tx(b, (unsigned)plane * 4u);
@@ -456,90 +461,80 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                     if (q < nquad && p + 1 < NP) load_quad(k, gu + 1, pre[k]);
                 }
             }
-            // single pass: id -> compact index through the {id, slot} entries, straight into the compact plane of the ring
-            {
-                unsigned char *cp = comp + rp * plane;
-                typename std::conditional<(KMAX > 32), unsigned long long, unsigned>::type seen = 0, one = 1;
 #pragma unroll
-                for (int k = 0; k < MAXQ; ++k) {
-                    const int q = tid + k * NT;
-                    if (q < nquad) {
-                        const uint4 a = reinterpret_cast<const uint4 *>(rawc)[q];
-                        const unsigned j0 = lookup(H, a.x);
-                        unsigned w4 = j0 * 0x01010101u;  // uniform quad (the common case)
-                        if (j0) seen |= one << (j0 - 1u);
-                        if (!(a.y == a.x && a.z == a.x && a.w == a.x)) {
-                            const unsigned j1 = a.y == a.x ? j0 : lookup(H, a.y);
-                            const unsigned j2 = a.z == a.x ? j0 : a.z == a.y ? j1 : lookup(H, a.z);
-                            const unsigned j3 = a.w == a.x ? j0 : a.w == a.y ? j1 : a.w == a.z ? j2 : lookup(H, a.w);
-                            w4 = j0 | (j1 << 8) | (j2 << 16) | (j3 << 24);
-                            if (j1) seen |= one << (j1 - 1u);
-                            if (j2) seen |= one << (j2 - 1u);
-                            if (j3) seen |= one << (j3 - 1u);
-                        }
-                        reinterpret_cast<unsigned *>(cp)[q] = w4;
-                        if (!VEC4) reinterpret_cast<uint4 *>(rawn)[q] = pre[VEC4 ? 0 : k];  // nobody reads raw plane p - 1 any more
+            for (int k = 0; k < MAXQ; ++k) {
+                const int q = tid + k * NT;
+                hidx[k][0] = hidx[k][1] = hidx[k][2] = hidx[k][3] = -1;
+                if (q < nquad) {
+                    const uint4 a = reinterpret_cast<const uint4 *>(rawc)[q];
+                    int h0 = -1, h1 = -1, h2 = -1, h3 = -1;
+                    if (a.x != 0u) h0 = hash_find_insert(H, a.x, p);
+                    if (a.y == a.x) h1 = h0;
+                    if (a.z == a.x) h2 = h0;
+                    if (a.w == a.x) h3 = h0;
+                    // the other distinct labels of the quad (rare: a boundary crosses it) share one call site
+                    unsigned need = 0u;
+                    if (a.y != 0u && a.y != a.x) need |= 2u;
+                    if (a.z != 0u && a.z != a.x && a.z != a.y) need |= 4u;
+                    if (a.w != 0u && a.w != a.x && a.w != a.y && a.w != a.z) need |= 8u;
+                    while (need) {
+                        const unsigned lab = (need & 2u) ? a.y : (need & 4u) ? a.z : a.w;
+                        const int h = hash_find_insert(H, lab, p);
+                        if (a.y == lab) h1 = h;
+                        if (a.z == lab) h2 = h;
+                        if (a.w == lab) h3 = h;
+                        need &= need - 1u;
                     }
+                    hidx[k][0] = h0;
+                    hidx[k][1] = h1;
+                    hidx[k][2] = h2;
+                    hidx[k][3] = h3;
                 }
-                unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)seen), hi = 0u;
-                if (KMAX > 32) hi = __reduce_or_sync(0xffffffffu, (unsigned)((unsigned long long)seen >> 32));
-                if ((tid & 31) == 0 && (lo | hi)) atomicOr(&H.seen[p & 1], ((unsigned long long)hi << 32) | lo);
             }
             __syncthreads();
-            // B. the compact plane is complete
+            // B. slots are published: compact-index plane; next raw plane
             if (H.ovf) { aborted = true; break; }
-            // groups the v-sums must cover: every slot in use before this step's recycling (the leaving plane may hold ids that
-            // are recycled right now) or handed out by this step's relabel
-            const unsigned long long used_c2 = (~(*(volatile unsigned long long *)&H.freemask) & ALL_SLOTS) | H.used_pub[(p + 1) & 1];
-            const int NG = used_c2 ? ((64 - __clzll((long long)used_c2) + 7) >> 3) : 0;
-            if (tid == 0) {
-                H.n_edge[(p + 1) & 1] = 0;  // everybody is past the previous plane's boundary-voxel loop
-                H.seen[(p + 1) & 1] = 0ull;
+            if (tid == 0) H.n_edge = 0;  // everybody is past the previous plane's boundary-voxel loop
+            const unsigned long long used = ~H.freemask & ALL_SLOTS;  // stable until phase C
+            if (H.newflag && tid < KMAX && ((used >> tid) & 1ull)) {  // ranks by id (arg-max tie-break: smallest id wins)
+                const unsigned me = H.ids[tid];
+                int r = 0;
+                for (unsigned long long m = used; m; m &= m - 1ull) r += H.ids[__ffsll((long long)m) - 1] < me;
+                const int n = tid & 7;
+                H.tb[(tid & ~7) | ((n & 1) << 2) | (n & 2) | (n >> 2)] = (unsigned short)(((255 - r) << 8) | tid);
             }
-            if (tid < 32) {
-                // one warp (lane handles slots lane and lane + 32): last-seen planes, recycling of the slots whose id left the
-                // su-plane window (after this step their sum fields are zero again), ranks by id for the arg-max tie-break
-                const unsigned long long seen = H.seen[p & 1];
-                unsigned long long used = ~H.freemask & ALL_SLOTS, mine_free = 0ull;
-#pragma unroll
-                for (int h = 0; h < (KMAX > 32 ? 2 : 1); ++h) {
-                    const int sl = tid + 32 * h;
-                    if (sl < KMAX && ((used >> sl) & 1ull)) {
-                        if ((seen >> sl) & 1ull) H.lastp[sl] = p;
-                        else if (H.lastp[sl] + su <= p) {
-                            mine_free |= 1ull << sl;
-                            H.ent[H.owner[sl]] = (unsigned long long)H.ids[sl];  // id known, no slot
-                        }
-                    }
-                }
-                const unsigned flo = __reduce_or_sync(0xffffffffu, (unsigned)mine_free);
-                const unsigned fhi = KMAX > 32 ? __reduce_or_sync(0xffffffffu, (unsigned)(mine_free >> 32)) : 0u;
-                const unsigned long long freed = ((unsigned long long)fhi << 32) | flo;
-                used &= ~freed;
-                if (tid == 0) {
-                    if (freed) atomicOr(&H.freemask, freed);
-                    H.ng = used ? ((64 - __clzll((long long)used) + 7) >> 3) : 0;
-                    H.used_pub[p & 1] = used;
-                }
-                if (H.newflag) {
-#pragma unroll
-                    for (int h = 0; h < (KMAX > 32 ? 2 : 1); ++h) {
-                        const int sl = tid + 32 * h;
-                        if (sl < KMAX && ((used >> sl) & 1ull)) {
-                            const unsigned me = H.ids[sl];
-                            int r = 0;
-                            for (unsigned long long m = used; m; m &= m - 1ull) r += H.ids[__ffsll((long long)m) - 1] < me;
-                            const int n = sl & 7;
-                            H.tb[(sl & ~7) | ((n & 1) << 2) | (n & 2) | (n >> 2)] = (unsigned short)(((255 - r) << 8) | sl);
-                        }
-                    }
-                }
-                __syncwarp();
-                if (tid == 0) H.newflag = 0;
-            }
+            const int NG = used ? ((64 - __clzll((long long)used) + 7) >> 3) : 0;
 #ifdef SYK_NG_HIST
-            if (tid == 0) atomicAdd(&g_ids_hist[__popcll(used_c2)], 1ull);  // development: live ids per plane
+            if (tid == 0) atomicAdd(&g_ids_hist[__popcll(used)], 1ull);  // development: live ids per plane
 #endif
+            unsigned char *cp = comp + rp * plane;
+#pragma unroll
+            for (int k = 0; k < MAXQ; ++k) {
+                const int q = tid + k * NT;
+                if (q < nquad) {
+                    const int h0 = hidx[k][0], h1 = hidx[k][1], h2 = hidx[k][2], h3 = hidx[k][3];
+                    const unsigned j0 = h0 < 0 ? 0u : H.sl[h0] + 1u;
+                    unsigned w4 = j0 * 0x01010101u;  // uniform quad (the common case)
+                    if (!(h1 == h0 && h2 == h0 && h3 == h0)) {
+                        const unsigned j1 = h1 < 0 ? 0u : H.sl[h1] + 1u;
+                        const unsigned j2 = h2 < 0 ? 0u : H.sl[h2] + 1u;
+                        const unsigned j3 = h3 < 0 ? 0u : H.sl[h3] + 1u;
+                        w4 = j0 | (j1 << 8) | (j2 << 16) | (j3 << 24);
+                    }
+                    reinterpret_cast<unsigned *>(cp)[q] = w4;
+                    if (!VEC4) reinterpret_cast<uint4 *>(rawn)[q] = pre[VEC4 ? 0 : k];
+                }
+            }
+            __syncthreads();
+            if (tid == 0) H.newflag = 0;
+            // recycle the slots of ids that left the su-plane window (after this step their sum fields are zero again)
+            if (tid < KMAX && ((used >> tid) & 1ull)) {
+                const int h = H.owner[tid];
+                if (H.lastp[h] + su <= p) {
+                    H.sl[h] = SL_DEAD;
+                    atomicOr(&H.freemask, 1ull << tid);
+                }
+            }
             // C1. boundary flags of plane p-1 (needs planes p-2, p-1, p), four voxels per thread
             if (tid < NOQ && p >= 2 && p - 1 >= ou && p - 1 <= LU - 1 + ou) {
                 const int pc = p - 1;
@@ -613,8 +608,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             if (uo >= 0 && u0 + uo < G.on[0]) {
                 const unsigned char *cf = cflag + (rf + 1 == CF ? 0 : rf + 1) * (TV * TW);
                 unsigned long long *orow = out + (u0 + uo) * G.ost[0];
-                const int ne = H.n_edge[p & 1];
-                const int NGD = H.ng;  // groups that can hold a non-zero sum after this step's recycling
+                const int ne = H.n_edge;
 #ifdef SYK_D_FORWARD
                 for (int e = tid; e < ne; e += NT) {
 #else
@@ -625,7 +619,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                     const int jc = cf[i] & 0x7F;
                     const int gc = (jc - 1) >> 3, nc = (jc - 1) & 7;
                     unsigned best = 0u;
-                    for (int g = 0; g < NGD; ++g) {
+                    for (int g = 0; g < NG; ++g) {
                         const uint2 *sp = ssum + g * oplane + b * WP + c;
                         unsigned c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
                         int r = 0;

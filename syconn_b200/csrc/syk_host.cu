@@ -80,7 +80,7 @@ static cudaError_t dev_alloc(DevBuf &b, size_t bytes, cudaStream_t s) {
 #define SYK_D2H(dst, src, bytes, s)                                            \
     do {                                                                       \
         SYK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)); \
-        SYK_CUDA(cudaStreamSynchronize(s));                                    \
+        SYK_CUDA(syk_stream_wait(s));                                    \
     } while (0)
 
 // a dense block viewed through `strides`: nbytes = elem_bytes * prod(shape); base offset must be 0
@@ -595,7 +595,7 @@ SYK_API int syk_find_object_properties_cs_64bit_host(const uint64_t *cs_host, co
         return SYK_ENOMEM;
     }
     cudaError_t e = cudaMemcpyAsync(idh, ids.p, n_ids * sizeof(uint64_t), cudaMemcpyDeviceToHost, hs);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(hs);
+    if (e == cudaSuccess) e = syk_stream_wait(hs);
     if (e != cudaSuccess) {
         syk_set_error("copy of the id list failed: %s", cudaGetErrorString(e));
         free(idh);

@@ -95,6 +95,19 @@ bool syk_make_tmap3(CUtensorMap *m, const void *base, int elem_bytes, const long
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+cudaError_t syk_stream_wait(cudaStream_t s) {
+    static thread_local cudaEvent_t ev[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return cudaStreamSynchronize(s);
+    if (!ev[dev] && cudaEventCreateWithFlags(&ev[dev], cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        return cudaStreamSynchronize(s);
+    }
+    cudaError_t e = cudaEventRecord(ev[dev], s);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ev[dev]);
+}
+
 cudaStream_t syk_host_stream() {
     static thread_local cudaStream_t streams[16] = {};
     int dev = 0;
