@@ -484,10 +484,10 @@ static int cs_launch_impl(const void *edges, int edge_bytes, const int64_t *edge
             for (int a = 0; a < 3; ++a) F.est[a] = G.est[a];
         }
         // tier 1 (<= 24 ids near the plane, many CTAs/SM) -> tier 2 (<= 64 ids) on the listed segments -> generic kernel
-        unsigned *hard = nullptr;  // [count1, count2, list1[nsegs], list2[nsegs]]
-        SYK_CUDA(cudaMallocAsync((void **)&hard, sizeof(unsigned) * (size_t)(2 * F.nsegs + 2), s));
-        SYK_CUDA(cudaMemsetAsync(hard, 0, 2 * sizeof(unsigned), s));
-        unsigned *cnt1 = hard, *cnt2 = hard + 1, *list1 = hard + 2, *list2 = hard + 2 + F.nsegs;
+        unsigned *hard = nullptr;  // [count1, count2, queue1, queue2 | list1[nsegs], list2[nsegs]]; counts and queue heads per tier
+        SYK_CUDA(cudaMallocAsync((void **)&hard, sizeof(unsigned) * (size_t)(2 * F.nsegs + 8), s));
+        SYK_CUDA(cudaMemsetAsync(hard, 0, 8 * sizeof(unsigned), s));
+        unsigned *cnt1 = hard, *cnt2 = hard + 4, *list1 = hard + 8, *list2 = hard + 8 + F.nsegs;
         // rows of uint32 that are 16-byte aligned everywhere => LDG.128 quads
         F.vec4 = (elem_bytes == 4 && F.ist[2] == 1 && (F.ist[0] % 4) == 0 && (F.ist[1] % 4) == 0 && ((uintptr_t)arr % 16) == 0) ? 1 : 0;
         F.out_vec = (F.ost[2] == 1 && (F.ost[0] % 2) == 0 && (F.ost[1] % 2) == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
@@ -589,9 +589,10 @@ static int cs_launch_impl(const void *edges, int edge_bytes, const int64_t *edge
         }
 #endif
         if (getenv("SYK_CS_DEBUG")) {
-            unsigned nh[2] = {0, 0};
-            cudaMemcpyAsync(nh, hard, sizeof(nh), cudaMemcpyDeviceToHost, s);
+            unsigned nh8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            cudaMemcpyAsync(nh8, hard, sizeof(nh8), cudaMemcpyDeviceToHost, s);
             cudaStreamSynchronize(s);
+            const unsigned nh[2] = {nh8[0], nh8[4]};
             fprintf(stderr, "[syk] detect_cs fast path: %lld segments, %u redone by tier 2, %u by the generic kernel; smem %d / %d B, "
                             "CTAs/SM %d / %d, vec4=%d out_vec=%d tma=%d\n", F.nsegs, nh[0], nh[1], L1.total, L2.total, ctas1, ctas2, F.vec4,
                     F.out_vec, F.tma);

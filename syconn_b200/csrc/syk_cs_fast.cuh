@@ -211,20 +211,34 @@ __device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *tm,
         : "memory");
 }
 
+// indicator word of compact index j in the group whose first slot is gsh / 4 - 1 ... : 1 << 4 * (j - 1 - 8 g) when j lies in
+// group g, else 0.  gsh = 4 + 32 g.  PTX shl clamps shift amounts >= 32 (result 0), and 4 j - gsh wraps to a huge amount
+// for j below the group (background included), so no table and no branch are needed.
+#ifndef SYK_VSUM_LUT
+__device__ __forceinline__ unsigned ind_word(unsigned j, unsigned gsh) {
+    unsigned r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(1u), "r"(4u * j - gsh));
+    return r;
+}
+#define SYK_IND(j) ind_word((unsigned)(j), gsh)
+#else
+#define SYK_IND(j) lut[(j)]
+#endif
+
 // sliding v-sum (window sv) of the indicator words of one column of a compact plane: acc[q], q = 0..7
-__device__ __forceinline__ void vsum8(const unsigned char *col, int WP, int sv, const unsigned *lut, unsigned (&acc)[8]) {
+__device__ __forceinline__ void vsum8(const unsigned char *col, int WP, int sv, const unsigned *lut, unsigned gsh, unsigned (&acc)[8]) {
     unsigned head[8];
     unsigned a = 0u;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        head[r] = lut[col[r * WP]];
+        head[r] = SYK_IND(col[r * WP]);
         if (r < sv) a += head[r];
     }
-    for (int r = 8; r < sv; ++r) a += lut[col[r * WP]];
+    for (int r = 8; r < sv; ++r) a += SYK_IND(col[r * WP]);
     acc[0] = a;
 #pragma unroll
     for (int q = 1; q < 8; ++q) {
-        a += lut[col[(q + sv - 1) * WP]] - head[q - 1];
+        a += SYK_IND(col[(q + sv - 1) * WP]) - head[q - 1];
         acc[q] = a;
     }
 }
@@ -283,8 +297,13 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
         H.lut[g][j] = (j != 0 && (s >> 3) == g) ? (1u << ((s & 7) * 4)) : 0u;
     }
 
+    // Segments are handed out dynamically after the first wave (hard_count[2] / [3] are the queue heads of tier 1 / tier 2):
+    // ~7 segments per CTA of unequal length (the last u segment is short, volume edges clip tiles) leave a static round
+    // robin with a long tail.
     const long long nwork = seg_list ? (long long)(*seg_count) : G.nsegs;
-    for (long long wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    unsigned *queue = hard_count + (seg_list ? 3 : 2);
+    __shared__ unsigned s_next;
+    for (long long wi = blockIdx.x; wi < nwork;) {
         const long long seg = seg_list ? (long long)seg_list[wi] : wi;
         const long long tw = seg % G.segs[2];
         const long long r0 = seg / G.segs[2];
@@ -293,6 +312,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
         const long long u0 = tu * LU, v0 = tv * TV, w0 = tw * TW;  // output origin == input origin of the haloed block
         const int NP = (int)min((long long)(LU + su - 1), G.n[0] - u0);  // input planes of the segment (the last one is short)
         __syncthreads();
+        if (tid == 0) s_next = gridDim.x + atomicAdd(queue, 1u);  // read after the barrier that ends the segment init
         // ---- segment init: zero running sums / hash ----
         {
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -578,8 +598,9 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
                     const int g = itg[k];
                     const unsigned *lut = H.lut[g];
                     unsigned an[8], ao[8];
-                    vsum8(cn + itoff[k], WP, sv, lut, an);
-                    if (has_old) vsum8(co + itoff[k], WP, sv, lut, ao);
+                    const unsigned gsh = 4u + 32u * (unsigned)g;
+                    vsum8(cn + itoff[k], WP, sv, lut, gsh, an);
+                    if (has_old) vsum8(co + itoff[k], WP, sv, lut, gsh, ao);
                     uint2 *sp = ssum + g * oplane + itoff[k];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
@@ -676,6 +697,7 @@ k_cs_fast(const void *__restrict__ arr, unsigned long long *__restrict__ out, Fa
             } else if (VEC4) cp_async_wait_all();
             if (tid == 0) hard_list[atomicAdd(hard_count, 1u)] = (unsigned)seg;
         }
+        wi = s_next;  // written before the segment's first barrier; the next write comes after the next segment's top barrier
     }
 }
 

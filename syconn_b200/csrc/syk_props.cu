@@ -355,6 +355,13 @@ struct MapArgs {
     int do_sub_props;
     int org_mode;  // organelle-first scan: the staged channel is ONE organelle volume (its props go to cell_t), sub[0] is the
                    // cell volume, read on demand only where the organelle is non-zero (organelles are sparse)
+    // organelle-first scan of SEVERAL channels in one launch: tiles [c * ntiles, (c + 1) * ntiles) belong to channel c, whose
+    // volume is org[c] (tensor map m[c]), props table org_t[c] and pair table pair_t[c]; one dynamic tile queue for all
+    int n_org;
+    const void *org[MAX_SUB];
+    TableView org_t[MAX_SUB];
+    unsigned long long *tile_ctr;  // device counter (zeroed per launch) for dynamic tile hand-out after the first wave; tiles differ
+                                   // a lot in cost (empty / organelle content), a static round robin leaves a long tail
 };
 
 // One kernel for both entry points: NCH = 1 + n_sub staged channels (n_sub == 0 => find_object_properties).
@@ -366,7 +373,7 @@ struct MapArgs {
 #define SYK_ORG_MINB 5
 #endif
 template <typename T, int R, int TU, int TV, int WARPS, int WS, int WSS, int PS, int NBUF, bool TMA, int MODE>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MODE == 2 ? SYK_ORG_MINB : 3)) k_scan(const T *__restrict__ cell, ScanGeom G, TableView cell_t, MapArgs A,
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MODE == 2 ? SYK_ORG_MINB : 3)) k_scan(const T *__restrict__ cell0, ScanGeom G, TableView cell_t, MapArgs A,
                                                      const __grid_constant__ TmapSet tm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long mbar[WARPS][2];
@@ -409,13 +416,16 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
     constexpr int NB = TU * (TV / R);  // batches per tile
     const long long nwarps = (long long)gridDim.x * WARPS;
     const long long my_first = (long long)blockIdx.x * WARPS + wib;
-    if (my_first >= G.ntiles) return;
+    const long long total_tiles = org_mode ? (long long)A.n_org * G.ntiles : G.ntiles;
+    if (my_first >= total_tiles) return;
 
     // issue the async loads of batch b of the tile at tile coordinates (tu, tv, tw) into stage buffer `sb`
-    struct TileId { long long tu, tv, tw; };
+    struct TileId { long long tu, tv, tw, local; int ch; };
     auto tile_id = [&](long long tile) {
         TileId t;
-        const unsigned t32 = (unsigned)tile, n2 = (unsigned)G.tiles[2], n1 = (unsigned)G.tiles[1];
+        t.ch = org_mode ? (int)(tile / G.ntiles) : 0;
+        t.local = tile - (long long)t.ch * G.ntiles;
+        const unsigned t32 = (unsigned)t.local, n2 = (unsigned)G.tiles[2], n1 = (unsigned)G.tiles[1];
         const unsigned rr = t32 / n2;
         t.tw = t32 - rr * n2;
         t.tu = rr / n1;
@@ -428,7 +438,9 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
                 const int c0 = (int)(t.tw * TW), c1 = (int)(t.tv * TV + (b % (TV / R)) * R), c2 = (int)(t.tu * TU + b / (TV / R));
                 mbar_expect_tx(bar_addr[sb], (unsigned)(nstage * R * 32 * sizeof(T)));
                 const unsigned dst0 = (unsigned)__cvta_generic_to_shared(stage + (size_t)sb * buf_elems);
-                for (int c = 0; c < nstage; ++c) tma_load_3d(dst0 + c * R * 32 * (unsigned)sizeof(T), &tm.m[c], c0, c1, c2, bar_addr[sb]);
+                if (org_mode) tma_load_3d(dst0, &tm.m[t.ch], c0, c1, c2, bar_addr[sb]);
+                else
+                    for (int c = 0; c < nstage; ++c) tma_load_3d(dst0 + c * R * 32 * (unsigned)sizeof(T), &tm.m[c], c0, c1, c2, bar_addr[sb]);
             }
             return;
         }
@@ -437,6 +449,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
         const long long v0 = t.tv * TV + (b % (TV / R)) * R;
         const bool ok = (w < G.n[2]) && (u < G.n[0]);
         T *dst = stage + (size_t)sb * buf_elems + lane;
+        const T *cell = org_mode ? reinterpret_cast<const T *>(A.org[t.ch]) : cell0;
         const T *src = ok ? cell + w * G.st[2] + u * G.st[0] + v0 * G.st[1] : cell;
 #pragma unroll
         for (int j = 0; j < R; ++j) {
@@ -459,11 +472,19 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
     int sb = 0;
     TileId cur = tile_id(my_first), nxt = cur;
     issue(cur, 0, 0);
-    for (long long tile = my_first; tile < G.ntiles; tile += nwarps) {
+    long long tile_next = my_first;
+    for (long long tile = my_first; tile < total_tiles; tile = tile_next) {
         TileCtx Tc;
-        tile_setup(G, tile, TU, TV, Tc);
-        const bool has_next = tile + nwarps < G.ntiles;
-        if (has_next) nxt = tile_id(tile + nwarps);
+        tile_setup(G, cur.local, TU, TV, Tc);
+        if (A.tile_ctr != nullptr) {  // first wave: one tile per warp; then whoever is free takes the next one
+            unsigned long long t = 0ull;
+            if (lane == 0) t = atomicAdd(A.tile_ctr, 1ull);
+            tile_next = nwarps + (long long)__shfl_sync(FULL, t, 0);
+        } else {
+            tile_next = tile + nwarps;
+        }
+        const bool has_next = tile_next < total_tiles;
+        if (has_next) nxt = tile_id(tile_next);
         for (int b = 0; b < NB; ++b) {
             const bool more = (b + 1 < NB) || has_next;
             // NBUF == 2: prefetch the next batch (possibly of the next tile) before consuming this one
@@ -513,11 +534,11 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
                     }
                     cp_async_commit();
                 }
-                if (A.do_cell_props) acc_batch<T, R, WS>(cb, bnd, nzs, *ctab, cell_t, G, Tc, lu, lv0, lane);
+                if (A.do_cell_props) acc_batch<T, R, WS>(cb, bnd, nzs, *ctab, A.org_t[cur.ch], G, Tc, lu, lv0, lane);
                 if (any) {
                     cp_async_wait<0>();
                     __syncwarp();
-                    acc_pairs<T, R, PS>(cb, cbuf, ptab[0], A.pair_t[0], lane);
+                    acc_pairs<T, R, PS>(cb, cbuf, ptab[0], A.pair_t[cur.ch], lane);
                 }
             } else if (A.do_cell_props) {
                 const unsigned bnd = run_starts<T, R>(cb, lane, nzs);
@@ -543,10 +564,10 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS == 8 && R == 16) ? 4 : (MOD
                 sb ^= 1;
             }
         }
-        if (A.do_cell_props) wtab_flush<WS>(*ctab, cell_t, G, Tc, lane);
+        if (A.do_cell_props) wtab_flush<WS>(*ctab, org_mode ? A.org_t[cur.ch] : cell_t, G, Tc, lane);
         for (int c = 0; c < n_sub; ++c) {
             if (A.do_sub_props) wtab_flush<WSS>(stab[c], A.sub_t[c], G, Tc, lane);
-            ptab_flush<PS>(ptab[c], A.pair_t[c], lane);  // per tile: a full private table would degrade every probe
+            ptab_flush<PS>(ptab[c], A.pair_t[org_mode ? cur.ch : c], lane);  // per tile: a full private table would degrade every probe
         }
         cur = nxt;
     }
@@ -653,11 +674,20 @@ static int launch_cfg(const void *cell, const ScanGeom &G, const TableView &cell
     int bps = 1;
     SYK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, WARPS * 32, smem));
     if (bps < 1) bps = 1;
-    long long want = (G.ntiles + WARPS - 1) / WARPS;
+    const long long all_tiles = (MODE != 0 && A.org_mode) ? G.ntiles * (A.n_org > 0 ? A.n_org : 1) : G.ntiles;
+    long long want = (all_tiles + WARPS - 1) / WARPS;
     long long grid = (long long)sms * bps;
     if (grid > want) grid = want < 1 ? 1 : want;
-    kern<<<(unsigned)grid, WARPS * 32, smem, s>>>((const T *)cell, G, cell_t, A, tm);
+    MapArgs A2 = A;
+    unsigned long long *ctr = nullptr;
+    if (!getenv("SYK_SCAN_STATIC")) {
+        SYK_CUDA(cudaMallocAsync((void **)&ctr, sizeof(unsigned long long), s));
+        SYK_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), s));
+    }
+    A2.tile_ctr = ctr;
+    kern<<<(unsigned)grid, WARPS * 32, smem, s>>>((const T *)cell, G, cell_t, A2, tm);
     SYK_CUDA(cudaGetLastError());
+    if (ctr) SYK_CUDA(cudaFreeAsync(ctr, s));
     return SYK_OK;
 }
 
@@ -667,6 +697,7 @@ static int launch_scan(const void *cell, const ScanGeom &G, const TableView &cel
     memset(&tm, 0, sizeof(tm));
     bool tma = make_tmap(&tm.m[0], cell, (int)sizeof(T), G.n, G.st, R);
     for (int c = 0; c < A.n_sub && tma && !A.org_mode; ++c) tma = make_tmap(&tm.m[1 + c], A.sub[c], (int)sizeof(T), G.n, G.sst, R);
+    for (int c = 1; c < A.n_org && tma && A.org_mode; ++c) tma = make_tmap(&tm.m[c], A.org[c], (int)sizeof(T), G.n, G.st, R);
     // TMA: one buffer per warp, many resident warps hide the latency; LDGSTS fallback: double buffered
     // (measured: one buffer + 32 resident warps/SM beats double buffering with 16-20 warps, and R=16 beats R=8)
 #ifndef SYK_TMA_NBUF
@@ -684,8 +715,12 @@ static int launch_scan(const void *cell, const ScanGeom &G, const TableView &cel
 
 // props: R=16 rows per batch, tiles of 4 x 32 rows x 32 lanes; map: R=8, tiles of 8 x 16 rows (more channels staged)
 #define PROPS_R 16
+#ifndef PROPS_TU
 #define PROPS_TU 4
+#endif
+#ifndef PROPS_TV
 #define PROPS_TV 32
+#endif
 #define PROPS_WARPS 8
 #define PROPS_CFG PROPS_R, PROPS_TU, PROPS_TV, PROPS_WARPS, 64, 32, 32
 #define MAP_CFG 8, 8, 16, 4, 64, 32, 32
@@ -694,7 +729,7 @@ static int launch_scan(const void *cell, const ScanGeom &G, const TableView &cel
 #define ORG_R 16
 #endif
 #ifndef ORG_TU
-#define ORG_TU 8
+#define ORG_TU 4  // with the dynamic tile queue smaller tiles balance better: 1.23 -> 1.15 ms for three 512^3 channels
 #endif
 #ifndef ORG_TV
 #define ORG_TV 32
@@ -749,25 +784,31 @@ SYK_API int syk_map_subcell_extract_props(syk_table_t *cell_t, syk_table_t *cons
     }
     if (!getenv("SYK_MAP_FUSED")) {
         // Organelle-first decomposition (organelles are sparse): the cell props are one dense scan; every organelle channel
-        // is streamed on its own, and the cell volume is touched again only where that organelle is non-zero.
+        // is streamed on its own (all of them by one launch), and the cell volume is touched again only where that organelle
+        // is non-zero.
         if (cell_t) {
             rc = syk_find_object_properties(cell_t, cell_dev, elem_bytes, shape, cell_strides, origin, chunk_seq, stream);
             if (rc) return rc;
         }
-        for (int c = 0; c < n_sub; ++c) {
+        if (n_sub > 0) {  // all organelle channels in ONE launch: a shared dynamic tile queue, one ramp-up and one tail
             ScanGeom G;
             plan_axes(shape, sub_strides, origin, chunk_seq, ORG_TU, ORG_TV, G);
             for (int a = 0; a < 3; ++a) G.sst[a] = cell_strides[G.la[a]];
+            SYK_CHECK_ARG(G.ntiles * n_sub < (1ll << 31), "too many tiles per call");
             MapArgs A;
             memset(&A, 0, sizeof(A));
             A.n_sub = 1;
             A.org_mode = 1;
-            A.do_cell_props = sub_t != nullptr;  // props of the staged (organelle) channel
+            A.do_cell_props = sub_t != nullptr;  // props of the staged (organelle) channels
             A.sub[0] = cell_dev;
-            A.pair_t[0] = view_of(pair_t[c]);
-            const TableView tv = view_of(sub_t ? sub_t[c] : nullptr);
-            rc = elem_bytes == 8 ? launch_scan<unsigned long long, 2, ORG_CFG>(subcell_dev[c], G, tv, A, (cudaStream_t)stream)
-                                 : launch_scan<unsigned int, 2, ORG_CFG>(subcell_dev[c], G, tv, A, (cudaStream_t)stream);
+            A.n_org = n_sub;
+            for (int c = 0; c < n_sub; ++c) {
+                A.org[c] = subcell_dev[c];
+                A.org_t[c] = view_of(sub_t ? sub_t[c] : nullptr);
+                A.pair_t[c] = view_of(pair_t[c]);
+            }
+            rc = elem_bytes == 8 ? launch_scan<unsigned long long, 2, ORG_CFG>(subcell_dev[0], G, A.org_t[0], A, (cudaStream_t)stream)
+                                 : launch_scan<unsigned int, 2, ORG_CFG>(subcell_dev[0], G, A.org_t[0], A, (cudaStream_t)stream);
             if (rc) return rc;
         }
         return SYK_OK;
