@@ -492,7 +492,10 @@ static int cs_launch_impl(const void *edges, int edge_bytes, const int64_t *edge
         F.vec4 = (elem_bytes == 4 && F.ist[2] == 1 && (F.ist[0] % 4) == 0 && (F.ist[1] % 4) == 0 && ((uintptr_t)arr % 16) == 0) ? 1 : 0;
         F.out_vec = (F.ost[2] == 1 && (F.ost[0] % 2) == 0 && (F.ost[1] % 2) == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
         const FastSmem L1 = fast_layout(F, GMAX_T1), L2 = fast_layout(F, GMAX_T2);
-        constexpr int MINB1 = SYK_MINB1, MINB2 = 2;
+#ifndef SYK_MINB2
+#define SYK_MINB2 2
+#endif
+        constexpr int MINB1 = SYK_MINB1, MINB2 = SYK_MINB2;
         int ctas1 = (int)((227 * 1024) / (L1.total + (int)sizeof(HashT<GMAX_T1>) + 1280));
         if (ctas1 > MINB1) ctas1 = MINB1;
         if (ctas1 < 1) ctas1 = 1;

@@ -1,5 +1,5 @@
-"""Host-side mirrors of the dict-level merge helpers of ``syconn.proc.sd_proc`` that the extraction workers call around the
-hot path (same names, argument meaning and in-place behaviour), plus converters between the reference's dict structures and
+"""COMPATIBILITY GLUE, not the compute path: host-side mirrors of the dict-level merge helpers of ``syconn.proc.sd_proc`` that
+the extraction workers call around the hot path (same names, argument meaning and in-place behaviour), plus converters between the reference's dict structures and
 the array/record form of the device pipeline (``syconn_b200.chunked``).
 
 These functions only re-arrange per-chunk RESULTS in Python, exactly where the reference does it in Python; all voxel work
