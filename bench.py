@@ -113,10 +113,29 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": (time.perf_counter() - t0) * 1e3 / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "timing": "wall clock of a bounded sample on host cores"},
+            "config": dict(base_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
+                           timing="wall clock of a bounded sample of 64^3 blocks of this workload on the host cores"),
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "GVoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def grid_of(total):
+    """chunk grid of `total` chunks: (.., 2, 2)-ish, z fastest; 8 GPUs x 8 chunks = 4 x 4 x 4 chunks of 512^3 = 2048^3"""
+    g = [1, 1, 1]
+    a = 2
+    while g[0] * g[1] * g[2] < total:
+        g[a] *= 2
+        a = (a - 1) % 3
+    return g
+
+
+def base_config(args, world):
+    """the keys both arms (ours and --impl reference) report identically"""
+    g = grid_of(world * args.chunks_per_gpu)
+    return {"workload": workload_name(args), "chunks_per_gpu": args.chunks_per_gpu, "chunk": args.chunk,
+            "volume": [g[0] * args.chunk, g[1] * args.chunk, g[2] * args.chunk], "cell_pitch": list(CELL_PITCH),
+            "layout": "x fastest (ZYX memory)"}
 
 
 def workload_name(args):
@@ -208,12 +227,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     E, cpg = args.chunk, args.chunks_per_gpu
     # global volume: world*cpg chunks laid out as an (nx, 2, 2)-ish grid; 8 GPUs x 8 chunks = 4x4x4 of 512^3 = 2048^3
-    total = world * cpg
-    g = [1, 1, 1]
-    a = 2
-    while g[0] * g[1] * g[2] < total:
-        g[a] *= 2
-        a = (a - 1) % 3
+    g = grid_of(world * cpg)
     plan = ChunkPlan((g[0] * E, g[1] * E, g[2] * E), (E, E, E))
     mine = plan.chunks_of_rank(rank, world)[:cpg]
     geoms = {"cell": np.zeros(len(plan), GEOM_DTYPE), "cs": np.zeros(len(plan), GEOM_DTYPE)}
@@ -322,10 +336,9 @@ def run_ours(args):
     line = {"metric": "GVoxels/s contact-site+property extraction", "value": value, "unit": "GVoxels/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "chunks_per_gpu": cpg, "chunk": E,
-                       "volume": list(plan.volume_shape), "cell_pitch": list(CELL_PITCH), "layout": "x fastest (ZYX memory)",
-                       "l2": f"inputs per step {in_bytes / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
-                       "objects": {k: int(v.shape[0]) for k, v in res[0].items()}},
+            "config": dict(base_config(args, world),
+                           l2=f"inputs per step {in_bytes / 1e9:.1f} GB per GPU >> 126 MB L2, no flush needed",
+                           objects={k: int(v.shape[0]) for k, v in res[0].items()}),
             "clocks": clk.summary(), "roofline": roofline, "gpu_launches": int(launches)}
 
     # ---- parity of the step's result (untimed): the merged tables against independent voxel counts of the inputs,

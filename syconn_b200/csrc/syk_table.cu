@@ -3,6 +3,7 @@
 //   merge_prop_dicts  syconn/proc/sd_proc.py:1248-1273     -> syk_table_merge_records
 //   merge_map_dicts   syconn/proc/sd_proc.py:1300-1322     -> syk_pairs_merge
 //   id -> reducer hash  syconn/reps/rep_helper.py:143-163  -> syk_records_bucket / syk_pairs_bucket
+#include <sched.h>
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -96,16 +97,13 @@ bool syk_make_tmap3(CUtensorMap *m, const void *base, int elem_bytes, const long
 }
 
 cudaError_t syk_stream_wait(cudaStream_t s) {
-    static thread_local cudaEvent_t ev[16] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return cudaStreamSynchronize(s);
-    if (!ev[dev] && cudaEventCreateWithFlags(&ev[dev], cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
-        cudaGetLastError();
-        return cudaStreamSynchronize(s);
-    }
-    cudaError_t e = cudaEventRecord(ev[dev], s);
-    if (e != cudaSuccess) return e;
-    return cudaEventSynchronize(ev[dev]);
+    // poll + yield: as prompt as a spinning cudaStreamSynchronize when the thread has a core to itself, but a waiter gives
+    // its core to the next runnable thread when there are more waiters than cores (SYK_SPIN_WAIT=1: plain synchronize)
+    static const bool spin = getenv("SYK_SPIN_WAIT") != nullptr;
+    if (spin) return cudaStreamSynchronize(s);
+    cudaError_t e;
+    while ((e = cudaStreamQuery(s)) == cudaErrorNotReady) sched_yield();
+    return e;
 }
 
 cudaStream_t syk_host_stream() {
