@@ -244,3 +244,20 @@ def write_segmentation_objects(sd_path, red, mapping=None, min_obj_vx=1, n_folde
         voxel_dc.push()
         written.append(folder)
     return written
+
+
+def reduced_from_device(final_records, voxel_index):
+    """Bridge from the device pipeline to the writers: ``final_records`` is the structured array of one kind returned by
+    ``ExtractionPipeline.reduce_on_device`` (``device.records_numpy``), ``voxel_index`` the ``(ids, start, boxes)`` triple of
+    ``ExtractionPipeline.voxel_index`` (device tensors or arrays).  Returns the dict ``write_segmentation_objects`` /
+    ``write_dataset_analysis_cache`` take (``id, size, bounding_box, rep_coord, bbs``), sorted by id."""
+    ids, start, boxes = (np.asarray(t.cpu().numpy() if hasattr(t, "cpu") else t) for t in voxel_index)
+    ids = ids.view(np.uint64)
+    o = np.argsort(final_records["id"])
+    rec = final_records[o]
+    v = np.argsort(ids)
+    assert np.array_equal(ids[v], rec["id"]), "voxel index and final records describe different id sets"
+    bbs = [boxes[start[i]:start[i + 1]].astype(np.int64) for i in v.tolist()]
+    return dict(id=rec["id"].copy(), size=rec["count"].astype(np.int64),
+                bounding_box=np.stack([rec["bb_min"], rec["bb_max"]], axis=1).astype(np.int32),
+                rep_coord=rec["rep"].astype(np.int32), bbs=bbs)

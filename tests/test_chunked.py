@@ -473,3 +473,45 @@ def test_pipeline_small_object_drop_mapping_inversion_and_voxel_index():
         cid, sid, ratio = (t.cpu().numpy() for t in inv[c])
         got = sorted(zip(cid.view(np.uint64).tolist(), sid.view(np.uint64).tolist(), ratio.tolist()))
         assert got == want and len(want) > 50
+
+
+@pytest.mark.gpu
+def test_device_pipeline_to_storage_files(tmp_path):
+    """device pipeline -> reduce_on_device + voxel_index -> write_segmentation_objects -> files read back like the reference
+    reads them (oracle/storage_ref.py) == the oracle worker's merged dicts (sd_proc.py:788-1000)."""
+    from oracle import storage_ref
+    from syconn_b200 import device as dev
+    from syconn_b200._lib import GEOM_DTYPE
+    from syconn_b200.chunked import ExtractionPipeline
+    from syconn_b200.proc import sd_proc
+    E = 32
+    plan = ChunkPlan((2 * E, 2 * E, E), (E, E, E))
+    pipe = ExtractionPipeline(1, (3, 3, 3), chunk_table_capacity=1 << 14, log_capacity=1 << 15, pair_log_capacity=1 << 15)
+    geoms = {"cell": np.zeros(len(plan), GEOM_DTYPE), "cs": np.zeros(len(plan), GEOM_DTYPE)}
+    pipe.reset()
+    acc, maps = oracle.new_prop_acc(), {}
+    for s in range(len(plan)):
+        off, size = plan.offsets[s], plan.sizes[s]
+        geoms["cell"][s] = geoms["cs"][s] = (off, size)
+        cell = dev.synth_labels(size, off, (9, 8, 7), 2, 5, 0, order="F")
+        subs = torch.stack([dev.synth_labels(size, off, (5, 4, 4), 2, 5, 1, 5)]) * 1009      # spread over storage folders
+        pipe.process_chunk(s, off, cell, subs, None)
+        cp, sp, md = oracle.map_subcell_extract_props(cell.cpu().numpy().view(np.uint64), subs.cpu().numpy().view(np.uint64))
+        oracle.merge_prop_dicts([acc, [sp[0][0], sp[1][0], sp[2][0]]], offset=np.array(off))
+        oracle.merge_map_dicts([maps, {k: dict(v) for k, v in md[0].items()}])
+    owned, owned_pairs = pipe.finish()
+    final, final_pairs = pipe.reduce_on_device(owned, owned_pairs, geoms)
+    red = sd_proc.reduced_from_device(dev.records_numpy(final["sub0"]), ExtractionPipeline.voxel_index(owned["sub0"]))
+    mapping = sd_proc.reduced_to_map_dict(reduce_pairs(dev.pairs_numpy(final_pairs[0])))
+    folders = sd_proc.write_segmentation_objects(str(tmp_path / "mi_0"), red, mapping=mapping, min_obj_vx=1, n_folders_fs=100)
+    rc, bb, sz = acc
+    seen = set()
+    for folder in folders:
+        attr = storage_ref.read_attr_dict(os.path.join(folder, "attr_dict.pkl"))
+        bbs, sizes, reps, _ = storage_ref.read_voxel_dyn(os.path.join(folder, "voxel.pkl"))
+        for k, a in attr.items():
+            assert a["size"] == sz[k] == sizes[k] and a["rep_coord"].tolist() == list(rc[k]) == reps[k].tolist()
+            assert np.array_equal(bbs[k], np.array(bb[k]))
+            assert dict(zip(a["mapping_ids"], a["mapping_ratios"])) == {c: n / sz[k] for c, n in maps.get(k, {}).items()}
+            seen.add(k)
+    assert seen == set(sz) and len(seen) > 50
