@@ -1,192 +1,181 @@
-"""Storage classes of row f3 with the reference's names and file formats (syconn/backend/storage.py:26-93, :208-421 and
-syconn/backend/base.py FSBase): pickled dictionaries (``pickle.HIGHEST_PROTOCOL``, written to ``<path>.tmp`` and moved,
-handler/basics.py:485-508) whose array values are lists of lz4 block strings.
+"""Storage classes of row f3: the reference's names, constructor arguments and ON-DISK FORMAT
+(syconn/backend/storage.py:26-93, :208-421 on top of syconn/backend/base.py FSBase), written in this repo's own way.
 
-Only what the extraction writers (syconn/proc/sd_proc.py:788-1215) and an unmodified ``SegmentationDataset`` /
-``SegmentationObject`` need: ``AttributeDict``, ``CompressedStorage`` and ``VoxelStorageDyn`` with ``voxel_mode=False``
-(bounding boxes, sizes, representative coordinates).  ``voxel_mode=True`` reads voxels back through a KnossosDataset
-(knossos_utils, third party, not in this image) and raises.  File locking (fasteners) is not implemented:
-``disable_locking`` must stay True, which is what every writer of the hot path passes.
+On disk every storage is ONE pickled ``dict`` (``pickle.HIGHEST_PROTOCOL``, written to ``<path>.tmp`` and renamed,
+handler/basics.py:485-508):
+
+  * ``AttributeDict``       ``{object id: {attribute name: value}}``
+  * ``CompressedStorage``   ``{key: {"arr": [lz4 strings], "sh": shape with -1 as first entry, "dt": dtype.str}}``
+  * ``VoxelStorageDyn``     a CompressedStorage of per-object box lists ``[N, 2, 3]`` plus the helper entries ``'meta'``
+                            (``{'voxeldata_path': ...}``), ``'size'`` (defaultdict(int)), ``'rep_coord'``, ``'voxel_cache'``
+
+Only what the extraction writers (syconn/proc/sd_proc.py:788-1215) and a reader of their files need is provided:
+``voxel_mode=True`` of ``VoxelStorageDyn`` fetches voxels through a KnossosDataset (knossos_utils, not in this image) and
+raises; file locking (fasteners) is not implemented, so ``disable_locking`` must stay True -- what every writer of the hot
+path passes anyway.
 """
 import os
 import pickle
-import shutil
 from collections import defaultdict
-from typing import Any, Optional, Union
+from typing import Optional
 
 import numpy as np
 
-from ..handler.compression import arrtolz4string_list, lz4string_listtoarr
-
-
-def write_obj2pkl(path: str, obj):
-    """handler/basics.py:485-508"""
-    with open(path + ".tmp", "wb") as f:
-        pickle.dump(obj, f, protocol=pickle.HIGHEST_PROTOCOL)
-    shutil.move(path + ".tmp", path)
-
-
-def load_pkl2obj(path: str):
-    with open(path, "rb") as f:
-        return pickle.load(f)
+from ..handler import compression as _codec
 
 
 class StorageClass:
-    """File-backed dictionary (backend/base.py FSBase): ``pull`` on construction when the file exists, ``push`` to write."""
+    """One pickled dictionary per file: read on construction when the file exists, written by ``push``."""
 
     def __init__(self, inp_p: Optional[str], cache_decomp: bool = False, read_only: bool = True,
-                 disable_locking: bool = True, **kwargs):
+                 disable_locking: bool = True, **_ignored):
         if not disable_locking:
             raise NotImplementedError("file locking (fasteners) is not available: pass disable_locking=True")
-        self.read_only = read_only
-        self._cache_decomp = cache_decomp
-        self._cache_dc = {}
-        self._dc_intern = {}
-        self._path = inp_p
+        if inp_p is not None and not isinstance(inp_p, str):
+            raise NotImplementedError(f"Unsupported initialization type {type(inp_p)} for 'FSBase'.")
+        self.read_only, self._cache_decomp = read_only, cache_decomp
+        self._path, self._cache_dc, self._dc_intern = inp_p, {}, {}
         if inp_p is not None:
-            if type(inp_p) is not str:
-                raise NotImplementedError(f"Unsupported initialization type {type(inp_p)} for 'FSBase'.")
-            self.pull(inp_p)
+            self.pull()
 
-    def __len__(self):
-        return len(self._dc_intern)
+    # -- file I/O
+    def pull(self, source: Optional[str] = None):
+        src = source or self._path
+        folder = os.path.dirname(src)
+        if folder and not self.read_only:
+            os.makedirs(folder, exist_ok=True)
+        self._dc_intern = {}
+        if os.path.isfile(src):
+            with open(src, "rb") as fh:
+                self._dc_intern = pickle.load(fh)
 
-    def __contains__(self, item):
-        return item in self._dc_intern
+    def push(self, dest: Optional[str] = None):
+        dst = dest or self._path
+        if dst is None:          # virtual storage: nothing to write
+            return
+        tmp = dst + ".tmp"
+        with open(tmp, "wb") as fh:
+            pickle.dump(self._dc_intern, fh, protocol=pickle.HIGHEST_PROTOCOL)
+        os.replace(tmp, dst)
+
+    # -- read-only mapping protocol over the raw dictionary; subclasses define item access
+    def keys(self):
+        return self._dc_intern.keys()
+
+    def values(self):
+        return (self[k] for k in list(self._dc_intern))
+
+    def items(self):
+        return ((k, self[k]) for k in list(self._dc_intern))
 
     def __iter__(self):
         return iter(self._dc_intern)
 
+    def __len__(self):
+        return len(self._dc_intern)
+
+    def __contains__(self, key):
+        return key in self._dc_intern
+
     def __eq__(self, other):
-        return isinstance(other, StorageClass) and self._dc_intern == other._dc_intern
+        return isinstance(other, StorageClass) and other._dc_intern == self._dc_intern
 
     def __repr__(self):
-        return repr(self._dc_intern)
-
-    def keys(self):
-        return self._dc_intern.keys()
-
-    def items(self):
-        for k in self._dc_intern.keys():
-            yield k, self[k]
-
-    def values(self):
-        for k in self._dc_intern.keys():
-            yield self[k]
-
-    def push(self, dest: Optional[str] = None):
-        dest = self._path if dest is None else dest
-        if dest is None:
-            return
-        write_obj2pkl(dest, self._dc_intern)
-
-    def pull(self, source: Optional[str] = None):
-        source = self._path if source is None else source
-        fold = os.path.split(source)[0]
-        if fold and not os.path.isdir(fold) and not self.read_only:
-            os.makedirs(fold, exist_ok=True)
-        if os.path.isfile(source):
-            self._dc_intern = load_pkl2obj(source)
-        else:
-            self._dc_intern = {}
+        return f"{type(self).__name__}({self._path!r}, {len(self._dc_intern)} entries)"
 
 
 class AttributeDict(StorageClass):
-    """storage.py:26-50: object id -> attribute dictionary."""
+    """object id -> attribute dictionary; reading an unknown id creates its (empty) entry, like the reference."""
 
-    def __getitem__(self, item):
-        try:
-            return self._dc_intern[item]
-        except KeyError:
-            self._dc_intern[item] = {}
-            return self._dc_intern[item]
+    def __getitem__(self, obj_id):
+        return self._dc_intern.setdefault(obj_id, {})
 
-    def __setitem__(self, key, value):
-        self._dc_intern[key] = value
+    def __setitem__(self, obj_id, attrs):
+        self._dc_intern[obj_id] = attrs
 
-    def update(self, other, **kwargs):
-        self._dc_intern.update(other, **kwargs)
+    def update(self, other, **kw):
+        self._dc_intern.update(other, **kw)
 
     def copy_intern(self):
         return dict(self._dc_intern)
 
 
 class CompressedStorage(StorageClass):
-    """storage.py:52-93: key -> ``{"arr": [lz4 strings], "sh": shape with -1 first, "dt": dtype.str}``."""
+    """key -> NumPy array, kept as lz4 strings."""
 
-    def __getitem__(self, item: Union[int, str]):
-        try:
-            return self._cache_dc[item]
-        except KeyError:
-            pass
-        value_intern = self._dc_intern[item]
-        decomp_arr = lz4string_listtoarr(value_intern["arr"], dtype=np.dtype(value_intern["dt"]), shape=value_intern["sh"])
+    @staticmethod
+    def _pack(arr: np.ndarray) -> dict:
+        return {"arr": _codec.arrtolz4string_list(arr), "sh": (-1,) + tuple(arr.shape[1:]), "dt": arr.dtype.str}
+
+    @staticmethod
+    def _unpack(entry: dict) -> np.ndarray:
+        return _codec.lz4string_listtoarr(entry["arr"], dtype=np.dtype(entry["dt"]), shape=entry["sh"])
+
+    def __getitem__(self, key):
+        if key in self._cache_dc:
+            return self._cache_dc[key]
+        arr = self._unpack(self._dc_intern[key])
         if self._cache_decomp:
-            self._cache_dc[item] = decomp_arr
-        return decomp_arr
+            self._cache_dc[key] = arr
+        return arr
 
-    def __setitem__(self, key: Union[int, str], value: np.ndarray):
+    def __setitem__(self, key, value):
         if type(value) is not np.ndarray:
             raise ValueError("CompressedStorage supports np.array values only.")
+        self._dc_intern[key] = self._pack(value)
         if self._cache_decomp:
             self._cache_dc[key] = value
-        sh = list(value.shape)
-        sh[0] = -1
-        self._dc_intern[key] = {"arr": arrtolz4string_list(value), "sh": tuple(sh), "dt": value.dtype.str}
 
     def __delitem__(self, key):
-        del self._dc_intern[key]
-        if key in self._cache_dc:
-            del self._cache_dc[key]
+        self._dc_intern.pop(key)
+        self._cache_dc.pop(key, None)
 
 
 class VoxelStorageDyn(CompressedStorage):
-    """storage.py:208-421 with ``voxel_mode=False``: object id -> all bounding boxes ``[N, 2, 3]`` that define the object
-    (one per chunk it touches), plus the helper entries ``'meta'`` (path of the voxel data), ``'size'``, ``'rep_coord'`` and
-    ``'voxel_cache'`` inside the same pickled dictionary."""
+    """Per object: all bounding boxes ``[N, 2, 3]`` that hold its voxels (one per chunk it touches) + size + representative
+    coordinate.  Opened with ``voxel_mode=False`` by the writers."""
+
+    _HELPERS = (("size", lambda: defaultdict(int)), ("rep_coord", dict), ("voxel_cache", dict))
 
     def __init__(self, inp: str, voxel_mode: bool = True, voxeldata_path: Optional[str] = None, **kwargs):
-        if not inp.endswith(".pkl"):
-            inp = inp + ".pkl"
-        super().__init__(inp, **kwargs)
+        super().__init__(inp if inp.endswith(".pkl") else inp + ".pkl", **kwargs)
         self.voxel_mode = voxel_mode
-        if "meta" not in self._dc_intern:
-            self._dc_intern["meta"] = dict(voxeldata_path=voxeldata_path)
-        if "size" not in self._dc_intern:
-            self._dc_intern["size"] = defaultdict(int)
-        if "rep_coord" not in self._dc_intern:
-            self._dc_intern["rep_coord"] = dict()
-        if "voxel_cache" not in self._dc_intern:
-            self._dc_intern["voxel_cache"] = dict()
-        if voxeldata_path is not None and self._dc_intern["meta"]["voxeldata_path"] != voxeldata_path:
-            self._dc_intern["meta"]["voxeldata_path"] = voxeldata_path
+        meta = self._dc_intern.setdefault("meta", {"voxeldata_path": voxeldata_path})
+        if voxeldata_path is not None:
+            meta["voxeldata_path"] = voxeldata_path
+        for name, make in self._HELPERS:
+            if name not in self._dc_intern:
+                self._dc_intern[name] = make()
         if voxel_mode:
             raise NotImplementedError("voxel_mode=True reads voxels through knossos_utils.KnossosDataset, which is not "
                                       "available here; use voxel_mode=False (bounding boxes, sizes, rep coords)")
 
-    def __setitem__(self, key: int, value: Any):
+    def _known(self, obj_id):
+        if obj_id not in self._dc_intern:
+            raise KeyError('KeyError: Could not find key "{}" in `self._dc_intern`.`'.format(obj_id))
+
+    def __setitem__(self, obj_id, boxes):
         if self.voxel_mode:
             raise RuntimeError("`VoxelStorageDyn.__setitem__` may only be used when `voxel_mode=False`.")
-        return super().__setitem__(key, value)
+        super().__setitem__(obj_id, boxes)
 
-    def object_size(self, item):
-        if item not in self._dc_intern:
-            raise KeyError('KeyError: Could not find key "{}" in `self._dc_intern`.`'.format(item))
-        return self._dc_intern["size"][item]
+    def get_boundingdata(self, obj_id):
+        return CompressedStorage.__getitem__(self, obj_id)
 
-    def increase_object_size(self, item, value):
-        self._dc_intern["size"][item] += value
+    def object_size(self, obj_id):
+        self._known(obj_id)
+        return self._dc_intern["size"][obj_id]
 
-    def object_repcoord(self, item):
-        if item not in self._dc_intern:
-            raise KeyError('KeyError: Could not find key "{}" in `self._dc_intern`.`'.format(item))
-        return self._dc_intern["rep_coord"][item]
+    def increase_object_size(self, obj_id, n_voxels):
+        self._dc_intern["size"][obj_id] += n_voxels
 
-    def set_object_repcoord(self, item, value):
-        self._dc_intern["rep_coord"][item] = value
+    def object_repcoord(self, obj_id):
+        self._known(obj_id)
+        return self._dc_intern["rep_coord"][obj_id]
 
-    def get_boundingdata(self, item: int):
-        return super().__getitem__(item)
+    def set_object_repcoord(self, obj_id, coord):
+        self._dc_intern["rep_coord"][obj_id] = coord
 
     def keys(self):
-        return [k for k in self._dc_intern.keys() if (type(k) is str and k.isdigit()) or (type(k) is not str)]
+        """object ids only (the helper entries have non-numeric string keys)"""
+        return [k for k in self._dc_intern if not isinstance(k, str) or k.isdigit()]

@@ -51,43 +51,45 @@ def decompress(data) -> bytes:
     return dst.raw[:n]
 
 
+def _as_array(arr):
+    return np.array(arr) if isinstance(arr, list) else arr
+
+
 def arrtolz4string(arr: np.ndarray) -> bytes:
-    """compression.py:39-57"""
-    if isinstance(arr, list):
-        arr = np.array(arr)
-    if len(arr) == 0:
-        return b""
-    return compress(arr.tobytes())
+    """array -> one lz4 string (``b""`` for an empty array); compression.py:39-57"""
+    arr = _as_array(arr)
+    return compress(arr.tobytes()) if len(arr) else b""
 
 
 def lz4stringtoarr(string: bytes, dtype=np.float32, shape: Optional[Tuple[int]] = None) -> np.ndarray:
-    """compression.py:60-81"""
-    if len(string) == 0:
+    """one lz4 string -> array of ``dtype`` (reshaped when ``shape`` is given); compression.py:60-81"""
+    if not string:
         return np.zeros((0,), dtype=dtype)
-    arr_1d = np.frombuffer(decompress(string), dtype=dtype)
-    if shape is not None:
-        arr_1d = arr_1d.reshape(shape)
-    return arr_1d
+    flat = np.frombuffer(decompress(string), dtype=dtype)
+    return flat if shape is None else flat.reshape(shape)
 
 
 def arrtolz4string_list(arr: np.ndarray) -> List[bytes]:
-    """compression.py:83-103: one string per array; arrays too large for one block are halved recursively."""
-    if isinstance(arr, list):
-        arr = np.array(arr)
+    """array -> list of lz4 strings: normally one; an array that is too large for a single LZ4 block is cut in halves along
+    its first axis until every piece fits (compression.py:83-103 does the same by recursion)."""
+    arr = _as_array(arr)
     if len(arr) == 0:
         return [b""]
-    try:
-        return [compress(arr.tobytes())]
-    except (OverflowError, ValueError, LZ4BlockError):
-        half_ix = len(arr) // 2
-        return arrtolz4string_list(arr[:half_ix]) + arrtolz4string_list(arr[half_ix:])
+    out, todo = [], [arr]
+    while todo:
+        piece = todo.pop()
+        if piece.nbytes <= LZ4_MAX_INPUT_SIZE or len(piece) < 2:
+            out.append(compress(piece.tobytes()) if len(piece) else b"")
+        else:
+            mid = len(piece) // 2
+            todo += [piece[mid:], piece[:mid]]      # stack: the first half is compressed first
+    return out
 
 
 def lz4string_listtoarr(str_lst: Union[List[bytes], np.ndarray], dtype=np.float32,
                         shape: Optional[Tuple[int]] = None) -> np.ndarray:
-    """compression.py:106-127"""
-    if type(str_lst) is np.ndarray:
+    """list of lz4 strings -> one array (an array passes through unchanged); compression.py:106-127"""
+    if isinstance(str_lst, np.ndarray):
         return str_lst
-    if len(str_lst) == 0:
-        return np.zeros((0,), dtype=dtype)
-    return np.concatenate([lz4stringtoarr(s, dtype=dtype, shape=shape) for s in str_lst])
+    pieces = [lz4stringtoarr(s, dtype=dtype, shape=shape) for s in str_lst]
+    return np.concatenate(pieces) if pieces else np.zeros((0,), dtype=dtype)
