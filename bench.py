@@ -250,7 +250,7 @@ def run_ours(args):
     in_bytes = sum(c[2].numel() * 8 + c[3].numel() * 8 + c[4].numel() * 4 for c in chunks)
 
     pipe = ExtractionPipeline(N_SUB, STENCIL, chunk_table_capacity=1 << 18, log_capacity=max(1 << 20, cpg << 17),
-                              pair_log_capacity=max(1 << 20, cpg << 17), rank=rank, world=world)
+                              pair_log_capacity=max(1 << 20, cpg << 17), rank=rank, world=world, sub_table_capacity=1 << 16)
     cs_events = []
 
     def step(timed):

@@ -171,7 +171,8 @@ class ExtractionPipeline:
     """Per-rank driver of the three hot-path stages over this rank's chunks (device-resident inputs)."""
 
     def __init__(self, n_sub: int, stencil=(13, 13, 7), chunk_table_capacity=1 << 18, log_capacity=1 << 21,
-                 pair_log_capacity=1 << 21, rank=0, world=1, group=None, min_obj_vx=None, with_syn=False, cs_dilation=2):
+                 pair_log_capacity=1 << 21, rank=0, world=1, group=None, min_obj_vx=None, with_syn=False, cs_dilation=2,
+                 sub_table_capacity=None):
         """``min_obj_vx``: {"cell": n, "sub0": n, ...} -- the worker's small-object drop (sd_proc.py:650-661, :667-680): objects
         that lie purely inside a chunk with fewer voxels are not reported (nor are their overlap pairs)."""
         from . import device as dev
@@ -179,8 +180,11 @@ class ExtractionPipeline:
         self.n_sub, self.stencil, self.rank, self.world, self.group = n_sub, tuple(stencil), rank, world, group
         self.t_cell = dev.IdTable(chunk_table_capacity)
         self.t_cs = dev.IdTable(chunk_table_capacity)
-        self.t_sub = [dev.IdTable(chunk_table_capacity) for _ in range(n_sub)]
-        self.t_pair = [dev.PairTable(chunk_table_capacity) for _ in range(n_sub)]
+        # per-chunk tables are cleared and scanned once per chunk: size the organelle / pair tables for the (far fewer) organelle
+        # objects of a chunk when the caller knows them (an overflow is detected and reported, never silent)
+        sub_cap = chunk_table_capacity if sub_table_capacity is None else sub_table_capacity
+        self.t_sub = [dev.IdTable(sub_cap) for _ in range(n_sub)]
+        self.t_pair = [dev.PairTable(sub_cap) for _ in range(n_sub)]
         self.kinds = ["cell", "cs"] + [f"sub{c}" for c in range(n_sub)] + (["syn"] if with_syn else [])
         self.min_obj_vx = dict(min_obj_vx or {})
         # with_syn: process_chunk(..., syn_masks=...) runs the whole numeric body of the contact-site worker

@@ -17,9 +17,8 @@ void syk_pool_keep_warm();  // raise the release threshold of the default stream
 // Stream of the calling host thread for the *_host entry points (non-blocking, created on first use): calls made
 // from different threads overlap their PCIe copies and kernels instead of serialising on the default stream.
 cudaStream_t syk_host_stream();
-// Wait for `s` by polling cudaStreamQuery and yielding the core in between.  The *_host entry points are called from many
-// worker threads / processes at once (one per GPU and more): waiters that spin inside cudaStreamSynchronize starve each
-// other as soon as there are more of them than cores.
+// Completion wait of the *_host entry points: cudaStreamSynchronize, or (SYK_YIELD_WAIT=1) a cudaStreamQuery poll that yields
+// the core, for hosts where more threads wait than there are cores.
 cudaError_t syk_stream_wait(cudaStream_t s);
 // Raise (never lower) a kernel's opt-in dynamic shared-memory limit.  The *_host API is thread-concurrent: setting the
 // attribute to the size of the current call would let two threads with different stencils undo each other between

@@ -97,10 +97,10 @@ bool syk_make_tmap3(CUtensorMap *m, const void *base, int elem_bytes, const long
 }
 
 cudaError_t syk_stream_wait(cudaStream_t s) {
-    // poll + yield: as prompt as a spinning cudaStreamSynchronize when the thread has a core to itself, but a waiter gives
-    // its core to the next runnable thread when there are more waiters than cores (SYK_SPIN_WAIT=1: plain synchronize)
-    static const bool spin = getenv("SYK_SPIN_WAIT") != nullptr;
-    if (spin) return cudaStreamSynchronize(s);
+    // Default: cudaStreamSynchronize (the driver spins; measured fastest for the *_host calls at 1 .. 8 ranks per box).
+    // SYK_YIELD_WAIT=1: poll cudaStreamQuery and yield the core in between -- for hosts with more waiting threads than cores.
+    static const bool yield = getenv("SYK_YIELD_WAIT") != nullptr;
+    if (!yield) return cudaStreamSynchronize(s);
     cudaError_t e;
     while ((e = cudaStreamQuery(s)) == cudaErrorNotReady) sched_yield();
     return e;
