@@ -536,6 +536,13 @@ def stress_section(local):
                                                   "contact_fraction": float((o != 0).float().mean())}
             del seg, o
         out["detect_cs_production_chunk_by_supervoxel_pitch"] = pitches
+        # row f4 (not part of the metric): scipy.ndimage.label equivalent on a thresholded 512^3 uint8 volume, ~6 % foreground blobs
+        prob = (dev.synth_labels((512, 512, 512), pitch=ORG_PITCH, seed=2, kind=7, density16=1, order="F") != 0).to(torch.uint8) * 200
+        lab, n_cc = dev.label_components(prob, 128)
+        ms = timeit(lambda: dev.label_components(prob, 128, out=lab))
+        out["label_components_512^3_uint8"] = {"ms": ms, "value": 512 ** 3 / ms / 1e6, "components": int(n_cc),
+                                               "foreground_fraction": float((prob != 0).float().mean())}
+        del prob, lab
         rnd = torch.randint(1, 2 ** 31 - 1, (96 + 12, 96 + 12, 96 + 6), dtype=torch.int32, device="cuda")
         o = dev.detect_cs(rnd, STENCIL)
         ms = timeit(lambda: dev.detect_cs(rnd, STENCIL, out=o), n=2)

@@ -108,8 +108,11 @@ __global__ void k_ccl_union(CclGeom G, unsigned *__restrict__ parent) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < G.total; i += (long long)gridDim.x * blockDim.x) {
         const unsigned p = parent[i];
         if (p == BG) continue;
-        const long long w = i % G.n[2];
-        const long long v = (i / G.n[2]) % G.n[1];
+        // total < 2^32 (checked on the host): 32-bit index arithmetic, a 64-bit division per voxel would dominate the pass
+        const unsigned iu = (unsigned)i, n2u = (unsigned)G.n[2], n1u = (unsigned)G.n[1];
+        const unsigned rowu = iu / n2u;
+        const long long w = iu - rowu * n2u;
+        const long long v = rowu % n1u;
         const bool run_start = (w == 0) || parent[i - 1] == BG || (w & 31) == 0;
         if ((w & 31) == 0 && w > 0 && parent[i - 1] != BG) unite(parent, (unsigned)i, (unsigned)(i - 1));
         // a voxel inside a run only needs its v / u neighbour when the neighbour's own left neighbour is background
@@ -120,7 +123,7 @@ __global__ void k_ccl_union(CclGeom G, unsigned *__restrict__ parent) {
 }
 
 // parent[i] = root; minlin[root] = min logical linear index over the component
-__global__ void k_ccl_flatten(CclGeom G, unsigned *__restrict__ parent, unsigned *__restrict__ minlin) {
+__global__ void k_ccl_flatten(CclGeom G, unsigned *__restrict__ parent, unsigned *__restrict__ minlin, unsigned long long *n_roots) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long rounds = (G.total + stride - 1) / stride;
     for (long long r = 0; r < rounds; ++r) {
@@ -129,14 +132,15 @@ __global__ void k_ccl_flatten(CclGeom G, unsigned *__restrict__ parent, unsigned
         if (i < G.total && parent[i] != BG) {
             root = find_root_ro(parent, (unsigned)i);
             parent[i] = root;
-            const long long w = i % G.n[2];
-            const long long q = i / G.n[2];
-            const long long v = q % G.n[1], u = q / G.n[1];
-            lin = (unsigned)(u * G.lc[0] + v * G.lc[1] + w * G.lc[2]);
+            const unsigned iu = (unsigned)i, n2u = (unsigned)G.n[2], n1u = (unsigned)G.n[1];
+            const unsigned q = iu / n2u, w = iu - q * n2u, u = q / n1u, v = q - u * n1u;
+            lin = u * (unsigned)G.lc[0] + v * (unsigned)G.lc[1] + w * (unsigned)G.lc[2];
         }
         const unsigned peers = __match_any_sync(FULL, root);
         const unsigned mn = __reduce_min_sync(peers, lin);
         if (root != BG && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicMin(&minlin[root], mn);
+        const unsigned roots_here = __ballot_sync(FULL, root != BG && root == (unsigned)i);  // the components are counted on the way
+        if ((threadIdx.x & 31) == 0 && roots_here) atomicAdd(n_roots, (unsigned long long)__popc(roots_here));
     }
 }
 
@@ -162,11 +166,10 @@ __global__ void k_ccl_rank(const unsigned *__restrict__ roots_sorted, unsigned l
 __global__ void k_ccl_write(CclGeom G, const unsigned *__restrict__ parent, const unsigned *__restrict__ label_of_root,
                             unsigned *__restrict__ out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < G.total; i += (long long)gridDim.x * blockDim.x) {
-        const long long w = i % G.n[2];
-        const long long q = i / G.n[2];
-        const long long v = q % G.n[1], u = q / G.n[1];
+        const unsigned iu = (unsigned)i, n2u = (unsigned)G.n[2], n1u = (unsigned)G.n[1];
+        const unsigned q = iu / n2u, w = iu - q * n2u, u = q / n1u, v = q - u * n1u;
         const unsigned p = parent[i];
-        out[u * G.ost[0] + v * G.ost[1] + w * G.ost[2]] = p == BG ? 0u : label_of_root[p];
+        out[(long long)u * G.ost[0] + (long long)v * G.ost[1] + (long long)w * G.ost[2]] = p == BG ? 0u : label_of_root[p];
     }
 }
 
@@ -241,9 +244,7 @@ SYK_API int syk_label_components(const void *vol_dev, int elem_bytes, const int6
     if (blocks > 148 * 16) blocks = 148 * 16;
     k_ccl_init<<<(unsigned)blocks, 256, 0, s>>>(vol_dev, G, parent);
     k_ccl_union<<<(unsigned)blocks, 256, 0, s>>>(G, parent);
-    k_ccl_flatten<<<(unsigned)blocks, 256, 0, s>>>(G, parent, minlin);
-    // pass 1: count the roots
-    k_ccl_collect_roots<<<(unsigned)blocks, 256, 0, s>>>(parent, minlin, total, nullptr, nullptr, counter, 0ull);
+    k_ccl_flatten<<<(unsigned)blocks, 256, 0, s>>>(G, parent, minlin, counter);
     SYK_CUDA(cudaGetLastError());
     unsigned long long n_roots = 0;
     SYK_CUDA(cudaMemcpyAsync(&n_roots, counter, sizeof(n_roots), cudaMemcpyDeviceToHost, s));
