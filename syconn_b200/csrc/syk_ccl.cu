@@ -23,7 +23,17 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr unsigned BG = 0xFFFFFFFFu;
 
+// exact division of a 32-bit number by a launch constant: one 64-bit multiply-high instead of the ~20-instruction udiv
+struct FastDiv {
+    unsigned long long m;  // floor(2^64 / d) + 1, 0 for d == 1
+    unsigned d;
+    __host__ FastDiv() : m(0), d(1) {}
+    __host__ explicit FastDiv(unsigned dd) : m(dd > 1 ? ~0ull / dd + 1ull : 0ull), d(dd) {}
+    __device__ __forceinline__ unsigned div(unsigned x) const { return m ? (unsigned)__umul64hi((unsigned long long)x, m) : x; }
+};
+
 struct CclGeom {
+    FastDiv dn2, dn1, dseg;  // by n[2], n[1], segments per row
     long long n[3];    // internal axes u, v, w (w = smallest input stride)
     long long ist[3];  // input strides (elements)
     long long ost[3];  // label strides (elements)
@@ -81,79 +91,148 @@ __device__ __forceinline__ void unite(unsigned *parent, unsigned a, unsigned b) 
     }
 }
 
-// rows of nw voxels are processed in segments of 32 lanes; index i = (u * nv + v) * nw + w
-__global__ void k_ccl_init(const void *__restrict__ vol, CclGeom G, unsigned *__restrict__ parent) {
-    const long long segs_per_row = (G.n[2] + 31) / 32;
-    const long long nseg = G.n[0] * G.n[1] * segs_per_row;
-    const int lane = threadIdx.x & 31;
-    for (long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < nseg; s += ((long long)gridDim.x * blockDim.x) >> 5) {
-        const long long row = s / segs_per_row, w = (s - row * segs_per_row) * 32 + lane;
-        const long long u = row / G.n[1], v = row - u * G.n[1];
-        const bool f = w < G.n[2] && fg_at(vol, G, u, v, w);
-        const unsigned m = __ballot_sync(FULL, f);
-        if (w < G.n[2]) {
-            unsigned p = BG;
-            if (f) {
-                const unsigned below = ~m & ((1u << lane) - 1u);            // background lanes before this one
-                const int start = below ? 32 - __clz((int)below) : 0;       // first lane of this run inside the segment
-                p = (unsigned)(row * G.n[2] + (w - lane + start));
+// rows of nw voxels are processed in segments of 32 lanes; index i = (u * nv + v) * nw + w.  A warp keeps four segments in
+// flight (a one-byte load per lane is only 32 B per request).  Roots are always foreground, so only segments with
+// foreground need the initial value of minlin.
+__global__ void k_ccl_init(const void *__restrict__ vol, CclGeom G, unsigned *__restrict__ parent, unsigned *__restrict__ minlin) {
+    // total < 2^32 (checked on the host): 32-bit index arithmetic, 64-bit divisions would dominate the pass
+    const unsigned n2 = (unsigned)G.n[2], n1 = (unsigned)G.n[1];
+    const unsigned segs_per_row = (n2 + 31u) / 32u;
+    const unsigned nseg = (unsigned)(G.n[0] * G.n[1]) * segs_per_row;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned wstride = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned s0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s0 < nseg; s0 += 4u * wstride) {
+        unsigned row[4], w[4];
+        bool f[4], live[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned s = s0 + (unsigned)k * wstride;
+            f[k] = false;
+            live[k] = s < nseg && s >= s0;  // s >= s0: no wrap-around
+            if (live[k]) {
+                row[k] = G.dseg.div(s);
+                w[k] = (s - row[k] * segs_per_row) * 32u + lane;
+                const unsigned u = G.dn1.div(row[k]), v = row[k] - u * n1;
+                f[k] = w[k] < n2 && fg_at(vol, G, u, v, w[k]);
             }
-            parent[row * G.n[2] + w] = p;
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!live[k]) break;  // warp-uniform
+            const unsigned m = __ballot_sync(FULL, f[k]);
+            if (w[k] < n2) {
+                unsigned p = BG;
+                const unsigned i = row[k] * n2 + w[k];
+                if (f[k]) {
+                    const unsigned below = ~m & ((1u << lane) - 1u);            // background lanes before this one
+                    const unsigned start = below ? 32u - __clz((int)below) : 0u;  // first lane of this run inside the segment
+                    p = i - lane + start;
+                }
+                parent[i] = p;
+                if (m) minlin[i] = BG;  // whole lines: scattered 4-byte stores would each cost a read-modify-write in DRAM
+            }
+        }
+        if (s0 + 4u * wstride < s0) break;  // the loop counter itself would wrap
     }
 }
 
-__global__ void k_ccl_union(CclGeom G, unsigned *__restrict__ parent) {
-    const long long plane = G.n[1] * G.n[2];
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < G.total; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned p = parent[i];
-        if (p == BG) continue;
-        // total < 2^32 (checked on the host): 32-bit index arithmetic, a 64-bit division per voxel would dominate the pass
-        const unsigned iu = (unsigned)i, n2u = (unsigned)G.n[2], n1u = (unsigned)G.n[1];
-        const unsigned rowu = iu / n2u;
-        const long long w = iu - rowu * n2u;
-        const long long v = rowu % n1u;
-        const bool run_start = (w == 0) || parent[i - 1] == BG || (w & 31) == 0;
-        if ((w & 31) == 0 && w > 0 && parent[i - 1] != BG) unite(parent, (unsigned)i, (unsigned)(i - 1));
-        // a voxel inside a run only needs its v / u neighbour when the neighbour's own left neighbour is background
-        // (otherwise the run start or an earlier voxel of the run already made that connection)
-        if (v > 0 && parent[i - G.n[2]] != BG && (run_start || parent[i - G.n[2] - 1] == BG)) unite(parent, (unsigned)i, (unsigned)(i - G.n[2]));
-        if (i >= plane && parent[i - plane] != BG && (run_start || parent[i - plane - 1] == BG)) unite(parent, (unsigned)i, (unsigned)(i - plane));
+// Foreground is sparse and a union is a chain of dependent loads: executed where they are found, one or two lanes of a warp
+// would chase pointers while thirty wait.  Every warp therefore queues its (voxel, neighbour) pairs in shared memory and
+// unites them 32 at a time, all lanes busy.
+__global__ void __launch_bounds__(256) k_ccl_union(CclGeom G, unsigned *__restrict__ parent) {
+    __shared__ unsigned q_a[8][128], q_b[8][128];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned *qa = q_a[wid], *qb = q_b[wid];
+    unsigned qn = 0u;  // warp-uniform, < 32 between iterations; one iteration adds at most 96
+    // total < 2^32 (checked on the host): 32-bit index arithmetic, a 64-bit division per voxel would dominate the pass
+    const unsigned n2 = (unsigned)G.n[2], n1 = (unsigned)G.n[1], plane = n1 * n2;
+    const unsigned lt = (1u << lane) - 1u;
+    const long long wstride = (long long)gridDim.x * 8 * 32;
+    long long base = ((long long)blockIdx.x * 8 + wid) * 32;
+    unsigned p = base + lane < G.total ? parent[base + lane] : BG;
+    for (; base < G.total; base += wstride) {
+        const long long nb = base + wstride;
+        const unsigned pn = nb + lane < G.total ? parent[nb + lane] : BG;  // next segment's load is in flight during this one
+        if (__any_sync(FULL, p != BG)) {
+            const unsigned i = (unsigned)base + (unsigned)lane;
+            bool t0 = false, t1 = false, t2 = false;
+            if (p != BG) {
+                const unsigned row = G.dn2.div(i), w = i - row * n2, v = row - G.dn1.div(row) * n1;
+                const bool left = w > 0 && parent[i - 1] != BG;
+                const bool run_start = !left || (w & 31) == 0;
+                t0 = left && (w & 31) == 0;  // runs were cut at the 32-voxel segment edge by the init pass
+                // a voxel inside a run only needs its v / u neighbour when the neighbour's own left neighbour is background
+                // (otherwise the run start or an earlier voxel of the run already made that connection)
+                t1 = v > 0 && parent[i - n2] != BG && (run_start || parent[i - n2 - 1] == BG);
+                t2 = i >= plane && parent[i - plane] != BG && (run_start || parent[i - plane - 1] == BG);
+            }
+            unsigned m = __ballot_sync(FULL, t0);
+            if (t0) { const unsigned k = qn + __popc(m & lt); qa[k] = i; qb[k] = i - 1; }
+            qn += __popc(m);
+            m = __ballot_sync(FULL, t1);
+            if (t1) { const unsigned k = qn + __popc(m & lt); qa[k] = i; qb[k] = i - n2; }
+            qn += __popc(m);
+            m = __ballot_sync(FULL, t2);
+            if (t2) { const unsigned k = qn + __popc(m & lt); qa[k] = i; qb[k] = i - plane; }
+            qn += __popc(m);
+            __syncwarp();
+            while (qn >= 32u) {
+                qn -= 32u;
+                unite(parent, qa[qn + lane], qb[qn + lane]);
+                __syncwarp();
+            }
+        }
+        p = pn;
     }
+    if ((unsigned)lane < qn) unite(parent, qa[lane], qb[lane]);
 }
 
-// parent[i] = root; minlin[root] = min logical linear index over the component
-__global__ void k_ccl_flatten(CclGeom G, unsigned *__restrict__ parent, unsigned *__restrict__ minlin, unsigned long long *n_roots) {
+// parent[i] = root; minlin[root] = min logical linear index over the component; the roots are counted and, while the list
+// has room, collected on the way
+__global__ void k_ccl_flatten(CclGeom G, unsigned *__restrict__ parent, unsigned *__restrict__ minlin, unsigned long long *n_roots,
+                              unsigned *__restrict__ root_list, unsigned long long list_cap) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long rounds = (G.total + stride - 1) / stride;
+    const unsigned lane = threadIdx.x & 31;
     for (long long r = 0; r < rounds; ++r) {
         const long long i = r * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        unsigned root = BG, lin = BG;
-        if (i < G.total && parent[i] != BG) {
-            root = find_root_ro(parent, (unsigned)i);
+        unsigned root = i < G.total ? parent[i] : BG;  // this entry is only ever written by this thread
+        if (!__any_sync(FULL, root != BG)) continue;
+        unsigned lin = BG;
+        if (root != BG) {
+            if (root != (unsigned)i) root = find_root_ro(parent, root);
             parent[i] = root;
             const unsigned iu = (unsigned)i, n2u = (unsigned)G.n[2], n1u = (unsigned)G.n[1];
-            const unsigned q = iu / n2u, w = iu - q * n2u, u = q / n1u, v = q - u * n1u;
+            const unsigned q = G.dn2.div(iu), w = iu - q * n2u, u = G.dn1.div(q), v = q - u * n1u;
             lin = u * (unsigned)G.lc[0] + v * (unsigned)G.lc[1] + w * (unsigned)G.lc[2];
         }
         const unsigned peers = __match_any_sync(FULL, root);
         const unsigned mn = __reduce_min_sync(peers, lin);
-        if (root != BG && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicMin(&minlin[root], mn);
-        const unsigned roots_here = __ballot_sync(FULL, root != BG && root == (unsigned)i);  // the components are counted on the way
-        if ((threadIdx.x & 31) == 0 && roots_here) atomicAdd(n_roots, (unsigned long long)__popc(roots_here));
+        if (root != BG && (unsigned)(__ffs(peers) - 1) == lane) atomicMin(&minlin[root], mn);
+        const bool is_root = root != BG && root == (unsigned)i;
+        const unsigned roots_here = __ballot_sync(FULL, is_root);
+        if (roots_here) {
+            unsigned long long base = 0ull;
+            if (lane == 0) base = atomicAdd(n_roots, (unsigned long long)__popc(roots_here));
+            base = __shfl_sync(FULL, base, 0);
+            const unsigned long long pos = base + __popc(roots_here & ((1u << lane) - 1u));
+            if (is_root && pos < list_cap) root_list[pos] = root;
+        }
     }
 }
 
-__global__ void k_ccl_collect_roots(const unsigned *__restrict__ parent, const unsigned *__restrict__ minlin, long long total,
-                                    unsigned *__restrict__ keys, unsigned *__restrict__ roots, unsigned long long *counter,
-                                    unsigned long long max_roots) {
+__global__ void k_ccl_keys(const unsigned *__restrict__ roots, const unsigned *__restrict__ minlin, unsigned long long n,
+                           unsigned *__restrict__ keys) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = minlin[roots[i]];
+}
+
+__global__ void k_ccl_collect_roots(const unsigned *__restrict__ parent, unsigned *__restrict__ roots, long long total,
+                                    unsigned long long *counter, unsigned long long max_roots) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         if (parent[i] == (unsigned)i) {
             const unsigned long long pos = atomicAdd(counter, 1ull);
-            if (pos < max_roots) {
-                keys[pos] = minlin[i];
-                roots[pos] = (unsigned)i;
-            }
+            if (pos < max_roots) roots[pos] = (unsigned)i;
         }
     }
 }
@@ -163,13 +242,20 @@ __global__ void k_ccl_rank(const unsigned *__restrict__ roots_sorted, unsigned l
     if (i < n) label_of_root[roots_sorted[i]] = (unsigned)(i + 1ull);
 }
 
+// DENSE: the label array has the layout of the internal index (the usual case: labels allocated like the input)
+template <bool DENSE>
 __global__ void k_ccl_write(CclGeom G, const unsigned *__restrict__ parent, const unsigned *__restrict__ label_of_root,
                             unsigned *__restrict__ out) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < G.total; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned iu = (unsigned)i, n2u = (unsigned)G.n[2], n1u = (unsigned)G.n[1];
-        const unsigned q = iu / n2u, w = iu - q * n2u, u = q / n1u, v = q - u * n1u;
         const unsigned p = parent[i];
-        out[(long long)u * G.ost[0] + (long long)v * G.ost[1] + (long long)w * G.ost[2]] = p == BG ? 0u : label_of_root[p];
+        const unsigned lab = p == BG ? 0u : label_of_root[p];
+        if (DENSE) {
+            __stcs(out + i, lab);
+        } else {
+            const unsigned iu = (unsigned)i, n2u = (unsigned)G.n[2], n1u = (unsigned)G.n[1];
+            const unsigned q = G.dn2.div(iu), w = iu - q * n2u, u = G.dn1.div(q), v = q - u * n1u;
+            out[(long long)u * G.ost[0] + (long long)v * G.ost[1] + (long long)w * G.ost[2]] = lab;
+        }
     }
 }
 
@@ -227,55 +313,65 @@ SYK_API int syk_label_components(const void *vol_dev, int elem_bytes, const int6
         G.ost[a] = label_strides[ax[a]];
         G.lc[a] = lcoef[ax[a]];
     }
+    G.dn2 = FastDiv((unsigned)G.n[2]);
+    G.dn1 = FastDiv((unsigned)G.n[1]);
+    G.dseg = FastDiv((unsigned)((G.n[2] + 31) / 32));
     G.total = total;
     G.thr = threshold;
     G.elem_bytes = elem_bytes;
-    unsigned *parent = nullptr, *minlin = nullptr, *keys = nullptr, *roots = nullptr, *keys2 = nullptr, *roots2 = nullptr;
-    unsigned long long *counter = nullptr;
-    void *tmp = nullptr;
-    // components are at most total / 2 + 1 under 6-connectivity only in pathological checkerboards; size the root list for the
-    // worst case lazily: first count, then allocate
-    SYK_CUDA(cudaMallocAsync((void **)&parent, sizeof(unsigned) * (size_t)total, s));
-    SYK_CUDA(cudaMallocAsync((void **)&minlin, sizeof(unsigned) * (size_t)total, s));
-    SYK_CUDA(cudaMallocAsync((void **)&counter, sizeof(unsigned long long), s));
-    SYK_CUDA(cudaMemsetAsync(minlin, 0xFF, sizeof(unsigned) * (size_t)total, s));
+    // scratch from the stream-ordered pool, returned on every exit path
+    struct Scratch {
+        cudaStream_t s;
+        void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        ~Scratch() {
+            for (void *x : p)
+                if (x) cudaFreeAsync(x, s);
+        }
+    } sc{s};
+    syk_pool_keep_warm();  // a call per chunk must not pay allocator round trips for its two 4-byte-per-voxel arrays
+    SYK_CUDA(cudaMallocAsync(&sc.p[0], sizeof(unsigned) * (size_t)total, s));
+    SYK_CUDA(cudaMallocAsync(&sc.p[1], sizeof(unsigned) * (size_t)total, s));
+    SYK_CUDA(cudaMallocAsync(&sc.p[2], sizeof(unsigned long long), s));
+    unsigned *parent = (unsigned *)sc.p[0], *minlin = (unsigned *)sc.p[1];
+    unsigned long long *counter = (unsigned long long *)sc.p[2];
     SYK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
     long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    k_ccl_init<<<(unsigned)blocks, 256, 0, s>>>(vol_dev, G, parent);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_ccl_init<<<(unsigned)blocks, 256, 0, s>>>(vol_dev, G, parent, minlin);
     k_ccl_union<<<(unsigned)blocks, 256, 0, s>>>(G, parent);
-    k_ccl_flatten<<<(unsigned)blocks, 256, 0, s>>>(G, parent, minlin, counter);
+    // roots found by the flatten pass go to a list sized for the common case; a volume with more components (up to total / 2
+    // in a checkerboard) is swept once more with a list of the counted size
+    unsigned long long list_cap = (unsigned long long)total / 64 + 1024;
+    SYK_CUDA(cudaMallocAsync(&sc.p[3], sizeof(unsigned) * 4 * (size_t)list_cap, s));
+    k_ccl_flatten<<<(unsigned)blocks, 256, 0, s>>>(G, parent, minlin, counter, (unsigned *)sc.p[3], list_cap);
     SYK_CUDA(cudaGetLastError());
     unsigned long long n_roots = 0;
     SYK_CUDA(cudaMemcpyAsync(&n_roots, counter, sizeof(n_roots), cudaMemcpyDeviceToHost, s));
     SYK_CUDA(cudaStreamSynchronize(s));
     *n_labels_host = n_roots;
-    int ret = SYK_OK;
     if (n_roots > 0) {
-        SYK_CUDA(cudaMallocAsync((void **)&keys, sizeof(unsigned) * 4 * (size_t)n_roots, s));
-        roots = keys + n_roots;
-        keys2 = roots + n_roots;
-        roots2 = keys2 + n_roots;
-        SYK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
-        k_ccl_collect_roots<<<(unsigned)blocks, 256, 0, s>>>(parent, minlin, total, keys, roots, counter, n_roots);
+        if (n_roots > list_cap) {
+            SYK_CUDA(cudaFreeAsync(sc.p[3], s));
+            sc.p[3] = nullptr;
+            SYK_CUDA(cudaMallocAsync(&sc.p[3], sizeof(unsigned) * 4 * (size_t)n_roots, s));
+            SYK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
+            k_ccl_collect_roots<<<(unsigned)blocks, 256, 0, s>>>(parent, (unsigned *)sc.p[3], total, counter, n_roots);
+        }
+        // [roots | keys | sorted keys | sorted roots]
+        unsigned *roots = (unsigned *)sc.p[3], *keys = roots + n_roots, *keys2 = keys + n_roots, *roots2 = keys2 + n_roots;
+        k_ccl_keys<<<(unsigned)((n_roots + 255) / 256), 256, 0, s>>>(roots, minlin, n_roots, keys);
         size_t tmp_bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, roots, roots2, (int)n_roots, 0, 32, s);
-        SYK_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, s));
-        cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, roots, roots2, (int)n_roots, 0, 32, s);
+        SYK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, roots, roots2, (int)n_roots, 0, 32, s));
+        SYK_CUDA(cudaMallocAsync(&sc.p[4], tmp_bytes ? tmp_bytes : 16, s));
+        SYK_CUDA(cub::DeviceRadixSort::SortPairs(sc.p[4], tmp_bytes, keys, keys2, roots, roots2, (int)n_roots, 0, 32, s));
         // minlin is no longer needed: reuse it as label_of_root
         k_ccl_rank<<<(unsigned)((n_roots + 255) / 256), 256, 0, s>>>(roots2, n_roots, minlin);
     }
-    k_ccl_write<<<(unsigned)blocks, 256, 0, s>>>(G, parent, minlin, labels_dev);
-    if (cudaGetLastError() != cudaSuccess) {
-        syk_set_error("syk_label_components: kernel launch failed");
-        ret = SYK_ECUDA;
-    }
-    if (tmp) cudaFreeAsync(tmp, s);
-    if (keys) cudaFreeAsync(keys, s);
-    cudaFreeAsync(counter, s);
-    cudaFreeAsync(minlin, s);
-    cudaFreeAsync(parent, s);
-    return ret;
+    const bool dense_out = G.ost[2] == 1 && G.ost[1] == G.n[2] && G.ost[0] == G.n[1] * G.n[2];
+    if (dense_out) k_ccl_write<true><<<(unsigned)blocks, 256, 0, s>>>(G, parent, minlin, labels_dev);
+    else k_ccl_write<false><<<(unsigned)blocks, 256, 0, s>>>(G, parent, minlin, labels_dev);
+    SYK_CUDA(cudaGetLastError());
+    return SYK_OK;
 }
 
 SYK_API int syk_label_overlap_pairs(syk_pairs_t *pairs, const uint32_t *a_dev, const int64_t a_strides[3], const uint32_t *b_dev,

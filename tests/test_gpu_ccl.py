@@ -59,6 +59,22 @@ def test_label_components_edge_cases():
         assert n == n_want and np.array_equal(lab.cpu().numpy(), want)
 
 
+def test_label_components_into_foreign_layout():
+    """Labels written into a caller's array whose memory order differs from the input's (strided store path)."""
+    from syconn_b200 import device as dev
+    rng = np.random.default_rng(5)
+    a = (rng.random((37, 29, 45)) < 0.45).astype(np.uint8)
+    want, n_want = scipy.ndimage.label(a)
+    vol = torch.from_numpy(np.asfortranarray(a).T.copy()).cuda().permute(2, 1, 0)  # x fastest in memory
+    assert vol.stride(0) == 1
+    out = torch.full(a.shape, -1, dtype=torch.int32, device="cuda")                # z fastest
+    lab, n = dev.label_components(vol, out=out)
+    assert lab is out and n == n_want and np.array_equal(out.cpu().numpy(), want)
+    big = torch.full((37, 29, 90), -1, dtype=torch.int32, device="cuda")           # every second element of a larger buffer
+    lab, n = dev.label_components(vol, out=big[:, :, ::2])
+    assert n == n_want and np.array_equal(big[:, :, ::2].cpu().numpy(), want) and bool((big[:, :, 1::2] == -1).all())
+
+
 def test_label_components_big_volume_properties():
     """256 x 256 x 320 (21 M voxels): equality with scipy on a volume that needs many CTAs and long-range unions."""
     from syconn_b200 import device as dev
