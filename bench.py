@@ -352,7 +352,7 @@ def run_ours(args):
         line["e2e"] = None
     if rank == 0 and world == 1 and not args.no_stress:
         line["worker_body"] = worker_body_section(args, plan, chunks)
-        line["stress"] = stress_section(local)
+        line["stress"] = stress_section(local, with_cpu=not args.no_cpu)
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"], _ = cpu_baseline(args.cpu_seconds)
     if world > 1:
@@ -478,7 +478,7 @@ def worker_body_section(args, plan, chunks):
                     "props + map_subcell_extract_props with min_obj_vx = 10 + merge + mapping inversion; CUDA events, median of 3"}
 
 
-def stress_section(local):
+def stress_section(local, with_cpu=False):
     """BASELINE config 5 and the second workload point, measured inside the same run (device-resident, CUDA events, min
     of 3 after a warm-up): 1e7 distinct ids through find_object_properties, the stencil sweep of detect_cs, supervoxel
     pitch 16x16x8 on the production chunk (runs in the 64-id tier), near-random labels (generic kernel)."""
@@ -542,6 +542,15 @@ def stress_section(local):
         ms = timeit(lambda: dev.label_components(prob, 128, out=lab))
         out["label_components_512^3_uint8"] = {"ms": ms, "value": 512 ** 3 / ms / 1e6, "components": int(n_cc),
                                                "foreground_fraction": float((prob != 0).float().mean())}
+        if with_cpu:  # what the reference's worker calls (object_extraction_steps.py:350), one core, on a 256^3 corner; the
+            import scipy.ndimage  # corner is also one more parity check of the labels
+            corner = prob[:256, :256, :256]
+            t0 = time.perf_counter()
+            want, _ = scipy.ndimage.label(corner.cpu().numpy() > 128)
+            dt = time.perf_counter() - t0
+            got, _ = dev.label_components(corner, 128)
+            out["label_components_512^3_uint8"].update(cpu_scipy_value=256 ** 3 / dt / 1e9, cpu_sample="256^3 corner, 1 core",
+                                                       corner_equals_scipy=bool(np.array_equal(got.cpu().numpy(), want)))
         del prob, lab
         rnd = torch.randint(1, 2 ** 31 - 1, (96 + 12, 96 + 12, 96 + 6), dtype=torch.int32, device="cuda")
         o = dev.detect_cs(rnd, STENCIL)
