@@ -33,7 +33,7 @@ struct FastDiv {
 };
 
 struct CclGeom {
-    FastDiv dn2, dn1, dseg;  // by n[2], n[1], segments per row
+    FastDiv dn2, dn1;  // by n[2], n[1]
     long long n[3];    // internal axes u, v, w (w = smallest input stride)
     long long ist[3];  // input strides (elements)
     long long ost[3];  // label strides (elements)
@@ -42,16 +42,6 @@ struct CclGeom {
     unsigned long long thr;
     int elem_bytes;
 };
-
-__device__ __forceinline__ bool fg_at(const void *vol, const CclGeom &G, long long u, long long v, long long w) {
-    const long long o = u * G.ist[0] + v * G.ist[1] + w * G.ist[2];
-    unsigned long long x;
-    if (G.elem_bytes == 1) x = ((const unsigned char *)vol)[o];
-    else if (G.elem_bytes == 2) x = ((const unsigned short *)vol)[o];
-    else if (G.elem_bytes == 4) x = ((const unsigned *)vol)[o];
-    else x = ((const unsigned long long *)vol)[o];
-    return x > G.thr;
-}
 
 __device__ __forceinline__ unsigned find_root(unsigned *parent, unsigned i) {
     unsigned p = parent[i];
@@ -91,48 +81,45 @@ __device__ __forceinline__ void unite(unsigned *parent, unsigned a, unsigned b) 
     }
 }
 
-// rows of nw voxels are processed in segments of 32 lanes; index i = (u * nv + v) * nw + w.  A warp keeps four segments in
-// flight (a one-byte load per lane is only 32 B per request).  Roots are always foreground, so only segments with
-// foreground need the initial value of minlin.
-__global__ void k_ccl_init(const void *__restrict__ vol, CclGeom G, unsigned *__restrict__ parent, unsigned *__restrict__ minlin) {
+// rows of nw voxels are processed in segments of 32 lanes; index i = (u * nv + v) * nw + w.  A warp owns whole rows (the
+// index arithmetic is paid once per row) and keeps four segments in flight (a one-byte load per lane is only 32 B per
+// request).  Roots are always foreground, so only segments with foreground need the initial value of minlin.
+template <typename T>
+__global__ void k_ccl_init(const T *__restrict__ vol, CclGeom G, unsigned *__restrict__ parent, unsigned *__restrict__ minlin) {
     // total < 2^32 (checked on the host): 32-bit index arithmetic, 64-bit divisions would dominate the pass
-    const unsigned n2 = (unsigned)G.n[2], n1 = (unsigned)G.n[1];
-    const unsigned segs_per_row = (n2 + 31u) / 32u;
-    const unsigned nseg = (unsigned)(G.n[0] * G.n[1]) * segs_per_row;
+    const unsigned n2 = (unsigned)G.n[2], n1 = (unsigned)G.n[1], nrows = (unsigned)(G.n[0] * G.n[1]);
     const unsigned lane = threadIdx.x & 31;
     const unsigned wstride = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned s0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s0 < nseg; s0 += 4u * wstride) {
-        unsigned row[4], w[4];
-        bool f[4], live[4];
+    const T thr = (T)G.thr;  // the host clamps the threshold to the element type's range
+    for (unsigned row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrows; row += wstride) {
+        const unsigned u = G.dn1.div(row), v = row - u * n1;
+        const T *src = vol + ((long long)u * G.ist[0] + (long long)v * G.ist[1]);
+        const unsigned i0 = row * n2;
+        for (unsigned w0 = 0; w0 < n2; w0 += 128u) {
+            bool f[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned s = s0 + (unsigned)k * wstride;
-            f[k] = false;
-            live[k] = s < nseg && s >= s0;  // s >= s0: no wrap-around
-            if (live[k]) {
-                row[k] = G.dseg.div(s);
-                w[k] = (s - row[k] * segs_per_row) * 32u + lane;
-                const unsigned u = G.dn1.div(row[k]), v = row[k] - u * n1;
-                f[k] = w[k] < n2 && fg_at(vol, G, u, v, w[k]);
+            for (int k = 0; k < 4; ++k) {
+                const unsigned w = w0 + 32u * k + lane;
+                f[k] = w < n2 && src[(long long)w * G.ist[2]] > thr;
             }
-        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!live[k]) break;  // warp-uniform
-            const unsigned m = __ballot_sync(FULL, f[k]);
-            if (w[k] < n2) {
-                unsigned p = BG;
-                const unsigned i = row[k] * n2 + w[k];
-                if (f[k]) {
-                    const unsigned below = ~m & ((1u << lane) - 1u);            // background lanes before this one
-                    const unsigned start = below ? 32u - __clz((int)below) : 0u;  // first lane of this run inside the segment
-                    p = i - lane + start;
+            for (int k = 0; k < 4; ++k) {
+                const unsigned w = w0 + 32u * k + lane;
+                const unsigned m = __ballot_sync(FULL, f[k]);
+                if (w < n2) {
+                    unsigned p = BG;
+                    if (f[k]) {
+                        const unsigned below = ~m & ((1u << lane) - 1u);            // background lanes before this one
+                        const unsigned start = below ? 32u - __clz((int)below) : 0u;  // first lane of this run inside the segment
+                        p = i0 + w - lane + start;
+                    }
+                    parent[i0 + w] = p;
+                    if (m) minlin[i0 + w] = BG;  // whole lines: scattered 4-byte stores would each cost a read-modify-write in DRAM
                 }
-                parent[i] = p;
-                if (m) minlin[i] = BG;  // whole lines: scattered 4-byte stores would each cost a read-modify-write in DRAM
             }
+            if (w0 + 128u < w0) break;
         }
-        if (s0 + 4u * wstride < s0) break;  // the loop counter itself would wrap
+        if (row + wstride < row) break;  // the loop counter itself would wrap
     }
 }
 
@@ -188,37 +175,64 @@ __global__ void __launch_bounds__(256) k_ccl_union(CclGeom G, unsigned *__restri
 }
 
 // parent[i] = root; minlin[root] = min logical linear index over the component; the roots are counted and, while the list
-// has room, collected on the way
-__global__ void k_ccl_flatten(CclGeom G, unsigned *__restrict__ parent, unsigned *__restrict__ minlin, unsigned long long *n_roots,
-                              unsigned *__restrict__ root_list, unsigned long long list_cap) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long rounds = (G.total + stride - 1) / stride;
-    const unsigned lane = threadIdx.x & 31;
-    for (long long r = 0; r < rounds; ++r) {
-        const long long i = r * stride + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        unsigned root = i < G.total ? parent[i] : BG;  // this entry is only ever written by this thread
-        if (!__any_sync(FULL, root != BG)) continue;
-        unsigned lin = BG;
-        if (root != BG) {
-            if (root != (unsigned)i) root = find_root_ro(parent, root);
-            parent[i] = root;
-            const unsigned iu = (unsigned)i, n2u = (unsigned)G.n[2], n1u = (unsigned)G.n[1];
-            const unsigned q = G.dn2.div(iu), w = iu - q * n2u, u = G.dn1.div(q), v = q - u * n1u;
-            lin = u * (unsigned)G.lc[0] + v * (unsigned)G.lc[1] + w * (unsigned)G.lc[2];
-        }
-        const unsigned peers = __match_any_sync(FULL, root);
-        const unsigned mn = __reduce_min_sync(peers, lin);
-        if (root != BG && (unsigned)(__ffs(peers) - 1) == lane) atomicMin(&minlin[root], mn);
-        const bool is_root = root != BG && root == (unsigned)i;
-        const unsigned roots_here = __ballot_sync(FULL, is_root);
-        if (roots_here) {
-            unsigned long long base = 0ull;
-            if (lane == 0) base = atomicAdd(n_roots, (unsigned long long)__popc(roots_here));
-            base = __shfl_sync(FULL, base, 0);
-            const unsigned long long pos = base + __popc(roots_here & ((1u << lane) - 1u));
-            if (is_root && pos < list_cap) root_list[pos] = root;
-        }
+// has room, collected on the way.  Foreground voxels are queued per warp like the unions, so that all lanes chase a chain.
+__device__ __forceinline__ void flatten32(const CclGeom &G, unsigned *parent, unsigned *minlin, bool valid, unsigned i, unsigned p,
+                                          unsigned lane) {
+    unsigned root = BG, lin = BG;
+    if (valid) {
+        root = p == i ? i : find_root_ro(parent, p);
+        if (root != p) parent[i] = root;  // this entry is only ever written here, by the one lane that owns voxel i
+        const unsigned n2u = (unsigned)G.n[2], n1u = (unsigned)G.n[1];
+        const unsigned q = G.dn2.div(i), w = i - q * n2u, u = G.dn1.div(q), v = q - u * n1u;
+        lin = u * (unsigned)G.lc[0] + v * (unsigned)G.lc[1] + w * (unsigned)G.lc[2];
     }
+    const unsigned peers = __match_any_sync(FULL, root);
+    const unsigned mn = __reduce_min_sync(peers, lin);
+    if (valid && (unsigned)(__ffs(peers) - 1) == lane) atomicMin(&minlin[root], mn);
+}
+
+__global__ void __launch_bounds__(256) k_ccl_flatten(CclGeom G, unsigned *__restrict__ parent, unsigned *__restrict__ minlin,
+                                                     unsigned long long *n_roots, unsigned *__restrict__ root_list,
+                                                     unsigned long long list_cap) {
+    __shared__ unsigned q_i[8][64], q_p[8][64];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned *qi = q_i[wid], *qp = q_p[wid];
+    unsigned qn = 0u;  // warp-uniform, < 32 between iterations
+    const unsigned lt = (1u << lane) - 1u;
+    const long long wstride = (long long)gridDim.x * 8 * 32;
+    long long base = ((long long)blockIdx.x * 8 + wid) * 32;
+    unsigned p = base + lane < G.total ? parent[base + lane] : BG;
+    for (; base < G.total; base += wstride) {
+        const long long nb = base + wstride;
+        const unsigned pn = nb + lane < G.total ? parent[nb + lane] : BG;
+        const bool fg = p != BG;
+        const unsigned m = __ballot_sync(FULL, fg);
+        if (m) {
+            const unsigned i = (unsigned)base + lane;
+            const bool is_root = fg && p == i;  // stable: only non-root entries are ever rewritten during this pass
+            const unsigned roots_here = __ballot_sync(FULL, is_root);
+            if (roots_here) {
+                unsigned long long at = 0ull;
+                if (lane == 0) at = atomicAdd(n_roots, (unsigned long long)__popc(roots_here));
+                at = __shfl_sync(FULL, at, 0) + __popc(roots_here & lt);
+                if (is_root && at < list_cap) root_list[at] = i;
+            }
+            if (fg) {
+                const unsigned k = qn + __popc(m & lt);
+                qi[k] = i;
+                qp[k] = p;
+            }
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32u) {
+                qn -= 32u;
+                flatten32(G, parent, minlin, true, qi[qn + lane], qp[qn + lane], lane);
+                __syncwarp();
+            }
+        }
+        p = pn;
+    }
+    if (qn) flatten32(G, parent, minlin, lane < qn, lane < qn ? qi[lane] : 0u, lane < qn ? qp[lane] : 0u, lane);
 }
 
 __global__ void k_ccl_keys(const unsigned *__restrict__ roots, const unsigned *__restrict__ minlin, unsigned long long n,
@@ -315,7 +329,6 @@ SYK_API int syk_label_components(const void *vol_dev, int elem_bytes, const int6
     }
     G.dn2 = FastDiv((unsigned)G.n[2]);
     G.dn1 = FastDiv((unsigned)G.n[1]);
-    G.dseg = FastDiv((unsigned)((G.n[2] + 31) / 32));
     G.total = total;
     G.thr = threshold;
     G.elem_bytes = elem_bytes;
@@ -337,7 +350,13 @@ SYK_API int syk_label_components(const void *vol_dev, int elem_bytes, const int6
     SYK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_ccl_init<<<(unsigned)blocks, 256, 0, s>>>(vol_dev, G, parent, minlin);
+    // a threshold at or above the element type's maximum selects nothing; clamping keeps the typed comparison exact
+    const unsigned long long tmax = elem_bytes == 8 ? ~0ull : (1ull << (8 * elem_bytes)) - 1ull;
+    if (G.thr > tmax) G.thr = tmax;
+    if (elem_bytes == 1) k_ccl_init<<<(unsigned)blocks, 256, 0, s>>>((const unsigned char *)vol_dev, G, parent, minlin);
+    else if (elem_bytes == 2) k_ccl_init<<<(unsigned)blocks, 256, 0, s>>>((const unsigned short *)vol_dev, G, parent, minlin);
+    else if (elem_bytes == 4) k_ccl_init<<<(unsigned)blocks, 256, 0, s>>>((const unsigned *)vol_dev, G, parent, minlin);
+    else k_ccl_init<<<(unsigned)blocks, 256, 0, s>>>((const unsigned long long *)vol_dev, G, parent, minlin);
     k_ccl_union<<<(unsigned)blocks, 256, 0, s>>>(G, parent);
     // roots found by the flatten pass go to a list sized for the common case; a volume with more components (up to total / 2
     // in a checkerboard) is swept once more with a list of the counted size
