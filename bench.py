@@ -551,7 +551,35 @@ def stress_section(local, with_cpu=False):
             got, _ = dev.label_components(corner, 128)
             out["label_components_512^3_uint8"].update(cpu_scipy_value=256 ** 3 / dt / 1e9, cpu_sample="256^3 corner, 1 core",
                                                        corner_equals_scipy=bool(np.array_equal(got.cpu().numpy(), want)))
-        del prob, lab
+        # row f4, the morphology hook between threshold and labelling: the default 'sj' op list (config.yml:135) with the
+        # anisotropic 5x5x3 element on the same volume, then the whole chunk step (threshold + ops + labelling)
+        from syconn_b200.proc import image
+        from syconn_b200.extraction import object_extraction_steps as oes
+        sj_ops = ["binary_opening", "binary_closing", "binary_erosion"]
+        st = image.get_aniso_struct((10, 10, 20))
+        mask = (prob > 128).to(torch.uint8)
+        work = mask.clone()
+
+        def morph():
+            work.copy_(mask)
+            image.apply_morphological_operations(work, sj_ops, dict(structure=st))
+        ms_copy = timeit(lambda: work.copy_(mask))
+        ms = timeit(morph) - ms_copy
+        out["binary_morph_ops_sj_512^3_uint8"] = {"ms": ms, "value": 512 ** 3 / ms / 1e6, "steps": 5,
+                                                  "foreground_after": float(work.float().mean())}
+        ms = timeit(lambda: oes.watershed_seeds_chunk(prob, 128, sj_ops, st, min_seed_vx=10))
+        out["watershed_seeds_chunk_sj_512^3"] = {"ms": ms, "value": 512 ** 3 / ms / 1e6}
+        if with_cpu:
+            import scipy.ndimage
+            from oracle import oracle
+            corner = mask[:128, :128, :128].cpu().numpy().copy()
+            t0 = time.perf_counter()
+            want = oracle.apply_morphological_operations(corner.copy(), sj_ops, st)  # calls scipy.ndimage like the reference
+            dt = time.perf_counter() - t0
+            got = image.apply_morphological_operations(torch.from_numpy(corner).cuda(), sj_ops, dict(structure=st))
+            out["binary_morph_ops_sj_512^3_uint8"].update(cpu_scipy_value=128 ** 3 / dt / 1e9, cpu_sample="128^3 corner, 1 core",
+                                                          corner_equals_scipy=bool(np.array_equal(got.cpu().numpy(), want)))
+        del prob, lab, mask, work
         rnd = torch.randint(1, 2 ** 31 - 1, (96 + 12, 96 + 12, 96 + 6), dtype=torch.int32, device="cuda")
         o = dev.detect_cs(rnd, STENCIL)
         ms = timeit(lambda: dev.detect_cs(rnd, STENCIL, out=o), n=2)

@@ -262,6 +262,25 @@ int syk_label_components(const void *vol_dev, int elem_bytes, const int64_t shap
 int syk_label_overlap_pairs(syk_pairs_t *pairs, const uint32_t *a_dev, const int64_t a_strides[3], const uint32_t *b_dev,
                             const int64_t b_strides[3], const int64_t shape[3], uint64_t a_offset, uint64_t b_offset, void *stream);
 
+/* relabel_vol(vol, label_map) of syconn/extraction/block_processing_C.pyx:161-170 for dense label maps: every label l with
+ * 0 < l < lut_len becomes lut_dev[l], other labels stay (the marker clean-up of _object_segmentation_thread,
+ * object_extraction_steps.py:325-343).  In place, any strides. */
+int syk_label_map(uint32_t *labels_dev, const int64_t shape[3], const int64_t strides[3], const uint32_t *lut_dev, uint64_t lut_len,
+                  void *stream);
+/* Binary morphology of a whole thresholded volume (row f4): apply_morphological_operations(vol, morph_ops,
+ * mop_kwargs=dict(structure=struct)) of syconn/proc/image.py:485-507 as called on the 0/1 volume by
+ * _object_segmentation_thread (object_extraction_steps.py:312-358), i.e. _multi_mop_findobjects (image.py:358-437) with the
+ * single object 1: every op runs inside the bounding box of the current foreground -- dilation / closing on the box padded
+ * by `iterations` zeros and cropped back, erosion / opening on the box itself, border_value 0 -- so the volume is
+ * bit-identical to the reference's.  vol_dev [X,Y,Z] (any dense or strided view, elem_bytes 1/2/4/8) is updated in place and
+ * must hold only 0 and 1 (SYK_EINVAL otherwise: multi-label overlays are not a device path).  structure_host: C-ordered
+ * uint8 [sx,sy,sz], odd extents, point-symmetric (e.g. get_aniso_struct, image.py:522-539).  ops_host[i]: 0 binary_erosion,
+ * 1 binary_dilation, 2 binary_opening, 3 binary_closing, iters_host[i] its iterations (runs of equal ops merged by the
+ * caller like _count_subsequent_mops).  Synchronises `stream` once per op (bounding box). */
+int syk_binary_morph_ops(void *vol_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                         const uint8_t *structure_host, const int64_t structure_shape[3], const int32_t *ops_host,
+                         const int32_t *iters_host, int n_ops, void *stream);
+
 /* ---- storage codec (row f3; host code, no GPU needed) ----------------------------------------------------- */
 /* LZ4 block format, the codec behind the reference's CompressedStorage / VoxelStorageDyn values
  * (python-lz4 `lz4.block.compress/decompress`, syconn/handler/compression.py:83-127, backend/storage.py:52-93).

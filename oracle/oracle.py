@@ -368,6 +368,86 @@ def close_contact_sites(contacts, bb_dc, n_closings, cs_dilation, use_scipy=Fals
     return contacts
 
 
+# ------------------------------------------------------------------------------------------ organelle morphology (f4)
+def get_aniso_struct(scaling):
+    """syconn/proc/image.py:522-539: 5 x 5 x 3 element -- single centre voxels above and below, and in the middle plane
+    the result of ``scaling[2] // scaling[0]`` cross dilations of the centre pixel of a 5 x 5 array."""
+    import scipy.ndimage
+    aniso = scaling[2] // scaling[0]
+    assert scaling[1] // scaling[0] == 1 and aniso >= 1
+    centre = np.zeros((5, 5))
+    centre[2, 2] = 1
+    disc = scipy.ndimage.binary_dilation(centre, iterations=int(aniso))
+    return np.stack([centre, disc.astype(np.float64), centre], axis=2)
+
+
+def apply_morphological_operations(vol, morph_ops, structure=None):
+    """syconn/proc/image.py:485-507 with _count_subsequent_mops (:510-519) and _multi_mop_findobjects (:358-437), restated
+    for the ops the organelle worker uses (binary erosion / dilation / opening / closing; scipy.ndimage is the third-party
+    home of the arithmetic): runs of equal ops become one call with that many iterations; every call goes object by
+    object through ``find_objects`` boxes -- dilation / closing on the box zero-padded by the iteration count and cropped
+    back, writing the object's own voxels and background only; erosion / opening on the box itself, writing the object's
+    own voxels only.  In place, like the reference."""
+    import scipy.ndimage
+    runs = []
+    for name in morph_ops:
+        if runs and runs[-1][0] == name:
+            runs[-1][1] += 1
+        else:
+            runs.append([name, 1])
+    kw = {} if structure is None else {"structure": structure}
+    for name, n in runs:
+        func = getattr(scipy.ndimage, name)
+        grows = ("closing" in name) or ("dilation" in name)
+        shrinks = ("erosion" in name) or ("opening" in name)
+        assert grows != shrinks, name
+        boxes = scipy.ndimage.find_objects(vol)
+        for ix in np.unique(vol[vol != 0]):
+            box = boxes[int(ix) - 1]
+            sub = vol[box]
+            if grows:
+                sub = np.pad(sub, n)
+            own = (sub == ix).astype(np.int32)
+            res = func(own, iterations=n, **kw)
+            if grows:
+                inner = (slice(n, -n),) * 3
+                res, own, sub = res[inner], own[inner], sub[inner]
+                target = (own == 1) | (sub == 0)
+            else:
+                target = own == 1
+            vol[box][target] = res[target] * ix
+    return vol
+
+
+def watershed_seeds(tmp_data, morph_ops, structure, min_size):
+    """syconn/extraction/object_extraction_steps.py:313-343, restated: the mask after the ops before the first erosion, and the
+    markers = scipy.ndimage.label of the mask after the remaining ops, cleaned of markers below ``min_size`` voxels with
+    the freed ids refilled from the largest kept ids.  (This stretch of the worker cannot be run on its own -- it sits
+    between KnossosDataset I/O and the vigra / skimage watershed -- so it is pinned by restatement only.)"""
+    import scipy.ndimage
+    first = morph_ops.index("binary_erosion")
+    mask = apply_morphological_operations(tmp_data.copy(), morph_ops[:first], structure)
+    markers = apply_morphological_operations(mask.copy(), morph_ops[first:], structure)
+    markers = scipy.ndimage.label(markers)[0].astype(np.uint32)
+    if min_size > 1:
+        ixs, cnt = np.unique(markers, return_counts=True)
+        m = (ixs != 0) & (cnt < min_size)
+        ixs_del = np.sort(ixs[m])
+        ixs_keep = np.sort(ixs[~m])
+        label_m = {ix_del: 0 for ix_del in ixs_del}
+        ii = len(ixs_keep) - 1
+        for ix_del in ixs_del:
+            if (ix_del > ixs_keep[ii]) or (ixs_keep[ii] == 0) or (ii < 0):
+                break
+            label_m[ixs_keep[ii]] = ix_del
+            ii -= 1
+        out = markers.copy()
+        for k, v in label_m.items():  # relabel_vol (block_processing_C.pyx:161-170): one look-up per voxel, no chaining
+            out[markers == k] = v
+        markers = out
+    return mask, markers
+
+
 def merge_prop_dicts(prop_dicts, offset=None):
     """syconn/proc/sd_proc.py:1248-1273: rc overwritten by later chunks, bboxes appended, sizes summed."""
     tot_rc, tot_bb, tot_size = prop_dicts[0]

@@ -35,7 +35,7 @@ EXPORTS = [
     "syk_detect_contact_partners_host", "syk_find_object_properties_cs_64bit_host",
     "syk_close_contacts", "syk_close_contacts_host",
     "syk_lz4_compress_bound", "syk_lz4_compress_block", "syk_lz4_decompress_block",
-    "syk_label_components", "syk_label_overlap_pairs",
+    "syk_label_components", "syk_label_overlap_pairs", "syk_binary_morph_ops", "syk_label_map",
     "syk_table_append_records_min_vx", "syk_pairs_append_min_vx", "syk_pairs_attach_size",
 ]
 
@@ -117,6 +117,8 @@ def load():
     L.syk_lz4_decompress_block.argtypes = [C.c_char_p, u64, vp, u64, u64p]
     L.syk_label_components.argtypes = [vp, ci, i64p, i64p, u64, vp, i64p, u64p, vp]
     L.syk_label_overlap_pairs.argtypes = [vp, vp, i64p, vp, i64p, i64p, u64, u64, vp]
+    L.syk_binary_morph_ops.argtypes = [vp, ci, i64p, i64p, C.c_char_p, i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), ci, vp]
+    L.syk_label_map.argtypes = [vp, i64p, i64p, vp, u64, vp]
     L.syk_free.argtypes = [vp]
     L.syk_free.restype = None
     for name in EXPORTS:

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, os.environ.get("SYK_LIB_NAME", "libsyk.so"))
-SOURCES = ["syk_table.cu", "syk_props.cu", "syk_cs.cu", "syk_morph.cu", "syk_host.cu", "syk_lz4.cu", "syk_ccl.cu"]
+SOURCES = ["syk_table.cu", "syk_props.cu", "syk_cs.cu", "syk_morph.cu", "syk_host.cu", "syk_lz4.cu", "syk_ccl.cu", "syk_morph_vol.cu"]
 HEADERS = ["syk_common.cuh", "syk_cs_fast.cuh", "syk_cs_march.cuh", os.path.join("..", "..", "include", "syk.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",

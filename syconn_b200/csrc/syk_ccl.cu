@@ -295,7 +295,46 @@ __global__ void k_label_pairs(const unsigned *__restrict__ a, long long a0, long
     }
 }
 
+__global__ void k_label_map(unsigned *__restrict__ lab, long long n0, long long n1, long long n2, long long s0, long long s1, long long s2,
+                            const unsigned *__restrict__ lut, unsigned long long lut_len) {
+    const long long total = n0 * n1 * n2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long w = i % n2, q = i / n2, v = q % n1, u = q / n1;
+        unsigned *p = lab + u * s0 + v * s1 + w * s2;
+        const unsigned x = *p;
+        if (x != 0u && x < lut_len) {
+            const unsigned y = lut[x];
+            if (y != x) *p = y;
+        }
+    }
+}
+
 }  // namespace
+
+SYK_API int syk_label_map(uint32_t *labels_dev, const int64_t shape[3], const int64_t strides[3], const uint32_t *lut_dev,
+                          uint64_t lut_len, void *stream) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(shape && strides, "NULL geometry argument");
+    const long long total = shape[0] * shape[1] * shape[2];
+    if (total == 0 || lut_len == 0) return SYK_OK;
+    SYK_CHECK_ARG(labels_dev && lut_dev, "NULL buffer");
+    int ax[3] = {0, 1, 2};  // iterate in memory order
+    auto key = [&](int a) { return strides[a] < 0 ? -strides[a] : strides[a]; };
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j)
+            if (key(ax[j]) > key(ax[i])) {
+                const int t = ax[i];
+                ax[i] = ax[j];
+                ax[j] = t;
+            }
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_label_map<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(labels_dev, shape[ax[0]], shape[ax[1]], shape[ax[2]], strides[ax[0]],
+                                                                    strides[ax[1]], strides[ax[2]], lut_dev, lut_len);
+    SYK_CUDA(cudaGetLastError());
+    return SYK_OK;
+}
 
 SYK_API int syk_label_components(const void *vol_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
                                  uint64_t threshold, uint32_t *labels_dev, const int64_t label_strides[3], uint64_t *n_labels_host,

@@ -282,3 +282,28 @@ def label_overlap_pairs(pairs, a, b, a_offset=0, b_offset=0, stream=None):
     assert tuple(a.shape) == tuple(b.shape) and a.dtype == torch.int32 and b.dtype == torch.int32
     check(_lib.load().syk_label_overlap_pairs(pairs.h, a.data_ptr(), i64(_strides(a)), b.data_ptr(), i64(_strides(b)), i64(a.shape),
                                               int(a_offset), int(b_offset), _stream_ptr(stream)))
+
+
+MORPH_OPS = {"binary_erosion": 0, "binary_dilation": 1, "binary_opening": 2, "binary_closing": 3}
+
+
+def binary_morph_ops(vol, ops, iterations, structure, stream=None):
+    """syk_binary_morph_ops: the reference's per-object morphology (``proc/image.py:358-437``) on a 0/1 CUDA volume
+    [X,Y,Z], in place.  ``ops``: names from MORPH_OPS (or their codes), ``iterations`` one count per op, ``structure`` a
+    point-symmetric 3-D array-like with odd extents."""
+    st = np.ascontiguousarray(np.asarray(structure) != 0, dtype=np.uint8)
+    assert st.ndim == 3, "3-D structuring element expected"
+    codes = (C.c_int32 * len(ops))(*[MORPH_OPS[o] if isinstance(o, str) else int(o) for o in ops])
+    its = (C.c_int32 * len(ops))(*[int(i) for i in iterations])
+    check(_lib.load().syk_binary_morph_ops(vol.data_ptr(), vol.element_size(), i64(vol.shape), i64(_strides(vol)), st.tobytes(),
+                                           i64(st.shape), codes, its, len(ops), _stream_ptr(stream)))
+    return vol
+
+
+def label_map(labels, lut, stream=None):
+    """syk_label_map: int32 label tensor [X,Y,Z] mapped in place through the dense int32 table ``lut`` (labels >= len(lut)
+    and 0 stay)."""
+    assert labels.dtype == torch.int32 and lut.dtype == torch.int32 and lut.is_cuda and lut.is_contiguous()
+    check(_lib.load().syk_label_map(labels.data_ptr(), i64(labels.shape), i64(_strides(labels)), lut.data_ptr(), lut.numel(),
+                                    _stream_ptr(stream)))
+    return labels

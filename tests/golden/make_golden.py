@@ -147,6 +147,57 @@ def main():
     np.savez_compressed(os.path.join(OUT, "hotpath_golden.npz"), **out)
     print("wrote", len(out), "arrays,", os.path.getsize(os.path.join(OUT, "hotpath_golden.npz")), "bytes")
     main64(fop, gp, rng)
+    main_morph()
+
+
+MORPH_CASES = {  # op lists of syconn/handler/config.yml:130-140 plus single ops / repeated runs
+    "mi": ["binary_opening", "binary_closing"] + ["binary_erosion"] * 4,
+    "sj": ["binary_opening", "binary_closing", "binary_erosion"],
+    "er": ["binary_dilation"] * 3 + ["binary_erosion"] * 3,
+    "closing2": ["binary_closing", "binary_closing"],
+    "dilation1": ["binary_dilation"],
+    "opening3": ["binary_opening"] * 3,
+}
+
+
+def morph_input(case_index, density, scaling):
+    """0/1 volume of a golden morphology case: random voxels thickened into blobs, empty margin on one side."""
+    import scipy.ndimage
+    rng = np.random.default_rng(100 + case_index)
+    v = rng.random((30, 27, 22)) < density * 0.004
+    v = scipy.ndimage.binary_dilation(v, iterations=3)
+    v[:2] = False
+    return v.astype(np.uint8)
+
+
+def main_morph():
+    """apply_morphological_operations / get_aniso_struct of the reference's syconn/proc/image.py (imported under a stub
+    ``syconn.proc`` package) -> morph_golden.npz"""
+    import logging
+    proc = types.ModuleType("syconn.proc")
+    proc.__path__ = []
+    proc.log_proc = logging.getLogger("reference")
+    sys.modules["syconn.proc"] = proc
+    spec = importlib.util.spec_from_file_location("syconn.proc.image", os.path.join(REF, "syconn/proc/image.py"))
+    img = importlib.util.module_from_spec(spec)
+    sys.modules["syconn.proc.image"] = img
+    spec.loader.exec_module(img)
+    out = {}
+    scalings = [(10, 10, 20), (9, 9, 20), (10, 10, 10), (10, 10, 45)]
+    for sc in scalings:
+        out["struct_%d_%d_%d" % sc] = img.get_aniso_struct(np.array(sc)).astype(np.uint8)
+    i = 0
+    for name, ops in MORPH_CASES.items():
+        for density, sc in ((1.0, scalings[0]), (2.5, scalings[1]), (5.0, scalings[2])):
+            v = morph_input(i, density, sc)
+            st = img.get_aniso_struct(np.array(sc))
+            res = img.apply_morphological_operations(v.copy(), list(ops), mop_kwargs=dict(structure=st))
+            out["in_%s_%d" % (name, i)] = np.packbits(v)
+            out["out_%s_%d" % (name, i)] = np.packbits(res)
+            out["sc_%s_%d" % (name, i)] = np.array(sc)
+            i += 1
+    np.savez_compressed(os.path.join(OUT, "morph_golden.npz"), **out)
+    print("wrote", len(out), "arrays,", os.path.getsize(os.path.join(OUT, "morph_golden.npz")), "bytes")
 
 
 def pair_props_arrays(dicts):

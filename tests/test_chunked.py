@@ -515,3 +515,28 @@ def test_device_pipeline_to_storage_files(tmp_path):
             assert dict(zip(a["mapping_ids"], a["mapping_ratios"])) == {c: n / sz[k] for c, n in maps.get(k, {}).items()}
             seen.add(k)
     assert seen == set(sz) and len(seen) > 50
+
+
+def test_seed_cleanup_table_matches_oracle_loop():
+    """Host logic of the marker clean-up against the loop of object_extraction_steps.py:325-343 restated on np.unique output."""
+    from syconn_b200.extraction.object_extraction_steps import seed_cleanup_table
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        n = int(rng.integers(1, 30))
+        sizes = np.concatenate([[0], rng.integers(1, 12, n)])
+        min_size = int(rng.integers(2, 12))
+        vol = np.repeat(np.arange(n + 1), np.concatenate([[5 if trial % 2 else 0], sizes[1:]])).astype(np.uint8)
+        vol = vol.reshape(1, 1, -1)
+        ixs, cnt = np.unique(vol, return_counts=True)
+        m = (ixs != 0) & (cnt < min_size)
+        dels, keep = np.sort(ixs[m]), np.sort(ixs[~m])
+        want = {int(d): 0 for d in dels}
+        ii = len(keep) - 1
+        for d in dels:
+            if len(keep) == 0 or (d > keep[ii]) or (keep[ii] == 0) or (ii < 0):
+                break
+            want[int(keep[ii])] = int(d)
+            ii -= 1
+        table = seed_cleanup_table(sizes, min_size)
+        for lab in range(1, n + 1):
+            assert table[lab] == want.get(lab, lab), (trial, lab)

@@ -193,3 +193,33 @@ def test_oracle_closing_vs_scipy():
     bb = oracle.find_object_properties(cs)[1]
     a = oracle.close_contact_sites(cs.copy(), bb, 3, 2, use_scipy=True)
     assert np.array_equal(a, oracle.close_contact_sites(cs.copy(), bb, 3, 2)) and (a != cs).any()
+
+
+def _morph_golden_cases():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "morph_golden.npz"))
+    shape = (30, 27, 22)
+    n = int(np.prod(shape))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_cases", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    src = open(spec.origin).read()
+    ns = {}
+    exec(src[src.index("MORPH_CASES = {"):src.index("def morph_input")], ns)  # the op lists, without importing the script
+    for key in g.files:
+        if key.startswith("in_"):
+            name = key[3:key.rindex("_")]
+            vin = np.unpackbits(g[key])[:n].reshape(shape).astype(np.uint8)
+            vout = np.unpackbits(g["out_" + key[3:]])[:n].reshape(shape).astype(np.uint8)
+            yield key[3:], ns["MORPH_CASES"][name], tuple(int(x) for x in g["sc_" + key[3:]]), vin, vout, g
+
+
+def test_oracle_morphology_vs_golden():
+    """Row f4: get_aniso_struct / apply_morphological_operations restatements against the reference's outputs."""
+    seen = 0
+    for tag, ops, scaling, vin, vout, g in _morph_golden_cases():
+        st = oracle.get_aniso_struct(np.array(scaling))
+        assert np.array_equal(st.astype(np.uint8), g["struct_%d_%d_%d" % scaling]), scaling
+        got = oracle.apply_morphological_operations(vin.copy(), ops, st)
+        assert np.array_equal(got, vout), tag
+        seen += 1
+    assert seen == 18
