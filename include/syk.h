@@ -110,6 +110,9 @@ int syk_records_bucket(const syk_record_t *records_dev, uint64_t n, uint32_t n_o
                        uint64_t *counts_dev, void *stream);
 int syk_records_decode_rep(syk_record_t *records_dev, uint64_t n, const syk_chunk_geom_t *geoms_host, uint32_t n_geoms,
                            void *stream);
+/* Sort n device records by ascending id (radix sort; the contact-site worker's per-id loop, cs_extraction_steps.py:440,
+ * runs over the keys of a dict built in ascending id order).  Ids are unique in a table export, so the order is total. */
+int syk_records_sort_by_id(syk_record_t *records_dev, uint64_t n, void *stream);
 
 /* syk_table_append_records with the worker's small-object drop (syconn/proc/sd_proc.py:650-661, :667-680): an object that
  * lies purely inside the chunk `geom_host` (its box touches none of the six faces) and has fewer than min_vx voxels is not
@@ -175,6 +178,15 @@ int syk_extract_cs_syntype(syk_table_t *cs_t, const void *cs_dev, int elem_bytes
                            const uint8_t *asym_dev, const int64_t asym_strides[3], const uint8_t *sym_dev,
                            const int64_t sym_strides[3], const int64_t origin[3], uint32_t chunk_seq, syk_synvox_t *vox_dev,
                            uint64_t max_vox, uint64_t *counter_dev, void *stream);
+
+/* Same, and the props of the synaptic part of every contact -- extract_cs_syntype's second return value
+ * ([rc, bb, size] over the voxels with syn_mask != 0, block_processing_C.pyx:117-137) -- accumulated in syn_t by the same
+ * pass (NULL: like syk_extract_cs_syntype).  Fewer than 2^31 voxels per call when syn_t is given. */
+int syk_extract_cs_syntype_props(syk_table_t *cs_t, syk_table_t *syn_t, const void *cs_dev, int elem_bytes, const int64_t shape[3],
+                                 const int64_t cs_strides[3], const uint8_t *syn_dev, const int64_t syn_strides[3],
+                                 const uint8_t *asym_dev, const int64_t asym_strides[3], const uint8_t *sym_dev,
+                                 const int64_t sym_strides[3], const int64_t origin[3], uint32_t chunk_seq, syk_synvox_t *vox_dev,
+                                 uint64_t max_vox, uint64_t *counter_dev, void *stream);
 
 /* detect_contact_partners(seg_arr, edge_arr, offset) -- syconn/extraction/find_object_properties.py:371-421, the
  * numba twin of process_block_nonzero behind detect_cs_64bit (:347-368).  Same window histogram; ties go to the id met
@@ -243,6 +255,11 @@ int syk_detect_contact_partners_host(const void *edges_host, int edge_bytes, con
  * contact volume (C = 2).  records_out[i].id is internal; partners_out[2 i .. 2 i + 1] are the pair's ids. */
 int syk_find_object_properties_cs_64bit_host(const uint64_t *cs_host, const int64_t shape[3], const int64_t strides[4],
                                              syk_record_t **records_out, uint64_t **partners_out, uint64_t *n_out);
+/* Same with the boxes taken from DEVICE records (a table export of find_object_properties(contacts) in volume-local
+ * coordinates, sorted by id with syk_records_sort_by_id): box planning runs on the device, the call reads back 32 bytes and
+ * does not wait for its kernels.  Processing order = record order. */
+int syk_close_contacts_records(void *cs_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                               const syk_record_t *records_dev, uint64_t n_ids, int n_closings, int n_dilations, void *stream);
 /* host-buffer form of syk_close_contacts: cs_host (dense block) is updated in place */
 int syk_close_contacts_host(void *cs_host, int elem_bytes, const int64_t shape[3], const int64_t strides[3], const uint64_t *ids_host,
                             const int32_t *bbox_host, uint64_t n_ids, int n_closings, int n_dilations);

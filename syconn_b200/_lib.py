@@ -33,9 +33,9 @@ EXPORTS = [
     "syk_process_block_nonzero_host", "syk_extract_cs_syntype_host", "syk_detect_seg_boundaries_host", "syk_free",
     "syk_detect_contact_partners", "syk_cs64_unpack", "syk_dense_relabel",
     "syk_detect_contact_partners_host", "syk_find_object_properties_cs_64bit_host",
-    "syk_close_contacts", "syk_close_contacts_host",
+    "syk_close_contacts", "syk_close_contacts_host", "syk_close_contacts_records",
     "syk_lz4_compress_bound", "syk_lz4_compress_block", "syk_lz4_decompress_block",
-    "syk_label_components", "syk_label_overlap_pairs", "syk_binary_morph_ops", "syk_label_map",
+    "syk_label_components", "syk_label_overlap_pairs", "syk_binary_morph_ops", "syk_label_map", "syk_extract_cs_syntype_props", "syk_records_sort_by_id",
     "syk_table_append_records_min_vx", "syk_pairs_append_min_vx", "syk_pairs_attach_size",
 ]
 
@@ -94,6 +94,8 @@ def load():
     L.syk_process_block_nonzero.argtypes = [vp, ci, i64p, vp, ci, i64p, i64p, i32p, vp, i64p, vp]
     L.syk_detect_cs.argtypes = [vp, ci, i64p, i64p, i32p, vp, i64p, vp]
     L.syk_extract_cs_syntype.argtypes = [vp, vp, ci, i64p, i64p, vp, i64p, vp, i64p, vp, i64p, i64p, u32, vp, u64, vp, vp]
+    L.syk_extract_cs_syntype_props.argtypes = [vp, vp, vp, ci, i64p, i64p, vp, i64p, vp, i64p, vp, i64p, i64p, u32, vp, u64, vp, vp]
+    L.syk_records_sort_by_id.argtypes = [vp, u64, vp]
     L.syk_extract_cs_syntype_host.argtypes = [vp, ci, i64p, i64p, vp, i64p, vp, i64p, vp, i64p, C.POINTER(vp), u64p,
                                               C.POINTER(vp), u64p]
     L.syk_synth_labels.argtypes = [vp, ci, i64p, i64p, i64p, i32p, C.c_int32, u64, ci, ci, vp]
@@ -118,6 +120,7 @@ def load():
     L.syk_label_components.argtypes = [vp, ci, i64p, i64p, u64, vp, i64p, u64p, vp]
     L.syk_label_overlap_pairs.argtypes = [vp, vp, i64p, vp, i64p, i64p, u64, u64, vp]
     L.syk_binary_morph_ops.argtypes = [vp, ci, i64p, i64p, C.c_char_p, i64p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), ci, vp]
+    L.syk_close_contacts_records.argtypes = [vp, ci, i64p, i64p, vp, u64, ci, ci, vp]
     L.syk_label_map.argtypes = [vp, i64p, i64p, vp, u64, vp]
     L.syk_free.argtypes = [vp]
     L.syk_free.restype = None

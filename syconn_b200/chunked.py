@@ -275,23 +275,19 @@ class ExtractionPipeline:
         full_shape = tuple(self.cs_out.shape)
         self.t_cs.clear()
         dev.find_object_properties(self.t_cs, self.cs_out)
-        rec = dev.records_numpy(self.t_cs.export(dev.geoms([[0, 0, 0]], [list(full_shape)])))   # host round trip: box list
-        rec = rec[np.argsort(rec["id"])]
-        if len(rec):
-            dev.close_contacts(self.cs_out, rec["id"].copy(), np.stack([rec["bb_min"], rec["bb_max"]], axis=1).astype(np.int32),
-                               overlap, self.cs_dilation)
+        rec = self.t_cs.export(dev.geoms([[0, 0, 0]], [list(full_shape)]), sort=True)   # ascending ids; stays on the device
+        if rec.shape[0]:
+            dev.close_contacts_records(self.cs_out, rec, overlap, self.cs_dilation)
         crop = tuple(slice(overlap, n - overlap) for n in full_shape)
         cs_c = self.cs_out[crop]
         sj, asym, sym = (m[crop] for m in syn_masks)
         self.t_cs.clear()
-        vox = dev.extract_cs_syntype(self.t_cs, cs_c, sj, asym, sym, origin=offset, chunk_seq=seq)
-        self._append(self.t_cs, 1, self.logs["cs"], offset, cs_c.shape)
-        syn_seg = torch.where(sj != 0, cs_c, torch.zeros_like(cs_c))                            # :476
         self.t_syn.clear()
-        dev.find_object_properties(self.t_syn, syn_seg, origin=offset, chunk_seq=seq)
+        vox = dev.extract_cs_syntype(self.t_cs, cs_c, sj, asym, sym, origin=offset, chunk_seq=seq, syn_table=self.t_syn)
+        self._append(self.t_cs, 1, self.logs["cs"], offset, cs_c.shape)
         self._append(self.t_syn, self.kinds.index("syn"), self.logs["syn"], offset, cs_c.shape)
         self.syn_voxels.append((seq, tuple(offset), tuple(cs_c.shape), vox))
-        self.launches += 3 + 2 + 4 + 3 + 1   # detect_cs tiers, props + export, morphology, extract_cs_syntype, syn props
+        self.launches += 3 + 2 + 4 + 4 + 3 + 1   # detect_cs tiers, props + export, sort, morphology, extract_cs_syntype (+ syn props), export
 
     def _cs_buffer(self, cell_halo):
         """Contact volume of one chunk, laid out like the input (same fastest axis) with the row pitch padded to a multiple

@@ -639,7 +639,9 @@ __global__ void k_syn_voxels(const void *__restrict__ cs, int elem_bytes, long l
                              long long s1, long long s2, const unsigned char *__restrict__ asym, long long a0, long long a1,
                              long long a2, const unsigned char *__restrict__ sym, long long y0, long long y1, long long y2,
                              long long l0, long long l1, long long l2,  // linear-index coefficients of the internal axes
-                             syk_synvox_t *__restrict__ out, unsigned long long max_out, unsigned long long *counter) {
+                             syk_synvox_t *__restrict__ out, unsigned long long max_out, unsigned long long *counter,
+                             TableView syn_t, int p0, int p1, int p2,  // logical axis of the internal axes u, v, w
+                             long long o0, long long o1, long long o2, unsigned chunk_seq) {
     const long long total = n0 * n1 * n2;
     const unsigned lane = threadIdx.x & 31;
     const long long start = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane;
@@ -648,10 +650,17 @@ __global__ void k_syn_voxels(const void *__restrict__ cs, int elem_bytes, long l
         unsigned long long key = 0ull;
         long long u = 0, v = 0, w = 0;
         if (i < total) {
-            w = i % n2;
-            const long long r = i / n2;
-            v = r % n1;
-            u = r / n1;
+            if (total < (1ll << 32)) {  // the usual chunk: 32-bit divisions (the 64-bit ones dominated this pass)
+                const unsigned iu = (unsigned)i, r = iu / (unsigned)n2;
+                w = iu - r * (unsigned)n2;
+                u = r / (unsigned)n1;
+                v = r - (unsigned)u * (unsigned)n1;
+            } else {
+                w = i % n2;
+                const long long r = i / n2;
+                v = r % n1;
+                u = r / n1;
+            }
             const long long ci = u * c0 + v * c1 + w * c2;
             key = elem_bytes == 8 ? __ldg((const unsigned long long *)cs + ci) : (unsigned long long)__ldg((const unsigned *)cs + ci);
         }
@@ -672,20 +681,36 @@ __global__ void k_syn_voxels(const void *__restrict__ cs, int elem_bytes, long l
                 t._pad = 0;
                 out[pos] = t;
             }
+            if (syn_t.slots) {  // props of the synaptic part of the contact (block_processing_C.pyx:117-137), one update per id and warp
+                const unsigned peers = __match_any_sync(m, key);
+                const long long lin = u * l0 + v * l1 + w * l2;
+                long long c[3];  // logical coordinates
+                c[p0] = u, c[p1] = v, c[p2] = w;
+                // voxels per call < 2^31 (checked on the host): 32-bit warp reductions
+                const int mn0 = __reduce_min_sync(peers, (int)c[0]), mn1 = __reduce_min_sync(peers, (int)c[1]), mn2 = __reduce_min_sync(peers, (int)c[2]);
+                const int mx0 = __reduce_max_sync(peers, (int)c[0]), mx1 = __reduce_max_sync(peers, (int)c[1]), mx2 = __reduce_max_sync(peers, (int)c[2]);
+                const unsigned first = __reduce_min_sync(peers, (unsigned)lin);
+                if ((unsigned)(__ffs(peers) - 1) == lane) {
+                    const unsigned long long rep_key = ((unsigned long long)chunk_seq << 40) | (SYK_REP_MASK - (unsigned long long)first);
+                    syk_table_update(syn_t, key, (unsigned long long)__popc(peers), rep_key, (int)(mn0 + o0), (int)(mn1 + o1), (int)(mn2 + o2),
+                                     (int)(mx0 + 1 + o0), (int)(mx1 + 1 + o1), (int)(mx2 + 1 + o2));
+                }
+            }
         }
     }
 }
 
-SYK_API int syk_extract_cs_syntype(syk_table_t *cs_t, const void *cs_dev, int elem_bytes, const int64_t shape[3],
-                                   const int64_t cs_strides[3], const uint8_t *syn_dev, const int64_t syn_strides[3],
-                                   const uint8_t *asym_dev, const int64_t asym_strides[3], const uint8_t *sym_dev,
-                                   const int64_t sym_strides[3], const int64_t origin[3], uint32_t chunk_seq, syk_synvox_t *vox_dev,
-                                   uint64_t max_vox, uint64_t *counter_dev, void *stream) {
+SYK_API int syk_extract_cs_syntype_props(syk_table_t *cs_t, syk_table_t *syn_t, const void *cs_dev, int elem_bytes, const int64_t shape[3],
+                                         const int64_t cs_strides[3], const uint8_t *syn_dev, const int64_t syn_strides[3],
+                                         const uint8_t *asym_dev, const int64_t asym_strides[3], const uint8_t *sym_dev,
+                                         const int64_t sym_strides[3], const int64_t origin[3], uint32_t chunk_seq, syk_synvox_t *vox_dev,
+                                         uint64_t max_vox, uint64_t *counter_dev, void *stream) {
     int rc = syk_require_device();
     if (rc) return rc;
     SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
     SYK_CHECK_ARG(shape && cs_strides && syn_strides && asym_strides && sym_strides, "NULL geometry argument");
     SYK_CHECK_ARG(counter_dev != nullptr && (vox_dev != nullptr || max_vox == 0), "NULL output");
+    SYK_CHECK_ARG(!syn_t || origin, "the synaptic props need the block origin");
     if (cs_t) {
         rc = syk_find_object_properties(cs_t, cs_dev, elem_bytes, shape, cs_strides, origin, chunk_seq, stream);
         if (rc) return rc;
@@ -693,6 +718,7 @@ SYK_API int syk_extract_cs_syntype(syk_table_t *cs_t, const void *cs_dev, int el
     const long long total = shape[0] * shape[1] * shape[2];
     if (total == 0) return SYK_OK;
     SYK_CHECK_ARG(cs_dev && syn_dev && asym_dev && sym_dev, "NULL buffer");
+    SYK_CHECK_ARG(!syn_t || total < (1ll << 31), "more than 2^31 voxels per call");
     int ax[3] = {0, 1, 2};  // internal order: largest |cs stride| first, lanes along the smallest
     auto key = [&](int a) { return cs_strides[a] < 0 ? -cs_strides[a] : cs_strides[a]; };
     for (int i = 0; i < 3; ++i)
@@ -709,9 +735,19 @@ SYK_API int syk_extract_cs_syntype(syk_table_t *cs_t, const void *cs_dev, int el
         cs_dev, elem_bytes, shape[ax[0]], shape[ax[1]], shape[ax[2]], cs_strides[ax[0]], cs_strides[ax[1]], cs_strides[ax[2]], syn_dev,
         syn_strides[ax[0]], syn_strides[ax[1]], syn_strides[ax[2]], asym_dev, asym_strides[ax[0]], asym_strides[ax[1]],
         asym_strides[ax[2]], sym_dev, sym_strides[ax[0]], sym_strides[ax[1]], sym_strides[ax[2]], lin[ax[0]], lin[ax[1]], lin[ax[2]],
-        vox_dev, max_vox, (unsigned long long *)counter_dev);
+        vox_dev, max_vox, (unsigned long long *)counter_dev, view_of(syn_t), ax[0], ax[1], ax[2], origin ? origin[0] : 0,
+        origin ? origin[1] : 0, origin ? origin[2] : 0, chunk_seq);
     SYK_CUDA(cudaGetLastError());
     return SYK_OK;
+}
+
+SYK_API int syk_extract_cs_syntype(syk_table_t *cs_t, const void *cs_dev, int elem_bytes, const int64_t shape[3],
+                                   const int64_t cs_strides[3], const uint8_t *syn_dev, const int64_t syn_strides[3],
+                                   const uint8_t *asym_dev, const int64_t asym_strides[3], const uint8_t *sym_dev,
+                                   const int64_t sym_strides[3], const int64_t origin[3], uint32_t chunk_seq, syk_synvox_t *vox_dev,
+                                   uint64_t max_vox, uint64_t *counter_dev, void *stream) {
+    return syk_extract_cs_syntype_props(cs_t, nullptr, cs_dev, elem_bytes, shape, cs_strides, syn_dev, syn_strides, asym_dev, asym_strides,
+                                        sym_dev, sym_strides, origin, chunk_seq, vox_dev, max_vox, counter_dev, stream);
 }
 
 SYK_API int syk_detect_seg_boundaries(const void *arr_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],

@@ -299,6 +299,107 @@ struct Scratch {  // stream-ordered device scratch, released when the call retur
     }
 };
 
+
+// large boxes in batches of at most BATCH_WORDS words per bit buffer (host-planned: CTA lists and word offsets)
+static int run_large_boxes(void *cs_dev, const MorphGeom &G, std::vector<MorphBox> &boxes, const std::vector<unsigned> &large,
+                           int n_closings, int n_dilations, unsigned *rankvol, cudaStream_t s) {
+    const unsigned long long BATCH_WORDS = getenv("SYK_MORPH_BATCH") ? strtoull(getenv("SYK_MORPH_BATCH"), nullptr, 10) : (1ull << 26);
+    size_t li = 0;
+    std::vector<MorphCta> ctas;
+    while (li < large.size()) {
+        unsigned long long total = 0;
+        ctas.clear();
+        size_t lj = li;
+        for (; lj < large.size(); ++lj) {
+            MorphBox &B = boxes[large[lj]];
+            const unsigned long long words = (unsigned long long)B.ext[0] * B.ext[1] * ((B.ext[2] + 31) / 32);
+            if (lj > li && total + words > BATCH_WORDS) break;
+            B.word0 = total;
+            total += words;
+            for (unsigned long long b = 0; b < words; b += MT) ctas.push_back(MorphCta{large[lj], (unsigned)b});
+        }
+        li = lj;
+        Scratch bx, ct, bufA, bufB;  // word0 is per batch: upload the boxes with this batch's offsets
+        SYK_CUDA(bx.alloc(boxes.size() * sizeof(MorphBox), s));
+        SYK_CUDA(cudaMemcpyAsync(bx.p, boxes.data(), boxes.size() * sizeof(MorphBox), cudaMemcpyHostToDevice, s));
+        SYK_CUDA(ct.alloc(ctas.size() * sizeof(MorphCta), s));
+        SYK_CUDA(cudaMemcpyAsync(ct.p, ctas.data(), ctas.size() * sizeof(MorphCta), cudaMemcpyHostToDevice, s));
+        SYK_CUDA(bufA.alloc(total * 4, s));
+        SYK_CUDA(bufB.alloc(total * 4, s));
+        const unsigned grid = (unsigned)ctas.size();
+        unsigned *a = (unsigned *)bufA.p, *b = (unsigned *)bufB.p;
+        const MorphBox *dbx = (const MorphBox *)bx.p;
+        const MorphCta *dct = (const MorphCta *)ct.p;
+        k_morph_build<<<grid, MT, 0, s>>>(cs_dev, G, dbx, dct, a);
+        for (int it = 0; it < 2 * n_closings + n_dilations; ++it) {
+            if (it >= n_closings && it < 2 * n_closings) k_morph_step<true><<<grid, MT, 0, s>>>(dbx, dct, a, b);
+            else k_morph_step<false><<<grid, MT, 0, s>>>(dbx, dct, a, b);
+            unsigned *t = a;
+            a = b;
+            b = t;
+        }
+        k_morph_apply<<<grid, MT, 0, s>>>(G, dbx, dct, a, rankvol);
+        SYK_CUDA(cudaGetLastError());
+        SYK_CUDA(cudaStreamSynchronize(s));  // the host vectors of this batch are reused by the next one
+    }
+    return SYK_OK;
+}
+
+// the six shared-memory size classes: lst[c] = device list of the cnt[c] boxes of class c
+static int run_small_boxes(void *cs_dev, const MorphGeom &G, const MorphBox *dbx, const unsigned *const lst[6], const size_t cnt[6],
+                           int n_closings, int n_dilations, unsigned *rk, int sms, cudaStream_t s) {
+#define SYK_MORPH_LAUNCH(c, WORDS, NT, WPR1, PER_SM)                                                                              \
+    if (cnt[c]) {                                                                                                                \
+        const unsigned long long n = cnt[c];                                                                                     \
+        const unsigned long long grid = n < (unsigned long long)sms * PER_SM ? n : (unsigned long long)sms * PER_SM;             \
+        k_morph_small<WORDS, NT, WPR1><<<(unsigned)grid, NT, 0, s>>>(cs_dev, G, dbx, lst[c], (unsigned)n, n_closings, n_dilations, \
+                                                                     rk);                                                        \
+    }
+    SYK_MORPH_LAUNCH(0, TINY_WORDS, 128, true, 64)
+    SYK_MORPH_LAUNCH(1, TINY_WORDS, 128, false, 64)
+    SYK_MORPH_LAUNCH(2, MID_WORDS, 256, true, 32)
+    SYK_MORPH_LAUNCH(3, MID_WORDS, 256, false, 32)
+    SYK_MORPH_LAUNCH(4, SMALL_WORDS, MT, true, 16)
+    SYK_MORPH_LAUNCH(5, SMALL_WORDS, MT, false, 16)
+#undef SYK_MORPH_LAUNCH
+    SYK_CUDA(cudaGetLastError());
+    return SYK_OK;
+}
+
+// device-side planning for syk_close_contacts_records: record i (ids ascending) -> MorphBox i, appended to the list of its
+// size class (class 6 = too large for shared memory).  err: a box outside the volume or id 0.
+__global__ void k_morph_plan(const syk_record_t *__restrict__ recs, unsigned n, MorphGeom G, int a0, int a1, int a2, int n_close,
+                             long long small_words, MorphBox *__restrict__ boxes, unsigned *__restrict__ lists,
+                             unsigned *__restrict__ counts, int *__restrict__ err) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const syk_record_t r = recs[i];
+    const int ax[3] = {a0, a1, a2};
+    MorphBox B;
+    B.id = r.id;
+    B.word0 = 0;
+    bool bad = r.id == 0ull;
+    for (int a = 0; a < 3; ++a) {
+        const long long mn = r.bb_min[ax[a]], mx = r.bb_max[ax[a]];
+        bad |= !(mn >= 0 && mn < mx && mx <= G.n[a]);
+        const long long lo = mn - n_close < 0 ? 0 : mn - n_close;
+        const long long hi = mx + n_close > G.n[a] ? G.n[a] : mx + n_close;
+        B.lo[a] = (int)lo;
+        B.ext[a] = (int)(hi - lo);
+        B.ilo[a] = (int)(mn - lo);
+        B.ihi[a] = (int)(mx - lo);
+    }
+    if (bad) {
+        *err = 1;
+        return;
+    }
+    boxes[i] = B;
+    const long long wpr = (B.ext[2] + 31) / 32;
+    const long long padded = (long long)(B.ext[0] + 2) * (B.ext[1] + 2) * wpr;
+    const int c = padded > small_words ? 6 : (padded <= TINY_WORDS ? 0 : padded <= MID_WORDS ? 2 : 4) + (wpr == 1 ? 0 : 1);
+    lists[(size_t)c * n + atomicAdd(&counts[c], 1u)] = i;
+}
+
 }  // namespace
 
 SYK_API int syk_close_contacts(void *cs_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3], const uint64_t *ids_host,
@@ -366,46 +467,8 @@ SYK_API int syk_close_contacts(void *cs_dev, int elem_bytes, const int64_t shape
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 
-    // large boxes in batches of at most BATCH_WORDS words per bit buffer
-    const unsigned long long BATCH_WORDS = getenv("SYK_MORPH_BATCH") ? strtoull(getenv("SYK_MORPH_BATCH"), nullptr, 10) : (1ull << 26);
-    size_t li = 0;
-    std::vector<MorphCta> ctas;
-    while (li < large.size()) {
-        unsigned long long total = 0;
-        ctas.clear();
-        size_t lj = li;
-        for (; lj < large.size(); ++lj) {
-            MorphBox &B = boxes[large[lj]];
-            const unsigned long long words = (unsigned long long)B.ext[0] * B.ext[1] * ((B.ext[2] + 31) / 32);
-            if (lj > li && total + words > BATCH_WORDS) break;
-            B.word0 = total;
-            total += words;
-            for (unsigned long long b = 0; b < words; b += MT) ctas.push_back(MorphCta{large[lj], (unsigned)b});
-        }
-        li = lj;
-        Scratch bx, ct, bufA, bufB;  // word0 is per batch: upload the boxes with this batch's offsets
-        SYK_CUDA(bx.alloc(boxes.size() * sizeof(MorphBox), s));
-        SYK_CUDA(cudaMemcpyAsync(bx.p, boxes.data(), boxes.size() * sizeof(MorphBox), cudaMemcpyHostToDevice, s));
-        SYK_CUDA(ct.alloc(ctas.size() * sizeof(MorphCta), s));
-        SYK_CUDA(cudaMemcpyAsync(ct.p, ctas.data(), ctas.size() * sizeof(MorphCta), cudaMemcpyHostToDevice, s));
-        SYK_CUDA(bufA.alloc(total * 4, s));
-        SYK_CUDA(bufB.alloc(total * 4, s));
-        const unsigned grid = (unsigned)ctas.size();
-        unsigned *a = (unsigned *)bufA.p, *b = (unsigned *)bufB.p;
-        const MorphBox *dbx = (const MorphBox *)bx.p;
-        const MorphCta *dct = (const MorphCta *)ct.p;
-        k_morph_build<<<grid, MT, 0, s>>>(cs_dev, G, dbx, dct, a);
-        for (int it = 0; it < 2 * n_closings + n_dilations; ++it) {
-            if (it >= n_closings && it < 2 * n_closings) k_morph_step<true><<<grid, MT, 0, s>>>(dbx, dct, a, b);
-            else k_morph_step<false><<<grid, MT, 0, s>>>(dbx, dct, a, b);
-            unsigned *t = a;
-            a = b;
-            b = t;
-        }
-        k_morph_apply<<<grid, MT, 0, s>>>(G, dbx, dct, a, (unsigned *)d_rank.p);
-        SYK_CUDA(cudaGetLastError());
-        SYK_CUDA(cudaStreamSynchronize(s));  // the host vectors of this batch are reused by the next one
-    }
+    rc = run_large_boxes(cs_dev, G, boxes, large, n_closings, n_dilations, (unsigned *)d_rank.p, s);
+    if (rc) return rc;
     SYK_CUDA(d_boxes.alloc(boxes.size() * sizeof(MorphBox), s));
     SYK_CUDA(cudaMemcpyAsync(d_boxes.p, boxes.data(), boxes.size() * sizeof(MorphBox), cudaMemcpyHostToDevice, s));
     {
@@ -418,28 +481,95 @@ SYK_API int syk_close_contacts(void *cs_dev, int elem_bytes, const int64_t shape
         if (!all.empty()) {
             SYK_CUDA(d_small.alloc(all.size() * sizeof(unsigned), s));
             SYK_CUDA(cudaMemcpyAsync(d_small.p, all.data(), all.size() * sizeof(unsigned), cudaMemcpyHostToDevice, s));
-            const unsigned *lst = (const unsigned *)d_small.p;
-            const MorphBox *dbx = (const MorphBox *)d_boxes.p;
-            unsigned *rk = (unsigned *)d_rank.p;
-#define SYK_MORPH_LAUNCH(c, WORDS, NT, WPR1, PER_SM)                                                                              \
-    if (first[c + 1] > first[c]) {                                                                                               \
-        const unsigned long long n = first[c + 1] - first[c];                                                                    \
-        const unsigned long long grid = n < (unsigned long long)sms * PER_SM ? n : (unsigned long long)sms * PER_SM;             \
-        k_morph_small<WORDS, NT, WPR1><<<(unsigned)grid, NT, 0, s>>>(cs_dev, G, dbx, lst + first[c], (unsigned)n, n_closings,     \
-                                                                     n_dilations, rk);                                           \
-    }
-            SYK_MORPH_LAUNCH(0, TINY_WORDS, 128, true, 64)
-            SYK_MORPH_LAUNCH(1, TINY_WORDS, 128, false, 64)
-            SYK_MORPH_LAUNCH(2, MID_WORDS, 256, true, 32)
-            SYK_MORPH_LAUNCH(3, MID_WORDS, 256, false, 32)
-            SYK_MORPH_LAUNCH(4, SMALL_WORDS, MT, true, 16)
-            SYK_MORPH_LAUNCH(5, SMALL_WORDS, MT, false, 16)
-#undef SYK_MORPH_LAUNCH
-            SYK_CUDA(cudaGetLastError());
+            const unsigned *lst[6];
+            size_t cnt[6];
+            for (int c = 0; c < 6; ++c) {
+                lst[c] = (const unsigned *)d_small.p + first[c];
+                cnt[c] = first[c + 1] - first[c];
+            }
+            rc = run_small_boxes(cs_dev, G, (const MorphBox *)d_boxes.p, lst, cnt, n_closings, n_dilations, (unsigned *)d_rank.p, sms, s);
+            if (rc) return rc;
         }
     }
     k_morph_final<<<sms * 8, MT, 0, s>>>(cs_dev, G, (const unsigned *)d_rank.p, (const MorphBox *)d_boxes.p);
     SYK_CUDA(cudaGetLastError());
     SYK_CUDA(cudaStreamSynchronize(s));  // `boxes` / `small` are pageable host memory owned by this call
+    return SYK_OK;
+}
+
+
+SYK_API int syk_close_contacts_records(void *cs_dev, int elem_bytes, const int64_t shape[3], const int64_t strides[3],
+                                       const syk_record_t *records_dev, uint64_t n_ids, int n_closings, int n_dilations, void *stream) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    SYK_CHECK_ARG(elem_bytes == 4 || elem_bytes == 8, "elem_bytes must be 4 or 8");
+    SYK_CHECK_ARG(shape && strides, "NULL argument");
+    SYK_CHECK_ARG(n_closings >= 0 && n_dilations >= 0 && n_closings <= 64 && n_dilations <= 64, "iterations must be in 0..64");
+    SYK_CHECK_ARG(n_ids < 0x7FFFFFFFull, "too many ids");
+    if (n_ids == 0 || (n_closings == 0 && n_dilations == 0)) return SYK_OK;
+    SYK_CHECK_ARG(cs_dev && records_dev, "NULL argument");
+    for (int a = 0; a < 3; ++a) SYK_CHECK_ARG(shape[a] > 0 && shape[a] < (1ll << 30), "bad shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    int ax[3] = {0, 1, 2};
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j)
+            if (llabs(strides[ax[j]]) > llabs(strides[ax[i]])) {
+                const int t = ax[i];
+                ax[i] = ax[j];
+                ax[j] = t;
+            }
+    MorphGeom G;
+    for (int a = 0; a < 3; ++a) {
+        G.st[a] = strides[ax[a]];
+        G.n[a] = (int)shape[ax[a]];
+    }
+    G.elem_bytes = elem_bytes;
+    long long small_words = SMALL_WORDS;
+    if (const char *e = getenv("SYK_MORPH_SMALL")) {
+        const long long v = atoll(e);
+        if (v >= 0 && v < small_words) small_words = v;
+    }
+    const unsigned n = (unsigned)n_ids;
+    const long long nvox = (long long)G.n[0] * G.n[1] * G.n[2];
+    Scratch d_boxes, d_lists, d_ctl, d_rank;
+    SYK_CUDA(d_boxes.alloc((size_t)n * sizeof(MorphBox), s));
+    SYK_CUDA(d_lists.alloc((size_t)n * 7 * sizeof(unsigned), s));
+    SYK_CUDA(d_ctl.alloc(8 * sizeof(unsigned), s));
+    SYK_CUDA(d_rank.alloc((size_t)nvox * 4, s));
+    SYK_CUDA(cudaMemsetAsync(d_ctl.p, 0, 8 * sizeof(unsigned), s));
+    SYK_CUDA(cudaMemsetAsync(d_rank.p, 0xFF, (size_t)nvox * 4, s));
+    unsigned *counts = (unsigned *)d_ctl.p;
+    k_morph_plan<<<(n + 255) / 256, 256, 0, s>>>(records_dev, n, G, ax[0], ax[1], ax[2], n_closings, small_words, (MorphBox *)d_boxes.p,
+                                                 (unsigned *)d_lists.p, counts, (int *)(counts + 7));
+    SYK_CUDA(cudaGetLastError());
+    unsigned h[8];
+    SYK_CUDA(cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, s));  // 32 bytes: the class sizes set the grids
+    SYK_CUDA(cudaStreamSynchronize(s));
+    if (h[7]) {
+        syk_set_error("invalid argument: a record with id 0 or a bounding box outside the volume");
+        return SYK_EINVAL;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (h[6]) {  // rare: boxes beyond the shared-memory classes are planned on the host
+        std::vector<MorphBox> boxes(n);
+        std::vector<unsigned> large(h[6]);
+        SYK_CUDA(cudaMemcpyAsync(boxes.data(), d_boxes.p, (size_t)n * sizeof(MorphBox), cudaMemcpyDeviceToHost, s));
+        SYK_CUDA(cudaMemcpyAsync(large.data(), (unsigned *)d_lists.p + (size_t)6 * n, (size_t)h[6] * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+        SYK_CUDA(cudaStreamSynchronize(s));
+        rc = run_large_boxes(cs_dev, G, boxes, large, n_closings, n_dilations, (unsigned *)d_rank.p, s);
+        if (rc) return rc;
+    }
+    const unsigned *lst[6];
+    size_t cnt[6];
+    for (int c = 0; c < 6; ++c) {  // the class lists live n entries apart
+        lst[c] = (const unsigned *)d_lists.p + (size_t)c * n;
+        cnt[c] = h[c];
+    }
+    rc = run_small_boxes(cs_dev, G, (const MorphBox *)d_boxes.p, lst, cnt, n_closings, n_dilations, (unsigned *)d_rank.p, sms, s);
+    if (rc) return rc;
+    k_morph_final<<<sms * 8, MT, 0, s>>>(cs_dev, G, (const unsigned *)d_rank.p, (const MorphBox *)d_boxes.p);
+    SYK_CUDA(cudaGetLastError());
     return SYK_OK;
 }

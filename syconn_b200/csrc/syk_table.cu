@@ -10,6 +10,8 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "syk_common.cuh"
 
 // ---- errors ---------------------------------------------------------------------------------------------------
@@ -757,5 +759,54 @@ SYK_API int syk_pairs_merge(syk_pairs_t *t, const syk_pair_t *pairs_dev, uint64_
     if (n == 0) return SYK_OK;
     k_pairs_merge<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(view_of(t), pairs_dev, n);
     SYK_CUDA(cudaGetLastError());
+    return SYK_OK;
+}
+
+
+// ---- records sorted by id (the contact-site worker walks its objects in ascending id order) ----------------
+__global__ void k_record_keys(const syk_record_t *__restrict__ recs, uint64_t n, unsigned long long *__restrict__ keys, unsigned *__restrict__ idx) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = recs[i].id;
+        idx[i] = (unsigned)i;
+    }
+}
+__global__ void k_record_gather(const syk_record_t *__restrict__ src, const unsigned *__restrict__ idx, uint64_t n, syk_record_t *__restrict__ dst) {
+    // 64-byte records as four 16-byte pieces: four consecutive lanes move one record
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t i = t >> 2;
+    if (i < n) reinterpret_cast<uint4 *>(dst + i)[t & 3] = reinterpret_cast<const uint4 *>(src + idx[i])[t & 3];
+}
+
+SYK_API int syk_records_sort_by_id(syk_record_t *records_dev, uint64_t n, void *stream) {
+    int rc = syk_require_device();
+    if (rc) return rc;
+    if (n < 2) return SYK_OK;
+    SYK_CHECK_ARG(records_dev, "NULL records");
+    SYK_CHECK_ARG(n < (1ull << 31), "too many records");
+    cudaStream_t s = (cudaStream_t)stream;
+    struct Scratch {
+        cudaStream_t s;
+        void *p[3] = {nullptr, nullptr, nullptr};
+        ~Scratch() {
+            for (void *x : p)
+                if (x) cudaFreeAsync(x, s);
+        }
+    } sc{s};
+    syk_pool_keep_warm();
+    // [keys | sorted keys | idx | sorted idx], the record copy, cub's temporary storage
+    SYK_CUDA(cudaMallocAsync(&sc.p[0], n * (2 * sizeof(unsigned long long) + 2 * sizeof(unsigned)), s));
+    SYK_CUDA(cudaMallocAsync(&sc.p[1], n * sizeof(syk_record_t), s));
+    unsigned long long *keys = (unsigned long long *)sc.p[0], *keys2 = keys + n;
+    unsigned *idx = (unsigned *)(keys2 + n), *idx2 = idx + n;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    k_record_keys<<<blocks, 256, 0, s>>>(records_dev, n, keys, idx);
+    size_t tmp_bytes = 0;
+    SYK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, idx, idx2, (int)n, 0, 64, s));
+    SYK_CUDA(cudaMallocAsync(&sc.p[2], tmp_bytes ? tmp_bytes : 16, s));
+    SYK_CUDA(cub::DeviceRadixSort::SortPairs(sc.p[2], tmp_bytes, keys, keys2, idx, idx2, (int)n, 0, 64, s));
+    k_record_gather<<<(unsigned)((4 * n + 255) / 256), 256, 0, s>>>(records_dev, idx2, n, (syk_record_t *)sc.p[1]);
+    SYK_CUDA(cudaGetLastError());
+    SYK_CUDA(cudaMemcpyAsync(records_dev, sc.p[1], n * sizeof(syk_record_t), cudaMemcpyDeviceToDevice, s));
     return SYK_OK;
 }

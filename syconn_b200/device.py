@@ -50,8 +50,9 @@ class IdTable:
         check(self._L.syk_table_count(self.h, _stream_ptr(stream), C.byref(n), C.byref(ovf)))
         return n.value, bool(ovf.value)
 
-    def export(self, geom_array, max_records=None, stream=None):
-        """-> int64 CUDA tensor [n, 8] (one ``syk_record_t`` per row); use ``records_numpy`` to view it."""
+    def export(self, geom_array, max_records=None, stream=None, sort=False):
+        """-> int64 CUDA tensor [n, 8] (one ``syk_record_t`` per row); use ``records_numpy`` to view it.
+        ``sort``: ascending ids (radix sort on the device)."""
         if max_records is None:
             max_records, ovf = self.count(stream)
             if ovf:
@@ -61,6 +62,8 @@ class IdTable:
         g = np.ascontiguousarray(geom_array)
         check(self._L.syk_table_export(self.h, g.ctypes.data, len(g), out.data_ptr(), int(max_records), C.byref(n),
                                        _stream_ptr(stream)))
+        if sort and n.value > 1:
+            check(self._L.syk_records_sort_by_id(out.data_ptr(), n.value, _stream_ptr(stream)))
         return out[:n.value]
 
     def merge_records(self, recs, stream=None):
@@ -198,11 +201,12 @@ def detect_seg_boundaries(arr, stream=None):
     return out
 
 
-def extract_cs_syntype(table, cs, syn, asym, sym, max_vox=None, origin=(0, 0, 0), chunk_seq=0, stream=None):
-    """syk_extract_cs_syntype on CUDA tensors (any strides, e.g. cropped views): contact-site props go to ``table``, the
-    synaptic voxel tuples are returned as an int64 tensor [n, 4] (``syk_synvox_t`` rows: id, lin, flags, pad).
-    Synchronises (the tuple count is read back; the call is repeated once when ``max_vox`` was too small -- ``table``
-    must then be cleared by the caller, so pass an empty table)."""
+def extract_cs_syntype(table, cs, syn, asym, sym, max_vox=None, origin=(0, 0, 0), chunk_seq=0, stream=None, syn_table=None):
+    """syk_extract_cs_syntype(_props) on CUDA tensors (any strides, e.g. cropped views): contact-site props go to ``table``,
+    the props of the synaptic parts to ``syn_table`` (optional), the synaptic voxel tuples are returned as an int64 tensor
+    [n, 4] (``syk_synvox_t`` rows: id, lin, flags, pad).
+    Synchronises (the tuple count is read back; the call is repeated once when ``max_vox`` was too small -- the tables
+    are cleared for the repeat, so pass empty tables)."""
     for m in (syn, asym, sym):
         assert m.dtype == torch.uint8 and tuple(m.shape) == tuple(cs.shape)
     L = _lib.load()
@@ -210,13 +214,16 @@ def extract_cs_syntype(table, cs, syn, asym, sym, max_vox=None, origin=(0, 0, 0)
     while True:
         vox = torch.empty((n_max, 4), dtype=torch.int64, device=cs.device)
         counter = torch.zeros(2, dtype=torch.int64, device=cs.device)
-        check(L.syk_extract_cs_syntype(table.h, cs.data_ptr(), _elem_bytes(cs), i64(cs.shape), i64(_strides(cs)), syn.data_ptr(),
-                                       i64(_strides(syn)), asym.data_ptr(), i64(_strides(asym)), sym.data_ptr(), i64(_strides(sym)),
-                                       i64(origin), int(chunk_seq), vox.data_ptr(), n_max, counter.data_ptr(), _stream_ptr(stream)))
+        check(L.syk_extract_cs_syntype_props(table.h, syn_table.h if syn_table is not None else None, cs.data_ptr(), _elem_bytes(cs),
+                                             i64(cs.shape), i64(_strides(cs)), syn.data_ptr(), i64(_strides(syn)), asym.data_ptr(),
+                                             i64(_strides(asym)), sym.data_ptr(), i64(_strides(sym)), i64(origin), int(chunk_seq),
+                                             vox.data_ptr(), n_max, counter.data_ptr(), _stream_ptr(stream)))
         n = int(counter[0].item())
         if n <= n_max:
             return vox[:n]
         table.clear(stream)
+        if syn_table is not None:
+            syn_table.clear(stream)
         n_max = n
 
 
@@ -229,6 +236,15 @@ def close_contacts(cs, ids, bbox, n_closings=6, cs_dilation=2, stream=None):
     assert len(ids) == len(bbox)
     check(_lib.load().syk_close_contacts(cs.data_ptr(), _elem_bytes(cs), i64(cs.shape), i64(_strides(cs)), ids.ctypes.data,
                                          bbox.ctypes.data, len(ids), int(n_closings), int(cs_dilation), _stream_ptr(stream)))
+    return cs
+
+
+def close_contacts_records(cs, records, n_closings=6, cs_dilation=2, stream=None):
+    """syk_close_contacts_records: like ``close_contacts`` with the boxes taken from DEVICE records (int64 tensor [n, 8] of a
+    table export in volume-local coordinates, sorted by id) -- no host round trip of the box list."""
+    assert records.is_cuda and records.dtype == torch.int64 and records.is_contiguous()
+    check(_lib.load().syk_close_contacts_records(cs.data_ptr(), _elem_bytes(cs), i64(cs.shape), i64(_strides(cs)), records.data_ptr(),
+                                                 records.shape[0], int(n_closings), int(cs_dilation), _stream_ptr(stream)))
     return cs
 
 

@@ -484,3 +484,44 @@ def test_detect_cs_wide_stencils_march_along_the_other_axis():
             got = dev.detect_cs(seg, st).cpu().numpy().view(np.uint64)
             want = oracle.detect_cs(seg.cpu().numpy().view(np.uint32), st)
             assert np.array_equal(got, want), (order, st)
+
+
+def test_close_contacts_from_device_records(mods, monkeypatch):
+    """syk_close_contacts_records (boxes planned on the device from a sorted table export) == the oracle's loop in ascending
+    id order; shared-memory classes, HBM path, both memory orders; sorted export == host-sorted export."""
+    import torch
+    from syconn_b200 import device as dev
+    oracle = mods["oracle"]
+    for seed, shape, pitch, st in ((1, (64, 60, 52), (14, 12, 8), (7, 7, 3)), (2, (50, 70, 90), (20, 9, 30), (5, 5, 3))):
+        seg = mods["synth"](shape, pitch=pitch, warp_amp=3, seed=seed, dtype=np.uint32)
+        cs = oracle.detect_cs(seg, st)
+        bb = oracle.find_object_properties(cs)[1]
+        order = {k: bb[k] for k in sorted(bb)}
+        for n_close, n_dil in ((3, 2), (6, 2), (0, 2), (2, 0)):
+            want = oracle.close_contact_sites(cs.copy(), order, n_close, n_dil)
+            for small in (None, "64", "0"):
+                if small is None:
+                    monkeypatch.delenv("SYK_MORPH_SMALL", raising=False)
+                else:
+                    monkeypatch.setenv("SYK_MORPH_SMALL", small)
+                    monkeypatch.setenv("SYK_MORPH_BATCH", "5000")
+                for fortran in (False, True):
+                    t = torch.from_numpy(cs.view(np.int64).copy()).cuda()
+                    if fortran:
+                        t = t.permute(2, 1, 0).contiguous().permute(2, 1, 0)
+                    table = dev.IdTable(1 << 14)
+                    dev.find_object_properties(table, t)
+                    g = dev.geoms([[0, 0, 0]], [list(t.shape)])
+                    rec = table.export(g, sort=True)
+                    host = dev.records_numpy(table.export(g))
+                    assert np.array_equal(dev.records_numpy(rec), host[np.argsort(host["id"])])
+                    dev.close_contacts_records(t, rec, n_close, n_dil)
+                    assert np.array_equal(t.cpu().numpy().view(np.uint64), want), (seed, n_close, n_dil, small, fortran)
+                    table.close()
+    monkeypatch.delenv("SYK_MORPH_SMALL", raising=False)
+    monkeypatch.delenv("SYK_MORPH_BATCH", raising=False)
+    # a bounding box outside the volume is refused
+    bad = rec.clone()
+    bad[0, 5] = 1 << 20  # bb_max words
+    with pytest.raises(Exception):
+        dev.close_contacts_records(t, bad, 1, 1)
