@@ -377,8 +377,25 @@ def get_aniso_struct(scaling):
     assert scaling[1] // scaling[0] == 1 and aniso >= 1
     centre = np.zeros((5, 5))
     centre[2, 2] = 1
-    disc = scipy.ndimage.binary_dilation(centre, iterations=int(aniso))
+    disc = centre != 0
+    for _ in range(int(aniso)):  # == binary_dilation(centre, iterations=aniso), one step at a time (see _scipy_binary_op)
+        disc = scipy.ndimage.binary_dilation(disc)
     return np.stack([centre, disc.astype(np.float64), centre], axis=2)
+
+
+def _scipy_binary_op(name, mask, n, kw):
+    """``getattr(scipy.ndimage, name)(mask, iterations=n, **kw)`` evaluated as single-iteration calls: n erosions, n
+    dilations, n erosions + n dilations (opening) or n dilations + n erosions (closing) -- scipy's own definition of
+    ``iterations``.  The literal multi-iteration call is avoided on purpose: scipy 1.18.1's iterated code path corrupts the heap
+    ("double free or corruption") when the array is smaller than the structuring element, which the per-object boxes of
+    the reference's loop often are; the golden vectors (made by the reference's literal calls) pin the equivalence."""
+    import scipy.ndimage
+    seq = {"binary_erosion": "e" * n, "binary_dilation": "d" * n, "binary_opening": "e" * n + "d" * n,
+           "binary_closing": "d" * n + "e" * n}[name]
+    m = np.asarray(mask) != 0
+    for step in seq:
+        m = (scipy.ndimage.binary_erosion if step == "e" else scipy.ndimage.binary_dilation)(m, **kw)
+    return m
 
 
 def apply_morphological_operations(vol, morph_ops, structure=None):
@@ -397,7 +414,6 @@ def apply_morphological_operations(vol, morph_ops, structure=None):
             runs.append([name, 1])
     kw = {} if structure is None else {"structure": structure}
     for name, n in runs:
-        func = getattr(scipy.ndimage, name)
         grows = ("closing" in name) or ("dilation" in name)
         shrinks = ("erosion" in name) or ("opening" in name)
         assert grows != shrinks, name
@@ -408,7 +424,7 @@ def apply_morphological_operations(vol, morph_ops, structure=None):
             if grows:
                 sub = np.pad(sub, n)
             own = (sub == ix).astype(np.int32)
-            res = func(own, iterations=n, **kw)
+            res = _scipy_binary_op(name, own, n, kw)
             if grows:
                 inner = (slice(n, -n),) * 3
                 res, own, sub = res[inner], own[inner], sub[inner]

@@ -172,7 +172,10 @@ def morph_input(case_index, density, scaling):
 
 def main_morph():
     """apply_morphological_operations / get_aniso_struct of the reference's syconn/proc/image.py (imported under a stub
-    ``syconn.proc`` package) -> morph_golden.npz"""
+    ``syconn.proc`` package) -> morph_golden.npz.  Note: with this image's scipy (1.18.1) the reference's literal
+    ``iterations=n`` calls corrupt the heap when an object's box is smaller than the 5 x 5 x 3 element (reproducible with
+    scipy alone); the golden volumes keep their foreground boxes larger than that, and the oracle evaluates the
+    iterations one at a time."""
     import logging
     proc = types.ModuleType("syconn.proc")
     proc.__path__ = []
