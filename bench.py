@@ -657,7 +657,7 @@ def e2e_host(args, chunks, rank=0, world=1):
             for f in futs:
                 f.result()
 
-    reps = max(1, min(args.steps, 3))
+    reps = max(1, min(args.steps, 5))  # median of up to five passes: host-side pass times scatter a lot on a shared box
     vox = sum(int(c[0].size) for c in host)
 
     def sync_all():
