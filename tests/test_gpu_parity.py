@@ -525,3 +525,50 @@ def test_close_contacts_from_device_records(mods, monkeypatch):
     bad[0, 5] = 1 << 20  # bb_max words
     with pytest.raises(Exception):
         dev.close_contacts_records(t, bad, 1, 1)
+
+
+def test_extract_cs_syntype_fused_syn_props(mods):
+    """syk_extract_cs_syntype_props: the synaptic props accumulated by the voxel-compaction pass itself == the second return
+    value of the oracle's extract_cs_syntype (block_processing_C.pyx:117-137); layouts, cropped views, offsets, chunk_seq."""
+    import torch
+    from syconn_b200 import device as dev
+    from syconn_b200.extraction._host import records_to_dicts
+    oracle = mods["oracle"]
+    rng = np.random.default_rng(9)
+    for shape, off in (((33, 40, 29), (1, 2, 3)), ((20, 64, 70), (100, -5, 7)), ((6, 5, 4), (0, 0, 0))):
+        cs = (mods["synth"](shape, pitch=(6, 5, 4), seed=4) % np.uint64(9)) * np.uint64(5)
+        syn = ((rng.random(shape) < 0.35) * rng.integers(1, 4, size=shape)).astype(np.uint8)
+        asym, sym = rng.integers(0, 3, size=shape).astype(np.uint8), rng.integers(0, 3, size=shape).astype(np.uint8)
+        want = oracle.extract_cs_syntype(cs, syn, asym, sym, list(off))
+
+        def shifted(props, o):  # the Cython props are block-local (the worker adds the offset when merging, :482-483)
+            rc, bb, sz = props
+            o = np.asarray(o)
+            return ({k: (np.asarray(v) + o).tolist() for k, v in rc.items()}, {k: (np.asarray(v) + o).tolist() for k, v in bb.items()}, sz)
+        want = (shifted(want[0], off), shifted(want[1], off)) + tuple(want[2:])
+        for fortran in (False, True):
+            def put(a):
+                t = torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).cuda()
+                return t.permute(2, 1, 0).contiguous().permute(2, 1, 0) if fortran else t
+            t_cs, t_syn = dev.IdTable(1 << 10), dev.IdTable(1 << 10)
+            vox = dev.extract_cs_syntype(t_cs, put(cs), put(syn), put(asym), put(sym), origin=off, chunk_seq=3, syn_table=t_syn)
+            g = dev.geoms([list(off)] * 4, [list(shape)] * 4)
+            got_cs = records_to_dicts(dev.records_numpy(t_cs.export(g)))
+            got_syn = records_to_dicts(dev.records_numpy(t_syn.export(g)))
+            assert_props_equal(tuple(got_cs), tuple(want[0]), "cs")
+            assert_props_equal(tuple(got_syn), tuple(want[1]), "syn")
+            assert int(vox.shape[0]) == sum(len(v) for v in want[4].values())
+            assert set(dev.records_numpy(t_syn.export(g))["chunk_seq"].tolist()) <= {3}
+            t_cs.close()
+            t_syn.close()
+    # a cropped view (strided) of larger volumes, as the worker passes them
+    big = (mods["synth"]((40, 44, 48), pitch=(7, 6, 5), seed=6) % np.uint64(11)) * np.uint64(3)
+    mask = (rng.random(big.shape) < 0.3).astype(np.uint8)
+    crop = (slice(6, -6),) * 3
+    want = oracle.extract_cs_syntype(np.ascontiguousarray(big[crop]), np.ascontiguousarray(mask[crop]), np.ascontiguousarray(mask[crop]),
+                                     np.ascontiguousarray(mask[crop]), [10, 20, 30])
+    tb, tm = torch.from_numpy(big.view(np.int64)).cuda(), torch.from_numpy(mask).cuda()
+    t_cs, t_syn = dev.IdTable(1 << 10), dev.IdTable(1 << 10)
+    dev.extract_cs_syntype(t_cs, tb[crop], tm[crop], tm[crop], tm[crop], origin=(10, 20, 30), syn_table=t_syn)
+    g = dev.geoms([[10, 20, 30]], [list(big[crop].shape)])
+    assert_props_equal(tuple(records_to_dicts(dev.records_numpy(t_syn.export(g)))), tuple(shifted(want[1], (10, 20, 30))), "syn crop")
