@@ -531,7 +531,10 @@ static int cs_launch_impl(const void *edges, int edge_bytes, const int64_t *edge
             k1 = s7 ? k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 7, 13, 13, false, true>
                     : s13 ? k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 13, 13, 7, false, true>
                           : k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 0, 0, 0, false, true>;
-            k2 = k_cs_fast<true, GMAX_T2, NT_T2, MINB2, 0, 0, 0, false, true>;
+            // tier 2 with the production stencil folded in as well: small supervoxels (pitch 16 x 16 x 8) run entirely in it
+            k2 = s7 ? k_cs_fast<true, GMAX_T2, NT_T2, MINB2, 7, 13, 13, false, true>
+                    : s13 ? k_cs_fast<true, GMAX_T2, NT_T2, MINB2, 13, 13, 7, false, true>
+                          : k_cs_fast<true, GMAX_T2, NT_T2, MINB2, 0, 0, 0, false, true>;
         } else if (F.vec4) {
             k1 = s7 ? k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 7, 13, 13>
                     : s13 ? k_cs_fast<true, GMAX_T1, NT_T1, MINB1, 13, 13, 7> : k_cs_fast<true, GMAX_T1, NT_T1, MINB1>;

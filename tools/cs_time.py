@@ -7,7 +7,8 @@ sys.path.insert(0, ".")
 from syconn_b200 import device as dev
 from tools.quick_bench import timeit
 S = 512
-seg = dev.synth_labels((S + 24, S + 24, S + 18), origin=(500, -12, 1015), pitch=(32, 32, 16), seed=0, dtype=torch.int32, order="F")
+PITCH = tuple(int(x) for x in os.environ.get("SYK_PITCH", "32,32,16").split(","))
+seg = dev.synth_labels((S + 24, S + 24, S + 18), origin=(500, -12, 1015), pitch=PITCH, seed=0, dtype=torch.int32, order="F")
 out = dev.detect_cs(seg)
 tmin, tmed = timeit(lambda: dev.detect_cs(seg, out=out), n=7, warm=3)
-print(f"{os.environ.get('SYK_LIB_NAME', 'libsyk.so')}: detect_cs min {tmin:.3f} ms med {tmed:.3f} ms  checksum {int(out.sum().item()) & 0xFFFFFFFF:08x}", flush=True)
+print(f"{os.environ.get('SYK_LIB_NAME', 'libsyk.so')} pitch {PITCH}: detect_cs min {tmin:.3f} ms med {tmed:.3f} ms  checksum {int(out.sum().item()) & 0xFFFFFFFF:08x}", flush=True)
