@@ -478,6 +478,13 @@ def worker_body_section(args, plan, chunks):
                     "props + map_subcell_extract_props with min_obj_vx = 10 + merge + mapping inversion; CUDA events, median of 3"}
 
 
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+    except Exception:
+        return 6650.0
+
+
 def stress_section(local, with_cpu=False):
     """BASELINE config 5 and the second workload point, measured inside the same run (device-resident, CUDA events, min
     of 3 after a warm-up): 1e7 distinct ids through find_object_properties, the stencil sweep of detect_cs, supervoxel
@@ -518,6 +525,21 @@ def stress_section(local, with_cpu=False):
             tab.close()
         del ar
         out["find_object_properties_224^3"] = props
+        # BASELINE config 2: find_object_properties on a 512^3 uint64 cube with ~1e5 ids (pitch 11), HBM roofline of the scan
+        lab = dev.synth_labels((512, 512, 512), pitch=(11, 11, 11), seed=5, order="F")
+        tab = dev.IdTable(1 << 19)
+
+        def run100k():
+            tab.clear()
+            dev.find_object_properties(tab, lab)
+        ms = timeit(run100k)
+        n, ovf = tab.count()
+        gbs = 512 ** 3 * 8 / ms / 1e6
+        out["find_object_properties_512^3_100k_ids"] = {"ms": ms, "value": 512 ** 3 / ms / 1e6, "ids": int(n),
+                                                        "ids_expected": int((torch.unique(lab) != 0).sum()), "table_overflow": bool(ovf),
+                                                        "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / _hbm_peak()}
+        tab.close()
+        del lab
         sweep = {}
         for st in ((3, 3, 3), (5, 5, 3), (7, 7, 3), (9, 9, 5), (13, 13, 7), (15, 15, 9), (17, 17, 9)):
             shape = tuple(256 + s - 1 for s in st)
