@@ -688,7 +688,8 @@ def e2e_host(args, chunks, rank=0, world=1):
             dist.barrier()
 
     def measure(fused, pool):
-        one_pass(fused, pool)
+        for _ in range(2):  # untimed: the first passes of a variant still grow the stream-ordered pool and map the pinned buffers
+            one_pass(fused, pool)
         sync_all()
         ts = []
         for _ in range(reps):
