@@ -123,3 +123,23 @@ def test_chunked_labelling_and_stitching_equals_whole_volume(chunk):
     cg, bg_g = _canon(got)
     cw, bg_w = _canon(want)
     assert np.array_equal(bg_g, bg_w) and np.array_equal(cg, cw)
+
+
+def test_label_components_degenerate_shapes_and_views():
+    from syconn_b200 import device as dev
+    rng = np.random.default_rng(8)
+    for shape in ((1, 1, 1), (1, 1, 70), (1, 33, 1), (40, 1, 1), (2, 2, 2), (3, 65, 31), (5, 4, 129)):
+        a = (rng.random(shape) < 0.6).astype(np.uint8)
+        want, n_want = scipy.ndimage.label(a)
+        for fortran in (False, True):
+            t = torch.from_numpy(a).cuda()
+            if fortran:
+                t = t.permute(2, 1, 0).contiguous().permute(2, 1, 0)
+            lab, n = dev.label_components(t)
+            assert n == n_want and np.array_equal(lab.cpu().numpy(), want), (shape, fortran)
+    # a strided view of a larger buffer (every second row, a sub-range of columns), uint16 with a threshold
+    big = torch.from_numpy(rng.integers(0, 1000, (12, 40, 60)).astype(np.int16)).cuda()
+    view = big[1:11, 2:38:2, 7:55]
+    want, n_want = scipy.ndimage.label(view.cpu().numpy() > 400)
+    lab, n = dev.label_components(view, 400)
+    assert n == n_want and np.array_equal(lab.cpu().numpy(), want)

@@ -139,3 +139,34 @@ def test_segmentation_chunk_with_morphology_and_seeds(kind):
         assert np.array_equal(markers.cpu().numpy().astype(np.uint32), markers_w), (kind, min_size)
         assert n == int(markers_w.max())
     assert torch.equal(t.cpu(), torch.from_numpy(prob))  # the probability map itself is untouched
+
+
+def test_degenerate_shapes_and_strided_views():
+    """Extents of 1, rows shorter / longer than a 32-voxel word, padding larger than the volume, non-dense views."""
+    from syconn_b200.proc import image
+    st = oracle.get_aniso_struct(np.array((10, 10, 20)))
+    rng = np.random.default_rng(21)
+    k = 0
+    for shape in ((1, 1, 1), (1, 5, 40), (7, 1, 33), (3, 3, 3), (2, 70, 5), (65, 4, 6)):
+        for ops in (["binary_closing"] * 6, ["binary_dilation", "binary_erosion"], ["binary_opening", "binary_closing"], ["binary_erosion"]):
+            k += 1
+            v = (rng.random(shape) < 0.6).astype(np.uint8)
+            want = oracle.apply_morphological_operations(v.copy(), ops, st)
+            for fortran in (False, True):
+                t = torch.from_numpy(v).cuda()
+                if fortran:
+                    t = t.permute(2, 1, 0).contiguous().permute(2, 1, 0)
+                image.apply_morphological_operations(t, ops, dict(structure=st))
+                assert np.array_equal(t.cpu().numpy(), want), (shape, ops, fortran)
+    # a view into a larger buffer: every second plane and a sub-range of rows; the rest of the buffer must stay untouched
+    big = torch.full((20, 30, 50), 7, dtype=torch.uint8, device="cuda")
+    view = big[2:18:2, 5:25, 3:47]
+    v = (rng.random(tuple(view.shape)) < 0.55).astype(np.uint8)
+    view.copy_(torch.from_numpy(v).cuda())
+    ops = ["binary_opening", "binary_closing", "binary_erosion"]
+    want = oracle.apply_morphological_operations(v.copy(), ops, st)
+    image.apply_morphological_operations(view, ops, dict(structure=st))
+    assert np.array_equal(view.cpu().numpy(), want)
+    mask = torch.ones_like(big, dtype=torch.bool)
+    mask[2:18:2, 5:25, 3:47] = False
+    assert bool((big[mask] == 7).all())
