@@ -637,7 +637,7 @@ static int cs_launch(const void *edges, int edge_bytes, const int64_t *edge_stri
 }  // namespace
 
 // extract_cs_syntype: stream compaction of the synaptic voxels (cs != 0 && syn != 0); lanes along the fastest cs axis
-__global__ void k_syn_voxels(const void *__restrict__ cs, int elem_bytes, long long n0, long long n1, long long n2,  // internal u,v,w
+__global__ void __launch_bounds__(256, 6) k_syn_voxels(const void *__restrict__ cs, int elem_bytes, long long n0, long long n1, long long n2,  // internal u,v,w
                              long long c0, long long c1, long long c2, const unsigned char *__restrict__ syn, long long s0,
                              long long s1, long long s2, const unsigned char *__restrict__ asym, long long a0, long long a1,
                              long long a2, const unsigned char *__restrict__ sym, long long y0, long long y1, long long y2,
@@ -645,61 +645,83 @@ __global__ void k_syn_voxels(const void *__restrict__ cs, int elem_bytes, long l
                              syk_synvox_t *__restrict__ out, unsigned long long max_out, unsigned long long *counter,
                              TableView syn_t, int p0, int p1, int p2,  // logical axis of the internal axes u, v, w
                              long long o0, long long o1, long long o2, unsigned chunk_seq) {
-    const long long total = n0 * n1 * n2;
     const unsigned lane = threadIdx.x & 31;
-    const long long start = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane;
-    for (long long base = start; base < total; base += (long long)gridDim.x * blockDim.x) {
-        const long long i = base + lane;
-        unsigned long long key = 0ull;
-        long long u = 0, v = 0, w = 0;
-        if (i < total) {
-            if (total < (1ll << 32)) {  // the usual chunk: 32-bit divisions (the 64-bit ones dominated this pass)
-                const unsigned iu = (unsigned)i, r = iu / (unsigned)n2;
-                w = iu - r * (unsigned)n2;
-                u = r / (unsigned)n1;
-                v = r - (unsigned)u * (unsigned)n1;
-            } else {
-                w = i % n2;
-                const long long r = i / n2;
-                v = r % n1;
-                u = r / n1;
+    const long long nrows = n0 * n1;
+    const long long wstride = ((long long)gridDim.x * blockDim.x) >> 5;  // warps in the grid
+    constexpr int ILP = 4;  // segments in flight per warp: one 256-byte request per warp and round trip starves the memory system
+    // a warp owns whole rows (u, v): the four base addresses are computed once per row, a segment costs a few additions --
+    // with the index arithmetic per 32-voxel segment the pass was instruction-bound (~150 instructions per segment)
+    for (long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrows; row += wstride) {
+      const long long u = row / n1, v = row - u * n1;
+      const long long cs_row = u * c0 + v * c1, syn_row = u * s0 + v * s1, as_row = u * a0 + v * a1, sy_row = u * y0 + v * y1;
+      const long long lin_row = u * l0 + v * l1;
+      for (long long w0 = 0; w0 < n2; w0 += ILP * 32) {
+        unsigned long long keys[ILP];
+        long long ws[ILP];
+        bool hits[ILP];
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) {
+            ws[k] = w0 + k * 32 + lane;
+            keys[k] = 0ull;
+            if (ws[k] < n2) {
+                const long long ci = cs_row + ws[k] * c2;
+                keys[k] = elem_bytes == 8 ? __ldg((const unsigned long long *)cs + ci) : (unsigned long long)__ldg((const unsigned *)cs + ci);
             }
-            const long long ci = u * c0 + v * c1 + w * c2;
-            key = elem_bytes == 8 ? __ldg((const unsigned long long *)cs + ci) : (unsigned long long)__ldg((const unsigned *)cs + ci);
         }
-        bool hit = false;
-        if (key != 0ull) hit = __ldg(syn + u * s0 + v * s1 + w * s2) != 0;
-        const unsigned m = __ballot_sync(FULL, hit);
-        if (!m) continue;
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) {
+            hits[k] = false;
+            if (keys[k] != 0ull) hits[k] = __ldg(syn + syn_row + ws[k] * s2) != 0;
+        }
+        // ONE position reservation per warp and round for all its segments: the tuple counter is a single address, and an
+        // atomic per 32-voxel segment with a hit (hundreds of thousands per chunk) serialises there
+        unsigned ms[ILP];
+        unsigned nhit = 0u;
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) {
+            ms[k] = __ballot_sync(FULL, hits[k]);
+            nhit += (unsigned)__popc(ms[k]);
+        }
+        if (nhit == 0u) continue;
         unsigned long long pos0 = 0;
-        if (lane == 0) pos0 = atomicAdd(counter, (unsigned long long)__popc(m));
+        if (lane == 0) pos0 = atomicAdd(counter, (unsigned long long)nhit);
         pos0 = __shfl_sync(FULL, pos0, 0);
-        if (hit) {
-            const unsigned long long pos = pos0 + __popc(m & ((1u << lane) - 1u));
-            if (pos < max_out) {
-                syk_synvox_t t;
-                t.id = key;
-                t.lin = (unsigned long long)(u * l0 + v * l1 + w * l2);
-                t.flags = (__ldg(asym + u * a0 + v * a1 + w * a2) == 1 ? 1ull : 0ull) | (__ldg(sym + u * y0 + v * y1 + w * y2) == 1 ? 2ull : 0ull);
-                t._pad = 0;
-                out[pos] = t;
-            }
-            if (syn_t.slots) {  // props of the synaptic part of the contact (block_processing_C.pyx:117-137), one update per id and warp
-                const unsigned peers = __match_any_sync(m, key);
-                const long long lin = u * l0 + v * l1 + w * l2;
-                long long c[3];  // logical coordinates
-                c[p0] = u, c[p1] = v, c[p2] = w;
-                // voxels per call < 2^31 (checked on the host): 32-bit warp reductions
-                const int mn0 = __reduce_min_sync(peers, (int)c[0]), mn1 = __reduce_min_sync(peers, (int)c[1]), mn2 = __reduce_min_sync(peers, (int)c[2]);
-                const int mx0 = __reduce_max_sync(peers, (int)c[0]), mx1 = __reduce_max_sync(peers, (int)c[1]), mx2 = __reduce_max_sync(peers, (int)c[2]);
-                const unsigned first = __reduce_min_sync(peers, (unsigned)lin);
-                if ((unsigned)(__ffs(peers) - 1) == lane) {
-                    const unsigned long long rep_key = ((unsigned long long)chunk_seq << 40) | (SYK_REP_MASK - (unsigned long long)first);
-                    syk_table_update(syn_t, key, (unsigned long long)__popc(peers), rep_key, (int)(mn0 + o0), (int)(mn1 + o1), (int)(mn2 + o2),
-                                     (int)(mx0 + 1 + o0), (int)(mx1 + 1 + o1), (int)(mx2 + 1 + o2));
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) {
+            const unsigned long long key = keys[k];
+            const long long w = ws[k];
+            const bool hit = hits[k];
+            const unsigned m = ms[k];
+            if (k > 0) pos0 += (unsigned long long)__popc(ms[k - 1]);
+            if (!m) continue;
+            if (hit) {
+                const unsigned long long pos = pos0 + __popc(m & ((1u << lane) - 1u));
+                if (pos < max_out) {
+                    syk_synvox_t t;
+                    t.id = key;
+                    t.lin = (unsigned long long)(lin_row + w * l2);
+                    t.flags = (__ldg(asym + as_row + w * a2) == 1 ? 1ull : 0ull) | (__ldg(sym + sy_row + w * y2) == 1 ? 2ull : 0ull);
+                    t._pad = 0;
+                    out[pos] = t;
+                }
+                if (syn_t.slots) {  // props of the synaptic part of the contact (block_processing_C.pyx:117-137), one update per id and warp
+                    const unsigned peers = __match_any_sync(m, key);
+                    const long long lin = lin_row + w * l2;
+                    long long c[3];  // logical coordinates
+                    c[p0] = u, c[p1] = v, c[p2] = w;
+                    // voxels per call < 2^31 (checked on the host): 32-bit warp reductions
+                    const int mn0 = __reduce_min_sync(peers, (int)c[0]), mn1 = __reduce_min_sync(peers, (int)c[1]), mn2 = __reduce_min_sync(peers, (int)c[2]);
+                    const int mx0 = __reduce_max_sync(peers, (int)c[0]), mx1 = __reduce_max_sync(peers, (int)c[1]), mx2 = __reduce_max_sync(peers, (int)c[2]);
+                    const unsigned first = __reduce_min_sync(peers, (unsigned)lin);
+                    if ((unsigned)(__ffs(peers) - 1) == lane) {
+                        const unsigned long long rep_key = ((unsigned long long)chunk_seq << 40) | (SYK_REP_MASK - (unsigned long long)first);
+                        syk_table_update(syn_t, key, (unsigned long long)__popc(peers), rep_key, (int)(mn0 + o0), (int)(mn1 + o1), (int)(mn2 + o2),
+                                         (int)(mx0 + 1 + o0), (int)(mx1 + 1 + o1), (int)(mx2 + 1 + o2));
+                    }
                 }
             }
         }
+      }
     }
 }
 
