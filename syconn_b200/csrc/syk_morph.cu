@@ -273,16 +273,37 @@ __global__ void __launch_bounds__(MT) k_morph_apply(MorphGeom G, const MorphBox 
 // background voxels covered by a closed mask take the id of the first such id in list order
 __global__ void __launch_bounds__(MT) k_morph_final(void *__restrict__ vol, MorphGeom G, const unsigned *__restrict__ rankvol,
                                                     const MorphBox *__restrict__ boxes) {
+    // the pass is a chain of dependent loads (vote -> label -> id of the winning box): four voxels per thread in flight
     const long long total = (long long)G.n[0] * G.n[1] * G.n[2];
-    for (long long i = (long long)blockIdx.x * MT + threadIdx.x; i < total; i += (long long)gridDim.x * MT) {
-        const unsigned r = rankvol[i];
-        if (r == NO_RANK) continue;
-        const long long w = i % G.n[2], q = i / G.n[2];
-        const long long a = (q / G.n[1]) * G.st[0] + (q % G.n[1]) * G.st[1] + w * G.st[2];
-        if (ld_label(vol, G.elem_bytes, a) != 0ull) continue;  // only background is ever written (cs_extraction_steps.py:460)
-        const unsigned long long id = boxes[r].id;
-        if (G.elem_bytes == 8) ((unsigned long long *)vol)[a] = id;
-        else ((unsigned *)vol)[a] = (unsigned)id;
+    const long long stride = (long long)gridDim.x * MT;
+    constexpr int ILP = 4;
+    for (long long i0 = (long long)blockIdx.x * MT + threadIdx.x; i0 < total; i0 += ILP * stride) {
+        unsigned r[ILP];
+        long long a[ILP];
+        unsigned long long cur[ILP], id[ILP];
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) {
+            const long long i = i0 + k * stride;
+            r[k] = i < total ? rankvol[i] : NO_RANK;
+        }
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) {
+            cur[k] = 1ull;
+            a[k] = 0;
+            if (r[k] != NO_RANK) {
+                const long long i = i0 + k * stride;
+                const long long w = i % G.n[2], q = i / G.n[2];
+                a[k] = (q / G.n[1]) * G.st[0] + (q % G.n[1]) * G.st[1] + w * G.st[2];
+                cur[k] = ld_label(vol, G.elem_bytes, a[k]);
+                id[k] = boxes[r[k]].id;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < ILP; ++k) {
+            if (r[k] == NO_RANK || cur[k] != 0ull) continue;  // only background is ever written (cs_extraction_steps.py:460)
+            if (G.elem_bytes == 8) ((unsigned long long *)vol)[a[k]] = id[k];
+            else ((unsigned *)vol)[a[k]] = (unsigned)id[k];
+        }
     }
 }
 
