@@ -24,7 +24,7 @@
 namespace {
 
 constexpr int MT = 256;              // threads per CTA
-constexpr int SMALL_WORDS = 6144;    // 2 buffers x 24 KB of shared memory, 256 threads
+constexpr int SMALL_WORDS = 6136;    // 2 buffers x 24 KB of shared memory (minus the queue word: 48 KB static limit), 256 threads
 constexpr int MID_WORDS = 3072;      // 2 buffers x 12 KB, 256 threads
 constexpr int TINY_WORDS = 1024;     // 2 buffers x 4 KB, 128 threads: the typical contact (sizes include the zero halo)
 constexpr unsigned NO_RANK = 0xFFFFFFFFu;
@@ -102,10 +102,13 @@ __device__ __forceinline__ void apply_word(const MorphGeom &G, const MorphBox &B
 template <int WORDS, int NT, bool WPR1>
 __global__ void __launch_bounds__(NT) k_morph_small(const void *__restrict__ vol, MorphGeom G, const MorphBox *__restrict__ boxes,
                                                     const unsigned *__restrict__ list, unsigned nlist, int n_close, int n_dil,
-                                                    unsigned *__restrict__ rankvol) {
+                                                    unsigned *__restrict__ rankvol, unsigned *__restrict__ queue) {
     __shared__ unsigned buf[2][WORDS];
+    __shared__ unsigned s_next;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (unsigned bi = blockIdx.x; bi < nlist; bi += gridDim.x) {
+    // boxes differ a lot in size: after its first box a CTA takes the next one from a device counter (a static round robin
+    // leaves a long tail)
+    for (unsigned bi = blockIdx.x; bi < nlist;) {
         const unsigned rank = list[bi];
         const MorphBox B = boxes[rank];
         const int eu = B.ext[0], ev = B.ext[1], ew = B.ext[2];
@@ -119,12 +122,14 @@ __global__ void __launch_bounds__(NT) k_morph_small(const void *__restrict__ vol
             u = r / ev;
             return (u + 1) * planep + (v + 1) * rowp + k;
         };
-        __syncthreads();  // the previous box is done with the buffers
+        __syncthreads();  // the previous box is done with the buffers (and everybody has read s_next)
+        if (tid == 0) s_next = gridDim.x + atomicAdd(queue, 1u);
         for (int i = tid; i < padded; i += NT) {
             buf[0][i] = 0u;
             buf[1][i] = 0u;
         }
         __syncthreads();
+        bi = s_next;
         // mask of the id: only the rows of its own bounding box can hold voxels; four words (loads) in flight per warp
         {
             const int k0 = B.ilo[2] >> 5, nk = ((B.ihi[2] + 31) >> 5) - k0;
@@ -369,12 +374,16 @@ static int run_large_boxes(void *cs_dev, const MorphGeom &G, std::vector<MorphBo
 // the six shared-memory size classes: lst[c] = device list of the cnt[c] boxes of class c
 static int run_small_boxes(void *cs_dev, const MorphGeom &G, const MorphBox *dbx, const unsigned *const lst[6], const size_t cnt[6],
                            int n_closings, int n_dilations, unsigned *rk, int sms, cudaStream_t s) {
+    Scratch d_queue;  // one box counter per class (dynamic hand-out after the first wave)
+    SYK_CUDA(d_queue.alloc(8 * sizeof(unsigned), s));
+    SYK_CUDA(cudaMemsetAsync(d_queue.p, 0, 8 * sizeof(unsigned), s));
+    unsigned *queue = (unsigned *)d_queue.p;
 #define SYK_MORPH_LAUNCH(c, WORDS, NT, WPR1, PER_SM)                                                                              \
     if (cnt[c]) {                                                                                                                \
         const unsigned long long n = cnt[c];                                                                                     \
         const unsigned long long grid = n < (unsigned long long)sms * PER_SM ? n : (unsigned long long)sms * PER_SM;             \
         k_morph_small<WORDS, NT, WPR1><<<(unsigned)grid, NT, 0, s>>>(cs_dev, G, dbx, lst[c], (unsigned)n, n_closings, n_dilations, \
-                                                                     rk);                                                        \
+                                                                     rk, queue + c);                                             \
     }
     SYK_MORPH_LAUNCH(0, TINY_WORDS, 128, true, 64)
     SYK_MORPH_LAUNCH(1, TINY_WORDS, 128, false, 64)
