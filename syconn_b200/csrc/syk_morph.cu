@@ -23,6 +23,9 @@
 
 namespace {
 
+#ifndef SYK_MORPH_BW
+#define SYK_MORPH_BW 4
+#endif
 constexpr int MT = 256;              // threads per CTA
 constexpr int SMALL_WORDS = 6136;    // 2 buffers x 24 KB of shared memory (minus the queue word: 48 KB static limit), 256 threads
 constexpr int MID_WORDS = 3072;      // 2 buffers x 12 KB, 256 threads
@@ -130,16 +133,17 @@ __global__ void __launch_bounds__(NT) k_morph_small(const void *__restrict__ vol
         }
         __syncthreads();
         bi = s_next;
-        // mask of the id: only the rows of its own bounding box can hold voxels; four words (loads) in flight per warp
+        // mask of the id: only the rows of its own bounding box can hold voxels; BW words (loads) in flight per warp
         {
+            constexpr int BW = SYK_MORPH_BW;
             const int k0 = B.ilo[2] >> 5, nk = ((B.ihi[2] + 31) >> 5) - k0;
             const int iv = B.ihi[1] - B.ilo[1];
             const int nin = (B.ihi[0] - B.ilo[0]) * iv * nk;
-            for (int i0 = warp * 4; i0 < nin; i0 += (NT / 32) * 4) {
-                bool hit[4];
-                int dst[4];
+            for (int i0 = warp * BW; i0 < nin; i0 += (NT / 32) * BW) {
+                bool hit[BW];
+                int dst[BW];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < BW; ++j) {
                     const int i = i0 + j;
                     hit[j] = false;
                     dst[j] = -1;
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(NT) k_morph_small(const void *__restrict__ vol
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < BW; ++j) {
                     const unsigned b = __ballot_sync(0xFFFFFFFFu, hit[j]);
                     if (lane == 0 && dst[j] >= 0) buf[0][dst[j]] = b;
                 }
